@@ -1,0 +1,117 @@
+/*
+ * tsta_cuda.h -- C ABI of the B200 (sm_100a) global-alignment hot path.
+ *
+ * This is the drop-in boundary for bxskdh/TSTA.  The reference has no library or FFI
+ * surface (its public interface is three executables, reference Makefile:11-32); the seam
+ * this ABI replaces is the region of each main()/control() between "sequences are in
+ * memory" and "scores / direction matrices are in memory":
+ *
+ *   tsta_psa_align / tsta_psa_plan_*   replace reference psa/psa.c:594-643
+ *       (state allocation 598-614, blockmatrix_init 219-232, the anti-diagonal tile loop
+ *        620-639 that feeds block_alignment()/row() 234-433 to the pthread pool, and
+ *        trace() 435-519).  Inputs are what readseq() (179-217) leaves in seq[0], seq[1];
+ *        outputs are `ms` (printed at 666) and the two strings trace() writes (512-515).
+ *   tsta_psa_batch                      the same seam for many independent pairs
+ *       (an extension: the reference reads record 1 only, psa/psa.c:192-193).
+ *   tsta_poa_*                          replace reference msa/c-t-simd.c:1003-1043 (control():
+ *       per-node trace allocation + the tile loop feeding block_alignment()/
+ *       block_line_alignment() 165-657).  Outputs are what node_fuse() (659-977) reads:
+ *       lastsorce of every sink and source/esource/fsource at (row, column).
+ *
+ * Plain C types only; caller-owned inputs; library-owned outputs are released with the
+ * matching *_free / *_destroy.  Every entry point returns 0 on success and a negative
+ * TSTA_E* code on failure; tsta_last_error() gives the message.  There is NO CPU fallback:
+ * without a CUDA device every compute entry point fails with TSTA_ENODEV.
+ */
+#ifndef TSTA_CUDA_H
+#define TSTA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSTA_OK        0
+#define TSTA_EINVAL   -1   /* bad argument / parameters outside the parity domain */
+#define TSTA_ENODEV   -2   /* no usable CUDA device                              */
+#define TSTA_ENOMEM   -3   /* host or device allocation failed                   */
+#define TSTA_ECUDA    -4   /* a CUDA call or kernel failed                       */
+
+/* Scoring parameters: reference globals M, X, E, O (psa/psa.c:114-117, msa/msa.c:21-24).
+ * Parity domain: O <= 0, E <= 0, X <= 0, all |.| <= 127. */
+typedef struct tsta_params {
+    int32_t M;  /* match      (-M, default  2) */
+    int32_t X;  /* mismatch   (-X, default -5) */
+    int32_t E;  /* gap extend (-E, default -2) */
+    int32_t O;  /* gap open   (-O, default -4; 0 = linear gaps) */
+} tsta_params;
+
+const char* tsta_last_error(void);
+int  tsta_device_count(void);            /* >= 0, or a negative TSTA_E* code */
+int  tsta_set_device(int device);        /* device used by the calling thread's later calls */
+const char* tsta_version(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Pairwise alignment (TSTA_psa / TSTA_psa_notrace)                                      */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct tsta_psa_result {
+    int32_t maxsorce;   /* what the reference prints: max(-100, max H over all cells) (psa.c:590,666) */
+    int32_t corner;     /* H(m-1, n-1), the global score (not printed by the reference)              */
+    int64_t alen;       /* alignment length; 0 when no traceback was requested                        */
+    char*   a;          /* ">1" row: s0 with '-' (NUL-terminated, library-owned) or NULL              */
+    char*   b;          /* ">2" row: s1 with '-' (NUL-terminated, library-owned) or NULL              */
+} tsta_psa_result;
+
+/* One pair, host buffers in, host strings out.  s0 must be the longer read (the caller
+ * applies the swap of psa/psa.c:194-199; tsta_psa_align returns TSTA_EINVAL if n < m).
+ * want_trace = 0 behaves like TSTA_psa_notrace, 1 like TSTA_psa. */
+int  tsta_psa_align(const tsta_params* p, const char* s0, int64_t n, const char* s1, int64_t m,
+                    int want_trace, tsta_psa_result* out);
+void tsta_psa_result_free(tsta_psa_result* r);
+
+/* Plan API: device-resident state that can be run repeatedly (what bench.py times).
+ *   create  -> allocates nothing big yet
+ *   upload  -> H2D copy + encoding of one pair (sizes may change between uploads)
+ *   run     -> fill (+ traceback) kernels on the plan's stream; optional CUDA-event timings
+ *   fetch   -> D2H of scores (and strings when traced)                                     */
+typedef struct tsta_psa_plan tsta_psa_plan;
+int  tsta_psa_plan_create(tsta_psa_plan** plan, int want_trace);
+int  tsta_psa_plan_upload(tsta_psa_plan* plan, const tsta_params* p,
+                          const char* s0, int64_t n, const char* s1, int64_t m);
+int  tsta_psa_plan_run(tsta_psa_plan* plan, float* fill_ms, float* trace_ms);
+int  tsta_psa_plan_fetch(tsta_psa_plan* plan, tsta_psa_result* out);
+/* Debug / parity helpers: last DP row H(m-1, 0..n-1) and the packed direction codes
+ * (one byte per cell: back | cF<<2 | cE<<3, row-major m x n). */
+int  tsta_psa_plan_lastrow(tsta_psa_plan* plan, int32_t* out_n);
+int  tsta_psa_plan_dirs(tsta_psa_plan* plan, uint8_t* out_m_by_n);
+/* Number of kernels the last run launched and the lane width it chose (for reporting). */
+int  tsta_psa_plan_info(tsta_psa_plan* plan, int* launches, int* cols_per_lane, int* bands);
+void tsta_psa_plan_destroy(tsta_psa_plan* plan);
+
+/* Many independent pairs.  seqs0/seqs1 are concatenations; off*[k], len*[k] locate pair k
+ * (len0[k] >= len1[k], caller swaps).  Outputs are arrays of npairs entries; when
+ * want_trace != 0, ops receives for pair k, at ops + ops_off[k] (capacity len0+len1), the
+ * alignment columns in order, one byte each (1 = both, 0 = gap in s1, 2 = gap in s0) and
+ * alen[k] their count.  ops/ops_off/alen may be NULL for score-only. */
+int  tsta_psa_batch(const tsta_params* p, int64_t npairs,
+                    const char* seqs0, const int64_t* off0, const int32_t* len0,
+                    const char* seqs1, const int64_t* off1, const int32_t* len1,
+                    int want_trace, int32_t* maxsorce, int32_t* corner,
+                    uint8_t* ops, const int64_t* ops_off, int32_t* alen,
+                    float* kernel_ms);
+
+/* ------------------------------------------------------------------------------------ */
+/* Measurement helpers                                                                   */
+/* ------------------------------------------------------------------------------------ */
+
+/* Dependency-free VIADDMNMX loop on every SM: measured int32 DPX lane-ops per second
+ * (the roofline denominator of SURVEY.md 8d; B200's DPX rate is not documented). */
+int  tsta_measure_dpx_peak(double* lane_ops_per_s, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSTA_CUDA_H */

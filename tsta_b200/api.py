@@ -1,0 +1,183 @@
+"""Python mirror of the C ABI in include/tsta_cuda.h (ctypes; no torch types cross it).
+
+The reference has no library API -- its interface is the TSTA_psa / TSTA_psa_notrace /
+TSTA_msa executables -- so this module mirrors those at function level for tests and
+bench.py: `psa(x, y, ...)` does what `TSTA_psa -1 x.fa -2 y.fa` does (swap so the longer
+read is first, psa/psa.c:194-199; fill; traceback) and returns the printed `maxsorce` plus
+the bytes of the `-o` file.
+
+There is no CPU fallback: if libtsta_cuda.so is missing or no CUDA device is usable every
+call raises TstaError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_build" / "libtsta_cuda.so"
+_lib = None
+
+
+class TstaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tsta error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("M", C.c_int32), ("X", C.c_int32), ("E", C.c_int32), ("O", C.c_int32)]
+
+
+class _PsaResult(C.Structure):
+    _fields_ = [("maxsorce", C.c_int32), ("corner", C.c_int32), ("alen", C.c_int64),
+                ("a", C.c_void_p), ("b", C.c_void_p)]
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TstaError(-2, f"{LIB_PATH} not built: run `python -m tsta_b200.build` (needs nvcc); "
+                            "there is no CPU fallback")
+    L = C.CDLL(str(LIB_PATH))
+    L.tsta_last_error.restype = C.c_char_p
+    L.tsta_version.restype = C.c_char_p
+    L.tsta_psa_align.argtypes = [C.POINTER(Params), C.c_char_p, C.c_int64, C.c_char_p, C.c_int64,
+                                 C.c_int, C.POINTER(_PsaResult)]
+    L.tsta_psa_result_free.argtypes = [C.POINTER(_PsaResult)]
+    L.tsta_psa_plan_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.tsta_psa_plan_upload.argtypes = [C.c_void_p, C.POINTER(Params), C.c_char_p, C.c_int64,
+                                       C.c_char_p, C.c_int64]
+    L.tsta_psa_plan_run.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.tsta_psa_plan_fetch.argtypes = [C.c_void_p, C.POINTER(_PsaResult)]
+    L.tsta_psa_plan_lastrow.argtypes = [C.c_void_p, C.c_void_p]
+    L.tsta_psa_plan_dirs.argtypes = [C.c_void_p, C.c_void_p]
+    L.tsta_psa_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tsta_psa_plan_destroy.argtypes = [C.c_void_p]
+    L.tsta_set_device.argtypes = [C.c_int]
+    L.tsta_measure_dpx_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    if hasattr(L, "tsta_psa_batch"):
+        L.tsta_psa_batch.argtypes = [
+            C.POINTER(Params), C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise TstaError(rc, load().tsta_last_error().decode())
+
+
+def device_count() -> int:
+    n = load().tsta_device_count()
+    if n < 0:
+        raise TstaError(n, load().tsta_last_error().decode())
+    return n
+
+
+def set_device(dev: int) -> None:
+    _check(load().tsta_set_device(dev))
+
+
+def order_pair(x: bytes, y: bytes):
+    """psa/psa.c:194-199: the longer read becomes s0 (columns); equal lengths keep order."""
+    return (y, x) if len(y) > len(x) else (x, y)
+
+
+@dataclass
+class PsaResult:
+    maxsorce: int
+    corner: int
+    a: bytes | None = None
+    b: bytes | None = None
+
+    def output_bytes(self) -> bytes:
+        """Bytes of the TSTA_psa -o file (psa/psa.c:512-515: no trailing newline)."""
+        return b">1\n" + self.a + b"\n>2\n" + self.b
+
+
+def _take(res: _PsaResult) -> PsaResult:
+    out = PsaResult(res.maxsorce, res.corner)
+    if res.a:
+        out.a = C.string_at(res.a, res.alen)
+        out.b = C.string_at(res.b, res.alen)
+    load().tsta_psa_result_free(C.byref(res))
+    return out
+
+
+def psa(x: bytes, y: bytes, M=2, X=-5, E=-2, O=-4, trace=True) -> PsaResult:
+    """One pair through the one-shot C entry point (host buffers in, host strings out)."""
+    s0, s1 = order_pair(x, y)
+    p = Params(M, X, E, O)
+    res = _PsaResult()
+    _check(load().tsta_psa_align(C.byref(p), s0, len(s0), s1, len(s1), int(trace), C.byref(res)))
+    return _take(res)
+
+
+class PsaPlan:
+    """Device-resident pair: upload once, run many times (what bench.py times)."""
+
+    def __init__(self, trace: bool):
+        self._h = C.c_void_p()
+        self.trace = bool(trace)
+        _check(load().tsta_psa_plan_create(C.byref(self._h), int(trace)))
+        self.n = self.m = 0
+
+    def upload(self, x: bytes, y: bytes, M=2, X=-5, E=-2, O=-4) -> None:
+        s0, s1 = order_pair(x, y)
+        self.n, self.m = len(s0), len(s1)
+        p = Params(M, X, E, O)
+        _check(load().tsta_psa_plan_upload(self._h, C.byref(p), s0, self.n, s1, self.m))
+
+    def run(self):
+        """Launch fill (+ traceback); returns (fill_ms, trace_ms) from CUDA events."""
+        f, t = C.c_float(), C.c_float()
+        _check(load().tsta_psa_plan_run(self._h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
+    def fetch(self) -> PsaResult:
+        res = _PsaResult()
+        _check(load().tsta_psa_plan_fetch(self._h, C.byref(res)))
+        return _take(res)
+
+    def lastrow(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.int32)
+        _check(load().tsta_psa_plan_lastrow(self._h, out.ctypes.data))
+        return out
+
+    def dirs(self) -> np.ndarray:
+        out = np.zeros((self.m, self.n), dtype=np.uint8)
+        _check(load().tsta_psa_plan_dirs(self._h, out.ctypes.data))
+        return out
+
+    def info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _check(load().tsta_psa_plan_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"launches": a.value, "cols_per_lane": b.value, "bands": c.value}
+
+    def close(self) -> None:
+        if self._h:
+            load().tsta_psa_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure_dpx_peak():
+    """(int32 DPX lane-ops per second, kernel ms) from the on-device microbenchmark."""
+    v, ms = C.c_double(), C.c_float()
+    _check(load().tsta_measure_dpx_peak(C.byref(v), C.byref(ms)))
+    return v.value, ms.value

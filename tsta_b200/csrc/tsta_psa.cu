@@ -1,0 +1,409 @@
+// tsta_psa.cu -- C-ABI host side of the pairwise path (include/tsta_cuda.h).
+//
+// Plays the role of the reference main() between readseq() and printf("maxsorce")
+// (psa/psa.c:588-666): state set-up (blockmatrix_init, 219-232, happens inside the fill
+// kernel), the fill, the traceback and the '-'-padded strings of trace() (467-515).
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "psa_fill.cuh"
+#include "psa_trace.cuh"
+
+namespace tsta {
+
+thread_local std::string g_last_error;
+
+int ensure_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return set_error(TSTA_ENODEV, "no CUDA device available (%s); tsta_b200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    return TSTA_OK;
+}
+
+int check_params(const tsta_params* p)
+{
+    if (!p) return set_error(TSTA_EINVAL, "params is NULL");
+    if (p->O > 0 || p->E > 0 || p->X > 0)
+        return set_error(TSTA_EINVAL, "parameters outside the parity domain: need O<=0, E<=0, X<=0 (got O=%d E=%d X=%d)",
+                         p->O, p->E, p->X);
+    const int lim = 127;
+    if (abs(p->M) > lim || abs(p->X) > lim || abs(p->E) > lim || abs(p->O) > lim)
+        return set_error(TSTA_EINVAL, "parameters outside the parity domain: |M|,|X|,|E|,|O| must be <= 127");
+    return TSTA_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// encoding: raw bytes -> small codes, per-row substitution table
+// ---------------------------------------------------------------------------------------
+struct EncodeArgs {
+    const uint8_t* s0;
+    const uint8_t* s1;
+    int n, m, n_pad;
+    uint8_t lut[256];
+    int pad_code;
+    int Ms, Xs;       // scaled match / mismatch
+    uint8_t* qcode;   // [n_pad]
+    uint8_t* rcode;   // [m]
+    uint2* rowtab;    // [m] or NULL
+};
+
+__global__ void psa_encode_kernel(const __grid_constant__ EncodeArgs a)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_pad; j += stride)
+        a.qcode[j] = j < a.n ? a.lut[a.s0[j]] : (uint8_t)a.pad_code;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.m; i += stride) {
+        const uint32_t c = a.lut[a.s1[i]];
+        a.rcode[i] = (uint8_t)c;
+        if (a.rowtab) {
+            uint32_t w[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int sc = ((uint32_t)(h * 4 + k) == c) ? a.Ms : a.Xs;
+                    v |= (uint32_t)(sc & 0xff) << (8 * k);
+                }
+                w[h] = v;
+            }
+            a.rowtab[i] = make_uint2(w[0], w[1]);
+        }
+    }
+}
+
+}  // namespace tsta
+
+using namespace tsta;
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+struct tsta_psa_plan {
+    int want_trace = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    tsta_params prm{};
+    int64_t n = 0, m = 0;
+    int n_pad = 0, nbands = 0, C = 4;
+    bool prmt = true;
+    bool uploaded = false, ran = false;
+    int launches = 0;
+    std::vector<char> h_s0, h_s1;  // host copies for string emission
+    DevBuf d_s0, d_s1, d_qcode, d_rcode, d_rowtab, d_bnd, d_ctl, d_dirs, d_ops, d_lastrow;
+    // d_ctl layout (ints): [0] ticket, [1] out_max, [2..4] trace out, [8 ..] progress[nbands]
+    int* h_small = nullptr;  // pinned, 8 ints
+};
+
+static void plan_free(tsta_psa_plan* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    p->d_s0.release(); p->d_s1.release(); p->d_qcode.release(); p->d_rcode.release();
+    p->d_rowtab.release(); p->d_bnd.release(); p->d_ctl.release(); p->d_dirs.release();
+    p->d_ops.release(); p->d_lastrow.release();
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->h_small) cudaFreeHost(p->h_small);
+    delete p;
+}
+
+template <int C, bool TRACE>
+static void launch_fill(const tsta_psa_plan* p, const PsaFillArgs& fa)
+{
+    if (p->prmt) psa_fill_kernel<C, TRACE, true><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    else psa_fill_kernel<C, TRACE, false><<<fa.nbands, 32, 0, p->stream>>>(fa);
+}
+
+extern "C" {
+
+const char* tsta_last_error(void) { return g_last_error.c_str(); }
+const char* tsta_version(void) { return "tsta_b200 0.1 (sm_100a)"; }
+
+int tsta_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(TSTA_ENODEV, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int tsta_set_device(int device)
+{
+    if (int rc = ensure_device()) return rc;
+    TSTA_CUDA_TRY(cudaSetDevice(device));
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_create(tsta_psa_plan** out, int want_trace)
+{
+    if (!out) return set_error(TSTA_EINVAL, "plan pointer is NULL");
+    *out = nullptr;
+    if (int rc = ensure_device()) return rc;
+    tsta_psa_plan* p = new (std::nothrow) tsta_psa_plan();
+    if (!p) return set_error(TSTA_ENOMEM, "out of host memory");
+    p->want_trace = want_trace ? 1 : 0;
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&p->ev[k]);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_small, 8 * sizeof(int));
+    if (e != cudaSuccess) {
+        plan_free(p);
+        return set_error(TSTA_ECUDA, "plan creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return TSTA_OK;
+}
+
+void tsta_psa_plan_destroy(tsta_psa_plan* p) { plan_free(p); }
+
+int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
+                         const char* s0, int64_t n, const char* s1, int64_t m)
+{
+    if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
+    if (int rc = check_params(prm)) return rc;
+    if (n < 0 || m < 0 || (n > 0 && !s0) || (m > 0 && !s1)) return set_error(TSTA_EINVAL, "bad sequence arguments");
+    if (n < m) return set_error(TSTA_EINVAL, "s0 must be the longer read (n=%lld < m=%lld); swap like psa.c:194-199",
+                                (long long)n, (long long)m);
+    // int32 headroom: doubled scores, worst step 2*127 per row/column
+    if ((n + m) > (int64_t)4000000) return set_error(TSTA_EINVAL, "n+m=%lld exceeds the supported 4e6", (long long)(n + m));
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    p->prm = *prm;
+    p->n = n;
+    p->m = m;
+    p->uploaded = false;
+    p->ran = false;
+    if (n == 0 || m == 0) {  // degenerate: nothing to fill (reference would not get here either)
+        p->uploaded = true;
+        p->h_s0.assign(s0, s0 + n);
+        p->h_s1.assign(s1, s1 + m);
+        return TSTA_OK;
+    }
+    const int S = p->want_trace ? 2 : 1;
+
+    // alphabet: distinct bytes of both reads -> codes 0..K-1 (comparison is raw-byte equality,
+    // psa.c:253 mm_cmpeq_epi8, so any byte-preserving relabelling is exact)
+    EncodeArgs ea{};
+    bool seen[256] = {false};
+    for (int64_t j = 0; j < n; j++) seen[(uint8_t)s0[j]] = true;
+    for (int64_t i = 0; i < m; i++) seen[(uint8_t)s1[i]] = true;
+    int K = 0;
+    for (int b = 0; b < 256; b++) if (seen[b]) ea.lut[b] = (uint8_t)K++;
+    if (K > 255) return set_error(TSTA_EINVAL, "more than 255 distinct symbols");
+    p->prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
+    ea.pad_code = p->prmt ? kPadCode : 255;
+
+    // lane strip width: narrow strips while the read is short enough that warps are scarce
+    p->C = (n <= 128 * 2368) ? 4 : 8;
+    const int band_cols = 32 * p->C;
+    p->nbands = (int)((n + band_cols - 1) / band_cols);
+    p->n_pad = p->nbands * band_cols;
+
+    if (int rc = p->d_s0.reserve((size_t)n)) return rc;
+    if (int rc = p->d_s1.reserve((size_t)m)) return rc;
+    if (int rc = p->d_qcode.reserve((size_t)p->n_pad)) return rc;
+    if (int rc = p->d_rcode.reserve((size_t)m)) return rc;
+    if (int rc = p->d_rowtab.reserve((size_t)m * sizeof(uint2))) return rc;
+    if (int rc = p->d_bnd.reserve((size_t)p->nbands * (size_t)m * sizeof(int2))) return rc;
+    if (int rc = p->d_ctl.reserve((size_t)(8 + p->nbands) * sizeof(int))) return rc;
+    if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
+    if (p->want_trace) {
+        if (int rc = p->d_dirs.reserve((size_t)m * (size_t)(p->n_pad / 2))) return rc;
+        if (int rc = p->d_ops.reserve((size_t)(n + m))) return rc;
+    }
+    p->h_s0.assign(s0, s0 + n);
+    p->h_s1.assign(s1, s1 + m);
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_s0.p, s0, (size_t)n, cudaMemcpyHostToDevice, p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_s1.p, s1, (size_t)m, cudaMemcpyHostToDevice, p->stream));
+    ea.s0 = p->d_s0.as<uint8_t>();
+    ea.s1 = p->d_s1.as<uint8_t>();
+    ea.n = (int)n; ea.m = (int)m; ea.n_pad = p->n_pad;
+    ea.Ms = S * prm->M; ea.Xs = S * prm->X;
+    ea.qcode = p->d_qcode.as<uint8_t>();
+    ea.rcode = p->d_rcode.as<uint8_t>();
+    ea.rowtab = p->prmt ? p->d_rowtab.as<uint2>() : nullptr;
+    psa_encode_kernel<<<148, 256, 0, p->stream>>>(ea);
+    TSTA_CUDA_TRY(cudaGetLastError());
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->uploaded = true;
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
+{
+    if (!p || !p->uploaded) return set_error(TSTA_EINVAL, "plan has no uploaded pair");
+    if (fill_ms) *fill_ms = 0.f;
+    if (trace_ms) *trace_ms = 0.f;
+    p->launches = 0;
+    if (p->n == 0 || p->m == 0) { p->ran = true; return TSTA_OK; }
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    int* ctl = p->d_ctl.as<int>();
+    // ticket = 0, progress = 0; out_max = INT_MIN
+    TSTA_CUDA_TRY(cudaMemsetAsync(ctl, 0, (size_t)(8 + p->nbands) * sizeof(int), p->stream));
+    p->h_small[0] = INT_MIN;
+    TSTA_CUDA_TRY(cudaMemcpyAsync(ctl + 1, p->h_small, sizeof(int), cudaMemcpyHostToDevice, p->stream));
+
+    PsaFillArgs fa{};
+    fa.qcode = p->d_qcode.as<uint8_t>();
+    fa.rowtab = p->d_rowtab.as<uint2>();
+    fa.rcode = p->d_rcode.as<uint8_t>();
+    fa.n = (int)p->n; fa.m = (int)p->m; fa.n_pad = p->n_pad; fa.nbands = p->nbands;
+    fa.M = p->prm.M; fa.X = p->prm.X; fa.E = p->prm.E; fa.O = p->prm.O;
+    fa.bnd = p->d_bnd.as<int2>();
+    fa.bnd_stride = p->m;
+    fa.progress = ctl + 8;
+    fa.ticket = reinterpret_cast<unsigned*>(ctl);
+    fa.dirs = p->d_dirs.as<uint8_t>();
+    fa.dirs_stride = p->n_pad / 2;
+    fa.out_max = ctl + 1;
+    fa.lastrow = p->d_lastrow.as<int>();
+
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+    if (p->want_trace) {
+        if (p->C == 4) launch_fill<4, true>(p, fa); else launch_fill<8, true>(p, fa);
+    } else {
+        if (p->C == 4) launch_fill<4, false>(p, fa); else launch_fill<8, false>(p, fa);
+    }
+    TSTA_CUDA_TRY(cudaGetLastError());
+    p->launches++;
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+    if (p->want_trace) {
+        PsaTraceArgs ta{};
+        ta.dirs = fa.dirs;
+        ta.dirs_stride = fa.dirs_stride;
+        ta.n = fa.n; ta.m = fa.m;
+        ta.ops = p->d_ops.as<uint8_t>();
+        ta.out = ctl + 2;
+        psa_trace_kernel<<<1, kTraceThreads, 0, p->stream>>>(ta);
+        TSTA_CUDA_TRY(cudaGetLastError());
+        p->launches++;
+    }
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    float ms = 0.f;
+    if (fill_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); *fill_ms = ms; }
+    if (trace_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); *trace_ms = ms; }
+    p->ran = true;
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_fetch(tsta_psa_plan* p, tsta_psa_result* out)
+{
+    if (!p || !out) return set_error(TSTA_EINVAL, "NULL argument");
+    if (!p->ran) return set_error(TSTA_EINVAL, "plan has not been run");
+    memset(out, 0, sizeof *out);
+    const int64_t n = p->n, m = p->m;
+    const int S = p->want_trace ? 2 : 1;
+    std::vector<uint8_t> ops;
+    int64_t nops = 0, fi = m - 1, fj = n - 1;
+    out->maxsorce = -100;  // reference seed, psa.c:110,590
+    if (n > 0 && m > 0) {
+        TSTA_CUDA_TRY(cudaSetDevice(p->device));
+        int* ctl = p->d_ctl.as<int>();
+        TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small, ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small + 7, p->d_lastrow.as<int>() + (n - 1), sizeof(int),
+                                      cudaMemcpyDeviceToHost, p->stream));
+        TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        out->maxsorce = std::max(-100, p->h_small[1] / S);
+        out->corner = p->h_small[7] / S;
+        if (p->want_trace) {
+            nops = p->h_small[2];
+            fi = p->h_small[3];
+            fj = p->h_small[4];
+            ops.resize((size_t)(n + m));
+            if (nops > 0)
+                TSTA_CUDA_TRY(cudaMemcpy(ops.data(), p->d_ops.p, (size_t)nops, cudaMemcpyDeviceToHost));
+        }
+    }
+    if (p->want_trace) {
+        ops.resize((size_t)(n + m));
+        // leftovers: rest of s0 against gaps, then rest of s1 (psa.c:497-510)
+        while (fj >= 0) { ops[(size_t)nops++] = 0; fj--; }
+        while (fi >= 0) { ops[(size_t)nops++] = 2; fi--; }
+        char* a = (char*)malloc((size_t)nops + 1);
+        char* b = (char*)malloc((size_t)nops + 1);
+        if (!a || !b) { free(a); free(b); return set_error(TSTA_ENOMEM, "out of host memory"); }
+        int64_t i = m - 1, j = n - 1, pos = nops;
+        for (int64_t k = 0; k < nops; k++) {
+            pos--;
+            const uint8_t d = ops[(size_t)k];
+            if (d == 1) { a[pos] = p->h_s0[(size_t)j--]; b[pos] = p->h_s1[(size_t)i--]; }
+            else if (d == 0) { a[pos] = p->h_s0[(size_t)j--]; b[pos] = '-'; }
+            else { a[pos] = '-'; b[pos] = p->h_s1[(size_t)i--]; }
+        }
+        a[nops] = b[nops] = '\0';
+        out->a = a; out->b = b; out->alen = nops;
+    }
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_lastrow(tsta_psa_plan* p, int32_t* out)
+{
+    if (!p || !out || !p->ran) return set_error(TSTA_EINVAL, "plan not run or NULL argument");
+    if (p->n == 0 || p->m == 0) return TSTA_OK;
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    TSTA_CUDA_TRY(cudaMemcpy(out, p->d_lastrow.p, (size_t)p->n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (p->want_trace) for (int64_t j = 0; j < p->n; j++) out[j] /= 2;
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_dirs(tsta_psa_plan* p, uint8_t* out)
+{
+    if (!p || !out || !p->ran || !p->want_trace) return set_error(TSTA_EINVAL, "plan not run with traceback");
+    if (p->n == 0 || p->m == 0) return TSTA_OK;
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    const size_t stride = (size_t)p->n_pad / 2;
+    std::vector<uint8_t> packed((size_t)p->m * stride);
+    TSTA_CUDA_TRY(cudaMemcpy(packed.data(), p->d_dirs.p, packed.size(), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < p->m; i++)
+        for (int64_t j = 0; j < p->n; j++) {
+            const uint8_t b = packed[(size_t)i * stride + (size_t)(j >> 1)];
+            out[(size_t)i * p->n + j] = (j & 1) ? (b >> 4) : (b & 15);
+        }
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_info(tsta_psa_plan* p, int* launches, int* cols_per_lane, int* bands)
+{
+    if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
+    if (launches) *launches = p->launches;
+    if (cols_per_lane) *cols_per_lane = p->C;
+    if (bands) *bands = p->nbands;
+    return TSTA_OK;
+}
+
+void tsta_psa_result_free(tsta_psa_result* r)
+{
+    if (!r) return;
+    free(r->a);
+    free(r->b);
+    r->a = r->b = nullptr;
+}
+
+int tsta_psa_align(const tsta_params* prm, const char* s0, int64_t n, const char* s1, int64_t m,
+                   int want_trace, tsta_psa_result* out)
+{
+    if (!out) return set_error(TSTA_EINVAL, "result pointer is NULL");
+    // one cached plan per (thread, trace mode): repeated calls reuse device buffers
+    thread_local tsta_psa_plan* cache[2] = {nullptr, nullptr};
+    const int k = want_trace ? 1 : 0;
+    if (!cache[k]) {
+        if (int rc = tsta_psa_plan_create(&cache[k], k)) return rc;
+    }
+    if (int rc = tsta_psa_plan_upload(cache[k], prm, s0, n, s1, m)) return rc;
+    if (int rc = tsta_psa_plan_run(cache[k], nullptr, nullptr)) return rc;
+    return tsta_psa_plan_fetch(cache[k], out);
+}
+
+}  // extern "C"
