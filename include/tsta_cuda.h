@@ -92,10 +92,12 @@ int  tsta_psa_plan_info(tsta_psa_plan* plan, int* launches, int* cols_per_lane, 
 void tsta_psa_plan_destroy(tsta_psa_plan* plan);
 
 /* Many independent pairs.  seqs0/seqs1 are concatenations; off*[k], len*[k] locate pair k
- * (len0[k] >= len1[k], caller swaps).  Outputs are arrays of npairs entries; when
- * want_trace != 0, ops receives for pair k, at ops + ops_off[k] (capacity len0+len1), the
- * alignment columns in order, one byte each (1 = both, 0 = gap in s1, 2 = gap in s0) and
- * alen[k] their count.  ops/ops_off/alen may be NULL for score-only. */
+ * (len0[k] >= len1[k], caller swaps).  Outputs are arrays of npairs entries.  When
+ * want_trace != 0, pair k owns the slot ops + ops_off[k] of capacity len0[k]+len1[k]; its
+ * alen[k] alignment columns are written, in reading order, into the LAST alen[k] bytes of
+ * that slot, one byte each (1 = both bases, 0 = s0 base against a gap, 2 = gap against an
+ * s1 base).  ops/ops_off/alen may be NULL for score-only.  kernel_ms (may be NULL) receives
+ * the CUDA-event time of the fill (+ traceback) kernels alone. */
 int  tsta_psa_batch(const tsta_params* p, int64_t npairs,
                     const char* seqs0, const int64_t* off0, const int32_t* len0,
                     const char* seqs1, const int64_t* off1, const int32_t* len1,

@@ -1,0 +1,74 @@
+"""Batched pairwise path (tsta_psa_batch): every pair must equal what the single-pair path /
+the oracle gives for that pair alone."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tsta_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mixed_pairs(count, seed, lens):
+    rnd = random.Random(seed)
+    pairs = []
+    for k in range(count):
+        la, lb = rnd.choice(lens), rnd.choice(lens)
+        x, y = synth.read_pair(la, lb, seed * 1000 + k, rnd.choice([None, 0.05, 0.15]))
+        pairs.append((x, y or b"A"))
+    return pairs
+
+
+@pytest.mark.parametrize("prm", [(2, -5, -2, -4), (2, -5, -2, 0), (5, -4, -1, -10)])
+def test_short_read_batch_vs_oracle(gpu, prm):
+    pairs = _mixed_pairs(300, 3, [1, 2, 30, 100, 127, 128, 129, 200, 250, 255, 256, 257, 300])
+    r0 = gpu.psa_batch(pairs, *prm, trace=False)
+    r1 = gpu.psa_batch(pairs, *prm, trace=True)
+    for k, (x, y) in enumerate(pairs):
+        o = ob.psa(x, y, *prm)
+        assert (r0.maxsorce[k], r0.corner[k]) == (o.maxsorce, o.corner), k
+        assert (r1.maxsorce[k], r1.corner[k]) == (o.maxsorce, o.corner), k
+        assert r1.output_bytes(k) == o.output_bytes(), k
+
+
+def test_long_pairs_in_a_batch(gpu):
+    pairs = _mixed_pairs(12, 5, [3000, 5000, 10000]) + _mixed_pairs(40, 6, [250])
+    r1 = gpu.psa_batch(pairs, trace=True)
+    r0 = gpu.psa_batch(pairs, trace=False)
+    for k, (x, y) in enumerate(pairs):
+        o = ob.psa(x, y)
+        assert (r0.maxsorce[k], r0.corner[k]) == (o.maxsorce, o.corner), k
+        assert (r1.maxsorce[k], r1.corner[k]) == (o.maxsorce, o.corner), k
+        assert r1.output_bytes(k) == o.output_bytes(), k
+
+
+def test_narrow_strip_batch_and_many_symbols(gpu):
+    rnd = random.Random(9)
+    alpha = b"ACDEFGHIKLMNPQRSTVWY"
+    pairs = [(bytes(rnd.choice(alpha) for _ in range(rnd.randint(1, 128))),
+              bytes(rnd.choice(alpha) for _ in range(rnd.randint(1, 128)))) for _ in range(100)]
+    r = gpu.psa_batch(pairs, 5, -4, -1, -10, trace=True)
+    for k, (x, y) in enumerate(pairs):
+        o = ob.psa(x, y, 5, -4, -1, -10)
+        assert (r.maxsorce[k], r.corner[k]) == (o.maxsorce, o.corner), k
+        assert r.output_bytes(k) == o.output_bytes(), k
+
+
+def test_batch_equals_single_pair_path_at_scale(gpu):
+    """20k pairs of 250 bp: spot-check against the oracle, checksum-compare score-only vs traced."""
+    n = 20000
+    a = synth.random_read(250 * n, 77)
+    pairs = []
+    for k in range(n):
+        x = a[250 * k: 250 * (k + 1)]
+        pairs.append((x, synth.mutate(x, 0.05, k) if k % 2 else synth.random_read(250, 10_000 + k)))
+    r0 = gpu.psa_batch(pairs, trace=False)
+    r1 = gpu.psa_batch(pairs, trace=True)
+    np.testing.assert_array_equal(r0.maxsorce, r1.maxsorce)
+    np.testing.assert_array_equal(r0.corner, r1.corner)
+    for k in range(0, n, 397):
+        o = ob.psa(*pairs[k])
+        assert (r0.maxsorce[k], r0.corner[k]) == (o.maxsorce, o.corner)
+        assert r1.output_bytes(k) == o.output_bytes()

@@ -109,14 +109,15 @@ def test_many_symbols_uses_generic_compare_path(gpu):
     assert r.output_bytes() == o.output_bytes() and r.maxsorce == o.maxsorce
 
 
-def test_wide_strip_variant_long_s0(gpu):
-    """n above the C=4 limit switches lanes to 8 columns; few rows keep the oracle fast."""
-    x, y = synth.read_pair(303200, 40, 42)
+@pytest.mark.parametrize("n,cols", [(160_000, 8), (303_200, 16)])
+def test_wide_strip_variants_long_s0(gpu, n, cols):
+    """Longer s0 switches lanes to 8 / 16 columns; few rows keep the oracle fast."""
+    x, y = synth.read_pair(n, 40, 42)
     o = ob.psa(x, y, want_lastrow=True)
     plan = gpu.PsaPlan(True)
     plan.upload(x, y)
     plan.run()
-    assert plan.info()["cols_per_lane"] == 8
+    assert plan.info()["cols_per_lane"] == cols
     r = plan.fetch()
     assert (r.maxsorce, r.corner) == (o.maxsorce, o.corner)
     np.testing.assert_array_equal(plan.lastrow(), o.lastrow)

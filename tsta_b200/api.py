@@ -181,3 +181,80 @@ def measure_dpx_peak():
     v, ms = C.c_double(), C.c_float()
     _check(load().tsta_measure_dpx_peak(C.byref(v), C.byref(ms)))
     return v.value, ms.value
+
+
+@dataclass
+class BatchResult:
+    maxsorce: np.ndarray            # int32 [npairs]
+    corner: np.ndarray              # int32 [npairs]
+    kernel_ms: float
+    swapped: np.ndarray             # bool [npairs]: pair k was swapped so that s0 is the longer read
+    _ops: np.ndarray | None = None
+    _ops_off: np.ndarray | None = None
+    _alen: np.ndarray | None = None
+    _pairs: list | None = None
+
+    def alignment(self, k: int):
+        """(a, b) strings of pair k exactly as TSTA_psa would write them (">1" = longer read)."""
+        s0, s1 = self._pairs[k]
+        cap = len(s0) + len(s1)
+        n = int(self._alen[k])
+        ops = self._ops[self._ops_off[k] + cap - n: self._ops_off[k] + cap]
+        A = np.full(n, ord("-"), dtype=np.uint8)
+        B = np.full(n, ord("-"), dtype=np.uint8)
+        A[ops != 2] = np.frombuffer(s0, dtype=np.uint8)
+        B[ops != 0] = np.frombuffer(s1, dtype=np.uint8)
+        return A.tobytes(), B.tobytes()
+
+    def output_bytes(self, k: int) -> bytes:
+        a, b = self.alignment(k)
+        return b">1\n" + a + b"\n>2\n" + b
+
+
+def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False) -> BatchResult:
+    """Many independent pairs through tsta_psa_batch.  `pairs` is a list of (x, y) byte strings
+    in any order; each pair is swapped like psa/psa.c:194-199."""
+    ordered = [order_pair(x, y) for x, y in pairs]
+    swapped = np.array([len(y) > len(x) for x, y in pairs], dtype=bool)
+    npairs = len(ordered)
+    len0 = np.array([len(a) for a, _ in ordered], dtype=np.int32)
+    len1 = np.array([len(b) for _, b in ordered], dtype=np.int32)
+    off0 = np.zeros(npairs, dtype=np.int64)
+    off1 = np.zeros(npairs, dtype=np.int64)
+    if npairs:
+        off0[1:] = np.cumsum(len0[:-1], dtype=np.int64)
+        off1[1:] = np.cumsum(len1[:-1], dtype=np.int64)
+    seqs0 = b"".join(a for a, _ in ordered) or b"\0"
+    seqs1 = b"".join(b for _, b in ordered) or b"\0"
+    return psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M, X, E, O, trace,
+                            pairs=ordered, swapped=swapped)
+
+
+def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4, trace=False,
+                     pairs=None, swapped=None) -> BatchResult:
+    """Array form of tsta_psa_batch (what bench.py uses; no per-pair Python objects)."""
+    npairs = len(len0)
+    ms = np.zeros(npairs, dtype=np.int32)
+    corner = np.zeros(npairs, dtype=np.int32)
+    p = Params(M, X, E, O)
+    kms = C.c_float()
+    ops = ops_off = alen = None
+    if trace:
+        cap = len0.astype(np.int64) + len1.astype(np.int64)
+        ops_off = np.zeros(npairs, dtype=np.int64)
+        if npairs:
+            ops_off[1:] = np.cumsum(cap[:-1])
+        ops = np.zeros(max(int(cap.sum()), 1), dtype=np.uint8)
+        alen = np.zeros(npairs, dtype=np.int32)
+    b0 = seqs0 if isinstance(seqs0, bytes) else seqs0.ctypes.data
+    b1 = seqs1 if isinstance(seqs1, bytes) else seqs1.ctypes.data
+    _check(load().tsta_psa_batch(
+        C.byref(p), npairs,
+        C.cast(b0, C.c_void_p), off0.ctypes.data, len0.ctypes.data,
+        C.cast(b1, C.c_void_p), off1.ctypes.data, len1.ctypes.data,
+        int(trace), ms.ctypes.data, corner.ctypes.data,
+        ops.ctypes.data if trace else None, ops_off.ctypes.data if trace else None,
+        alen.ctypes.data if trace else None, C.byref(kms)))
+    return BatchResult(ms, corner, kms.value,
+                       swapped if swapped is not None else np.zeros(npairs, dtype=bool),
+                       ops, ops_off, alen, pairs)

@@ -1,28 +1,34 @@
-// psa_fill.cuh -- the pairwise score-matrix fill for ONE long pair on sm_100a.
+// psa_fill.cuh -- the pairwise score-matrix fill on sm_100a (one long pair, or a batch).
 //
 // Replaces the tile wavefront of the reference (psa/psa.c:620-639 scheduling
 // block_alignment()/row() psa/psa.c:234-433 onto a pthread pool).
 //
 // Decomposition
 //   * the n columns (s0, the longer read) are cut into BANDS of 32*C columns; one warp
-//     owns one band for the whole sweep over the m rows (s1);
+//     sweeps one band over all m rows (s1);
 //   * inside a warp, lane k owns C consecutive columns (H(i-1,.) and Eg(i,.) live in
 //     registers) and is SKEWED one row behind lane k-1: at step t lane k computes row
 //     t-k.  The right edge (H, F) of a lane's strip travels to lane k+1 with
-//     __shfl_up_sync -- this is the anti-diagonal wavefront at register granularity;
-//   * band b hands its right boundary column to band b+1 through a global (L2-resident)
-//     array in chunks of 32 rows, published with a release store on a per-band progress
-//     counter and consumed with an acquire load.  Bands take their index from an atomic
-//     ticket, so a waiting band only ever waits for a band that started earlier --
-//     forward progress does not depend on the grid fitting on the chip.  CUDA streams +
-//     these counters replace threadPoolAdd() and the busy-wait barrier of psa.c:638.
+//     __shfl_up_sync -- the anti-diagonal wavefront at register granularity;
+//   * PIPE mode (one long pair): every band is its own warp.  Band b hands its right
+//     boundary column to band b+1 through a global (L2-resident) array in chunks of 32
+//     rows, published with a release store on a per-band progress counter and consumed
+//     after an acquire.  Bands take their index from an atomic ticket, so a waiting band
+//     only ever waits for a band that started earlier -- forward progress does not depend
+//     on the grid fitting on the chip.  CUDA streams + these counters replace
+//     threadPoolAdd() and the busy-wait barrier of psa.c:638;
+//   * sequential mode (batches of independent pairs): one warp walks the bands of its
+//     pair one after the other, the boundary column parked in a per-warp scratch column.
 //
 // Arithmetic: absolute int32 Gotoh recurrences (exactly what the reference's int8
 // difference encoding computes inside its parameter domain):
 //      Eg(i,j) = max(Eg(i-1,j)+E, H(i-1,j)+O+E)     Fg(i,j) = max(Fg(i,j-1)+E, H(i,j-1)+O+E)
 //      H(i,j)  = max(H(i-1,j-1)+sub, Eg, Fg)        maxsorce = max over cells of H
-// with DPX instructions (__viaddmax_s32 -> VIADDMNMX, __vimax3_s32 -> VIMNMX3) and the
-// substitution score fetched with one PRMT from a per-row 8-entry int8 table.
+// with DPX instructions (__viaddmax_s32 -> VIADDMNMX, __vimax3_s32 -> VIMNMX3).  Because
+// O <= 0, H+O+E inside the F recurrence can be replaced by max(h,Eg)+O+E, which does not
+// depend on F: the serial chain along a row is ONE VIADDMNMX per cell.  The substitution
+// score comes from one PRMT on a per-row 8-entry int8 table (alphabets of <= 7 symbols) or
+// a compare/select (any alphabet).
 //
 // Traceback variant (TRACE): every score is carried DOUBLED and the spare low bit of the
 // E/F gap states holds "this gap state was opened, not extended" (the reference's
@@ -39,115 +45,150 @@
 namespace tsta {
 
 constexpr int kPadCode = 7;      // PRMT mode: column code that never matches a row
-constexpr int kChunkRows = 32;   // rows per inter-band hand-off chunk
+constexpr int kChunkRows = 32;   // rows per hand-off chunk
 constexpr int kRing = 64;        // shared-memory ring depth in rows (>= 32 skew + 32 chunk)
 
-struct PsaFillArgs {
-    const uint8_t* qcode;   // [n_pad] column (s0) codes, pad columns = kPadCode / 255
-    const uint2* rowtab;    // [m] PRMT mode: 8 x int8 substitution scores of row i (scaled)
-    const uint8_t* rcode;   // [m] generic mode: row (s1) codes
-    int n, m, n_pad, nbands;
-    int M, X, E, O;         // unscaled
-    int2* bnd;              // [nbands][bnd_stride] right boundary (H|cF, F) of every band
-    long long bnd_stride;
-    int* progress;          // [nbands] rows published by each band
-    unsigned* ticket;       // band index dispenser
-    uint8_t* dirs;          // TRACE: [m][dirs_stride] packed 4-bit codes
-    long long dirs_stride;  // bytes per row (= n_pad / 2)
-    int* out_max;           // atomicMax target (scaled units)
-    int* lastrow;           // [n_pad] H(m-1, j) (scaled units)
+// Scoring + alphabet, shared by every kernel of the pairwise path.
+struct PsaScoring {
+    int M, X, E, O;        // unscaled
+    uint8_t lut[256];      // raw byte -> code 0..6 (PRMT mode only)
 };
 
-template <int C, bool TRACE, bool PRMT>
-__global__ void __launch_bounds__(32) psa_fill_kernel(const PsaFillArgs a)
+// Per-warp shared-memory workspace.
+template <int C, bool TRACE>
+struct __align__(16) PsaWarpSmem {
+    uint8_t dir[TRACE ? kRing * (32 * C / 2) : 16];  // ring of packed direction rows
+    uint2 rowring[kRing];   // per-row substitution table (PRMT) / raw row byte in .x (generic)
+    int2 in[kChunkRows];    // left boundary (H|cF, F) of the current chunk
+    int2 out[kRing];        // right boundary produced by lane 31
+};
+
+// Everything one band sweep needs.
+struct PsaBand {
+    const uint8_t* s0;      // raw columns of this pair
+    const uint8_t* s1;      // raw rows of this pair
+    int n, m;
+    int band, nbands;
+    const int2* bnd_in;     // [m] left boundary column (band > 0)
+    int2* bnd_out;          // [m] right boundary column (written when band+1 < nbands)
+    const int* wait_flag;   // PIPE: progress counter of band-1
+    int* post_flag;         // PIPE: progress counter of this band
+    uint8_t* dirs;          // TRACE: [m][dirs_stride] packed codes of this pair
+    long long dirs_stride;
+    int* lastrow;           // H(m-1, j) goes to lastrow[j - lastrow_col0] (scaled units), or NULL
+    int lastrow_col0;
+};
+
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Fills the 256-entry byte -> substitution-table map (PRMT mode).
+__device__ __forceinline__ void psa_build_tab(uint2* tab, const PsaScoring& sc, int S, int tid, int nthreads)
+{
+    const int Ms = S * sc.M, Xs = S * sc.X;
+    for (int b = tid; b < 256; b += nthreads) {
+        const uint32_t c = sc.lut[b];
+        uint32_t w[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int s = ((uint32_t)(h * 4 + k) == c) ? Ms : Xs;
+                v |= (uint32_t)(s & 0xff) << (8 * k);
+            }
+            w[h] = v;
+        }
+        tab[b] = make_uint2(w[0], w[1]);
+    }
+}
+
+// One band of one pair.  Returns the lane-local running maximum (scaled units).
+template <int C, bool TRACE, bool PRMT, bool PIPE>
+__device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring& sc, const uint2* tab,
+                                              PsaWarpSmem<C, TRACE>& sm, const int lane)
 {
     constexpr int S = TRACE ? 2 : 1;                    // score scale
     constexpr int kDirBytesPerLane = C / 2;             // 4 bits per cell
     constexpr int kDirRowBytes = 32 * kDirBytesPerLane; // bytes of one band row
-    static_assert(C == 4 || C == 8, "lane strip width");
+    constexpr int kWords = (C + 7) / 8;
+    static_assert(C == 4 || C == 8 || C == 16, "lane strip width");
 
-    __shared__ int2 s_in[kChunkRows];
-    __shared__ int2 s_out[kRing];
-    __shared__ __align__(16) uint8_t s_dir[TRACE ? kRing * kDirRowBytes : 16];
-
-    const int lane = threadIdx.x;
-    int band = 0;
-    if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
-    band = __shfl_sync(kFullMask, band, 0);
-
-    const int m = a.m;
-    const int Es = S * a.E;
-    const int OEs = S * (a.O + a.E) + (TRACE ? 1 : 0);  // TRACE: 2(O+E)+1, the "opened" form
-    const int Ms = S * a.M, Xs = S * a.X;
-    const int j0 = (band * 32 + lane) * C;
+    const int m = b.m;
+    const int Es = S * sc.E;
+    const int OEs = S * (sc.O + sc.E) + (TRACE ? 1 : 0);  // TRACE: 2(O+E)+1, the "opened" form
+    const int Ms = S * sc.M, Xs = S * sc.X;
+    const int j0 = (b.band * 32 + lane) * C;
 
     // ---- per-lane column state -----------------------------------------------------------
     int Hup[C];          // H(i-1, j0+c)
     int Eg[C];           // Eg(i, j0+c)   (TRACE: doubled, bit0 = opened)
-    uint32_t sel[C];     // PRMT selector (PRMT) or column code (generic)
+    uint32_t sel[C];     // PRMT selector (PRMT) or raw column byte / 256 for pad (generic)
     int cEf[C];          // TRACE: cE(i, j0+c) as 0/8
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int j = j0 + c;
-        const uint32_t code = a.qcode[j];
-        sel[c] = PRMT ? (code * 0x1111u | 0x8880u) : code;
-        const int hb = a.O + (j + 1) * a.E;             // H(-1, j)        psa.c:226
+        if (PRMT) {
+            const uint32_t code = j < b.n ? sc.lut[b.s0[j]] : (uint32_t)kPadCode;
+            sel[c] = code * 0x1111u | 0x8880u;
+        } else {
+            sel[c] = j < b.n ? (uint32_t)b.s0[j] : 256u;
+        }
+        const int hb = sc.O + (j + 1) * sc.E;             // H(-1, j)        psa.c:226
         Hup[c] = S * hb;
-        Eg[c] = S * (hb + a.O + a.E) + (TRACE ? 1 : 0); // Eg(0, j), opened psa.c:222-224
+        Eg[c] = S * (hb + sc.O + sc.E) + (TRACE ? 1 : 0); // Eg(0, j), opened psa.c:222-224
         cEf[c] = 0;
     }
-    int diag = S * (j0 == 0 ? 0 : a.O + j0 * a.E);      // H(i-1, j0-1)
+    int diag = S * (j0 == 0 ? 0 : sc.O + j0 * sc.E);      // H(i-1, j0-1)
     int ms = INT_MIN;
-    int Hout = 0, Fout = 0;                              // right edge of the previous step
+    int Hout = 0, Fout = 0;                                // right edge of the previous step
 
-    const int2* bnd_in = a.bnd + (long long)(band - 1) * a.bnd_stride;
-    int2* bnd_out = a.bnd + (long long)band * a.bnd_stride;
     const int nchunks = (m + 31 + kChunkRows - 1) / kChunkRows;
-
-    // software-pipelined per-row substitution table: every lane starts at row 0
-    uint2 Tnext = make_uint2(0, 0);
-    uint32_t rnext = 0;
-    if (m > 0) {
-        if (PRMT) Tnext = __ldg(&a.rowtab[0]);
-        else rnext = __ldg(&a.rcode[0]);
-    }
+    const bool export_right = (b.band + 1 < b.nbands) && b.bnd_out != nullptr;
 
     for (int ch = 0; ch < nchunks; ch++) {
         const int t0 = ch * kChunkRows;
-        if (band > 0 && t0 < m) {
-            const int need = min(m, t0 + kChunkRows);
-            if (lane == 0) {
-                while (ld_acquire_gpu(a.progress + band - 1) < need) __nanosleep(64);
-            }
-            __syncwarp();
+        // ---- stage this chunk's rows: substitution tables and the left boundary -----------
+        __syncwarp();
+        if (t0 < m) {
             const int row = t0 + lane;
-            if (row < m) s_in[lane] = __ldcg(bnd_in + row);
-            __syncwarp();
+            if (row < m) {
+                const uint32_t raw = b.s1[row];
+                sm.rowring[row & (kRing - 1)] = PRMT ? tab[raw] : make_uint2(raw, 0u);
+            }
+            if (b.band > 0) {
+                if (PIPE) {
+                    const int need = min(m, t0 + kChunkRows);
+                    if (lane == 0) {
+                        while (ld_relaxed_gpu(b.wait_flag) < need) __nanosleep(32);
+                        __threadfence();  // acquire: order the boundary loads after the flag
+                    }
+                    __syncwarp();
+                }
+                if (row < m) sm.in[lane] = __ldcg(b.bnd_in + row);
+            } else if (row < m) {
+                const int hb = sc.O + (row + 1) * sc.E;   // H(i, -1)   psa.c:228-231; Fg(i,0) opened
+                sm.in[lane] = make_int2(S * hb, S * (hb + sc.O + sc.E) + (TRACE ? 1 : 0));
+            }
         }
+        __syncwarp();
 
-#pragma unroll 1
+#pragma unroll 2
         for (int s = 0; s < kChunkRows; s++) {
             const int i = t0 + s - lane;
             int Hin = __shfl_up_sync(kFullMask, Hout, 1);
             int Fin = __shfl_up_sync(kFullMask, Fout, 1);
             if (lane == 0) {
-                if (band > 0) {
-                    const int2 v = s_in[s];
-                    Hin = v.x;
-                    Fin = v.y;
-                } else {
-                    const int hb = a.O + (i + 1) * a.E;                // H(i, -1)     psa.c:228-231
-                    Hin = S * hb;
-                    Fin = S * (hb + a.O + a.E) + (TRACE ? 1 : 0);      // Fg(i, 0), opened
-                }
+                const int2 v = sm.in[s];
+                Hin = v.x;
+                Fin = v.y;
             }
-            if (i >= 0 && i < m) {
-                const uint2 T = Tnext;
-                const uint32_t rc = rnext;
-                if (i + 1 < m) {
-                    if (PRMT) Tnext = __ldg(&a.rowtab[i + 1]);
-                    else rnext = __ldg(&a.rcode[i + 1]);
-                }
+            if ((unsigned)i < (unsigned)m) {
+                const uint2 T = sm.rowring[i & (kRing - 1)];
                 int cFv = 0;
                 if (TRACE) {
                     cFv = (Hin & 1) << 2;
@@ -156,26 +197,30 @@ __global__ void __launch_bounds__(32) psa_fill_kernel(const PsaFillArgs a)
                 int D = diag;
                 diag = Hin;
                 int F = Fin;
-                uint32_t word = 0;
+                uint32_t word[kWords];
+#pragma unroll
+                for (int k = 0; k < kWords; k++) word[k] = 0;
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    const int sub = PRMT ? prmt(T.x, T.y, sel[c]) : (sel[c] == rc ? Ms : Xs);
-                    const int hs = D + sub;
-                    D = Hup[c];
+                    const int sub = PRMT ? prmt(T.x, T.y, sel[c]) : (sel[c] == T.x ? Ms : Xs);
                     if (!TRACE) {
-                        const int H = __vimax3_s32(hs, Eg[c], F);
-                        const int t = H + OEs;
-                        F = __viaddmax_s32(F, Es, t);
-                        Eg[c] = __viaddmax_s32(Eg[c], Es, t);
+                        const int hE = __viaddmax_s32(D, sub, Eg[c]);   // max(h, Eg)
+                        D = Hup[c];
+                        const int g = hE + OEs;                         // independent of F
+                        const int H = max(hE, F);
+                        F = __viaddmax_s32(F, Es, g);                   // the only serial op per cell
+                        Eg[c] = __viaddmax_s32(Eg[c], Es, H + OEs);
                         Hup[c] = H;
                     } else {
+                        const int hs = D + sub;
+                        D = Hup[c];
                         const int Ec = Eg[c] & ~1;
                         const int Fc = F & ~1;
                         const int H = __vimax3_s32(hs, Ec, Fc);
                         int code = (H == Fc) ? 0 : 2;
                         code = (H == hs) ? 1 : code;
                         code |= cFv | cEf[c];
-                        word |= (uint32_t)code << (4 * c);
+                        word[c / 8] |= (uint32_t)code << (4 * (c & 7));
                         const int Tp = H + OEs;                        // 2(H+O+E)+1
                         cFv = (F + Es >= Tp) ? 4 : 0;                  // cF of column j+1
                         cEf[c] = (Eg[c] + Es >= Tp) ? 8 : 0;           // cE of row i+1
@@ -191,11 +236,12 @@ __global__ void __launch_bounds__(32) psa_fill_kernel(const PsaFillArgs a)
                 for (int c = 0; c < C; c += 2) ms = __vimax3_s32(ms, Hup[c], Hup[c + 1]);
                 Hout = Hup[C - 1] | (TRACE ? (cFv >> 2) : 0);
                 Fout = F;
-                if (lane == 31) s_out[i & (kRing - 1)] = make_int2(Hout, Fout);
+                if (lane == 31) sm.out[i & (kRing - 1)] = make_int2(Hout, Fout);
                 if (TRACE) {
-                    uint8_t* dst = s_dir + (i & (kRing - 1)) * kDirRowBytes + lane * kDirBytesPerLane;
-                    if (C == 8) *reinterpret_cast<uint32_t*>(dst) = word;
-                    else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word;
+                    uint8_t* dst = sm.dir + (i & (kRing - 1)) * kDirRowBytes + lane * kDirBytesPerLane;
+                    if (C == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(word[0], word[kWords - 1]);
+                    else if (C == 8) *reinterpret_cast<uint32_t*>(dst) = word[0];
+                    else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word[0];
                 }
             }
         }
@@ -205,38 +251,154 @@ __global__ void __launch_bounds__(32) psa_fill_kernel(const PsaFillArgs a)
         const int hi = min(m, t0 + 1);
         const int lo = ch == 0 ? 0 : min(m, t0 - kChunkRows + 1);
         if (hi > lo) {
-            if (band + 1 < a.nbands) {
+            if (export_right) {
                 const int row = lo + lane;
-                if (row < hi) bnd_out[row] = s_out[row & (kRing - 1)];
+                if (row < hi) b.bnd_out[row] = sm.out[row & (kRing - 1)];
             }
             if (TRACE) {
-                // 16-byte units: C per row; lane handles units lane, lane+32, ...
+                // 16-byte units: kDirRowBytes/16 per row; lane handles units lane, lane+32, ...
                 constexpr int kUnitsPerRow = kDirRowBytes / 16;
                 const int units = (hi - lo) * kUnitsPerRow;
                 for (int u = lane; u < units; u += 32) {
                     const int row = lo + u / kUnitsPerRow;
                     const int part = u % kUnitsPerRow;
                     const uint4 v = *reinterpret_cast<const uint4*>(
-                        s_dir + (row & (kRing - 1)) * kDirRowBytes + part * 16);
+                        sm.dir + (row & (kRing - 1)) * kDirRowBytes + part * 16);
                     uint4* dst = reinterpret_cast<uint4*>(
-                        a.dirs + (long long)row * a.dirs_stride + (long long)band * kDirRowBytes + part * 16);
+                        b.dirs + (long long)row * b.dirs_stride + (long long)b.band * kDirRowBytes + part * 16);
                     __stcs(dst, v);
                 }
             }
-            __syncwarp();
-            if (lane == 0 && band + 1 < a.nbands) {
-                __threadfence();
-                st_release_gpu(a.progress + band, hi);
+            if (PIPE && export_right) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(b.post_flag, hi);
+                }
             }
         }
     }
 
     // after the sweep Hup[] holds the last DP row
+    if (b.lastrow) {
 #pragma unroll
-    for (int c = 0; c < C; c++) a.lastrow[j0 + c] = Hup[c];
+        for (int c = 0; c < C; c++) b.lastrow[j0 - b.lastrow_col0 + c] = Hup[c];
+    }
+    return ms;
+}
 
+// ---------------------------------------------------------------------------------------
+// one long pair: one warp (= one CTA) per band, pipelined through global flags
+// ---------------------------------------------------------------------------------------
+struct PsaPairArgs {
+    PsaScoring sc;
+    const uint8_t* s0;
+    const uint8_t* s1;
+    int n, m, nbands;
+    int2* bnd;              // [nbands][bnd_stride]
+    long long bnd_stride;
+    int* progress;          // [nbands]
+    unsigned* ticket;
+    uint8_t* dirs;
+    long long dirs_stride;
+    int* out_max;           // atomicMax target (scaled units)
+    int* lastrow;           // [n_pad]
+};
+
+template <int C, bool TRACE, bool PRMT>
+__global__ void __launch_bounds__(32) psa_pair_kernel(const __grid_constant__ PsaPairArgs a)
+{
+    __shared__ PsaWarpSmem<C, TRACE> sm;
+    __shared__ uint2 tab[PRMT ? 256 : 1];
+    const int lane = threadIdx.x;
+    int band = 0;
+    if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
+    band = __shfl_sync(kFullMask, band, 0);
+    if (PRMT) psa_build_tab(tab, a.sc, TRACE ? 2 : 1, lane, 32);
+    __syncwarp();
+
+    PsaBand b;
+    b.s0 = a.s0; b.s1 = a.s1; b.n = a.n; b.m = a.m;
+    b.band = band; b.nbands = a.nbands;
+    b.bnd_in = a.bnd + (long long)(band - 1) * a.bnd_stride;
+    b.bnd_out = a.bnd + (long long)band * a.bnd_stride;
+    b.wait_flag = a.progress + band - 1;
+    b.post_flag = a.progress + band;
+    b.dirs = a.dirs; b.dirs_stride = a.dirs_stride;
+    b.lastrow = a.lastrow; b.lastrow_col0 = 0;
+    int ms = psa_sweep_band<C, TRACE, PRMT, true>(b, a.sc, tab, sm, lane);
     ms = warp_max(ms);
-    if (lane == 0 && ms != INT_MIN) atomicMax(a.out_max, ms);
+    if (lane == 0) atomicMax(a.out_max, ms);
+}
+
+// ---------------------------------------------------------------------------------------
+// a batch of independent pairs: persistent warps, each takes whole pairs from a ticket and
+// walks that pair's bands sequentially (no inter-warp dependency at all)
+// ---------------------------------------------------------------------------------------
+struct PsaBatchArgs {
+    PsaScoring sc;
+    const uint8_t* seqs0;
+    const uint8_t* seqs1;
+    const long long* off0;  // [npairs]
+    const long long* off1;
+    const int* len0;        // [npairs] (len0 >= len1)
+    const int* len1;
+    long long npairs;
+    int2* scratch;          // [total warps][scratch_stride] boundary column parking
+    long long scratch_stride;
+    unsigned long long* ticket;
+    uint8_t* dirs;          // TRACE: packed codes of all pairs
+    const long long* dirs_off;  // [npairs] byte offset of pair k's matrix
+    int* lastrow;           // [total warps][32*C] last-band last row, for the corner read
+    int* maxsorce;          // [npairs] unscaled, seeded with -100
+    int* corner;            // [npairs] unscaled
+};
+
+template <int C, bool TRACE, bool PRMT, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) psa_batch_kernel(const __grid_constant__ PsaBatchArgs a)
+{
+    constexpr int S = TRACE ? 2 : 1;
+    __shared__ PsaWarpSmem<C, TRACE> sm[WARPS];
+    __shared__ uint2 tab[PRMT ? 256 : 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (PRMT) psa_build_tab(tab, a.sc, S, threadIdx.x, 32 * WARPS);
+    __syncthreads();
+    const long long gw = (long long)blockIdx.x * WARPS + w;
+    int2* scratch = a.scratch + gw * a.scratch_stride;
+    int* lastrow = a.lastrow + gw * (32 * C);
+
+    while (true) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(a.ticket, 1ull);
+        k = __shfl_sync(kFullMask, k, 0);
+        if (k >= (unsigned long long)a.npairs) break;
+        const int n = a.len0[k], m = a.len1[k];
+        const int nbands = (n + 32 * C - 1) / (32 * C);
+        PsaBand b;
+        b.s0 = a.seqs0 + a.off0[k]; b.s1 = a.seqs1 + a.off1[k];
+        b.n = n; b.m = m; b.nbands = nbands;
+        b.bnd_in = scratch; b.bnd_out = scratch;   // in place: a row is read >= 31 steps before it is rewritten
+        b.wait_flag = nullptr; b.post_flag = nullptr;
+        b.dirs = TRACE ? a.dirs + a.dirs_off[k] : nullptr;
+        b.dirs_stride = (long long)nbands * (32 * C / 2);
+        b.lastrow_col0 = (nbands - 1) * 32 * C;
+        int ms = INT_MIN;
+        if (m > 0) {
+            for (int band = 0; band < nbands; band++) {
+                b.band = band;
+                b.lastrow = (band == nbands - 1) ? lastrow : nullptr;
+                ms = max(ms, psa_sweep_band<C, TRACE, PRMT, false>(b, a.sc, tab, sm[w], lane));
+            }
+        }
+        ms = warp_max(ms);
+        __syncwarp();
+        if (lane == 0) {
+            const bool real = n > 0 && m > 0;
+            a.maxsorce[k] = real ? max(-100, ms / S) : -100;   // seed: psa.c:110,590
+            a.corner[k] = real ? __ldcg(lastrow + (n - 1) - b.lastrow_col0) / S : 0;
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace tsta

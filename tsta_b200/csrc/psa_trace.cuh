@@ -27,7 +27,7 @@ struct PsaTraceArgs {
     int* out;                // out[0] = number of moves written, out[1] = final i, out[2] = final j
 };
 
-__global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const PsaTraceArgs a)
+static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const PsaTraceArgs a)
 {
     __shared__ __align__(16) uint8_t tile[kTraceRows * kTraceBytes];
     __shared__ int s_i, s_j, s_forced, s_nops;
@@ -81,6 +81,50 @@ __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const PsaTrace
         a.out[1] = s_i;
         a.out[2] = s_j;
     }
+}
+
+}  // namespace tsta
+
+namespace tsta {
+
+// Batch traceback: one thread per pair, straight from global memory (millions of
+// independent walks hide each other's latency).  The walk runs from the end of the
+// alignment to its start, so moves are written from the END of pair k's slot
+// (ops + ops_off[k], capacity len0+len1) backwards, INCLUDING the leftover moves of
+// psa.c:497-510: the alignment ends up in reading order in the last alen[k] bytes.
+struct PsaBatchTraceArgs {
+    const uint8_t* dirs;
+    const long long* dirs_off;   // [npairs]
+    const int* len0;
+    const int* len1;
+    long long npairs;
+    int cols_per_band;           // 32*C of the fill that produced dirs
+    uint8_t* ops;
+    const long long* ops_off;
+    int* alen;
+};
+
+static __global__ void __launch_bounds__(128) psa_batch_trace_kernel(const PsaBatchTraceArgs a)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.npairs) return;
+    const int n = a.len0[k], m = a.len1[k];
+    const long long stride = (long long)((n + a.cols_per_band - 1) / a.cols_per_band) * (a.cols_per_band / 2);
+    const uint8_t* d = a.dirs + a.dirs_off[k];
+    uint8_t* ops = a.ops + a.ops_off[k] + (n + m - 1);   // written backwards
+    int i = m - 1, j = n - 1, forced = -1, nops = 0;
+    while (i >= 0 && j >= 0) {
+        const uint8_t byte = __ldcs(d + (long long)i * stride + (j >> 1));
+        const int c = (j & 1) ? (byte >> 4) : (byte & 15);
+        const int mv = forced >= 0 ? forced : (c & 3);
+        ops[-(nops++)] = (uint8_t)mv;
+        if (mv == 1) { i--; j--; forced = -1; }
+        else if (mv == 0) { forced = (c & 4) ? 0 : -1; j--; }
+        else { forced = (c & 8) ? 2 : -1; i--; }
+    }
+    while (j >= 0) { ops[-(nops++)] = 0; j--; }
+    while (i >= 0) { ops[-(nops++)] = 2; i--; }
+    a.alen[k] = nops;
 }
 
 }  // namespace tsta

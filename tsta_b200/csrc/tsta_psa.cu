@@ -40,43 +40,47 @@ int check_params(const tsta_params* p)
 }
 
 // ---------------------------------------------------------------------------------------
-// encoding: raw bytes -> small codes, per-row substitution table
+// alphabet: which byte values occur (device-side, so batches of 1e6 reads cost microseconds)
 // ---------------------------------------------------------------------------------------
-struct EncodeArgs {
-    const uint8_t* s0;
-    const uint8_t* s1;
-    int n, m, n_pad;
-    uint8_t lut[256];
-    int pad_code;
-    int Ms, Xs;       // scaled match / mismatch
-    uint8_t* qcode;   // [n_pad]
-    uint8_t* rcode;   // [m]
-    uint2* rowtab;    // [m] or NULL
-};
-
-__global__ void psa_encode_kernel(const __grid_constant__ EncodeArgs a)
+__global__ void __launch_bounds__(256) byte_presence_kernel(const uint8_t* p, long long nbytes, unsigned* present)
 {
-    const int stride = gridDim.x * blockDim.x;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_pad; j += stride)
-        a.qcode[j] = j < a.n ? a.lut[a.s0[j]] : (uint8_t)a.pad_code;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.m; i += stride) {
-        const uint32_t c = a.lut[a.s1[i]];
-        a.rcode[i] = (uint8_t)c;
-        if (a.rowtab) {
-            uint32_t w[2];
+    __shared__ unsigned s_present[8];
+    if (threadIdx.x < 8) s_present[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
+        const unsigned b = p[i];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int sc = ((uint32_t)(h * 4 + k) == c) ? a.Ms : a.Xs;
-                    v |= (uint32_t)(sc & 0xff) << (8 * k);
-                }
-                w[h] = v;
-            }
-            a.rowtab[i] = make_uint2(w[0], w[1]);
-        }
+        for (int k = 0; k < 8; k++) loc[k] |= ((b >> 5) == (unsigned)k) ? (1u << (b & 31)) : 0u;
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned v = loc[k];
+        for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(kFullMask, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicOr(&s_present[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_present[threadIdx.x]) atomicOr(&present[threadIdx.x], s_present[threadIdx.x]);
+}
+
+// Builds the byte -> code LUT from the presence bitmap; returns the number of symbols.
+int build_lut(const unsigned present[8], uint8_t lut[256])
+{
+    int K = 0;
+    for (int b = 0; b < 256; b++) {
+        lut[b] = 0;
+        if (present[b >> 5] & (1u << (b & 31))) lut[b] = (uint8_t)std::min(K++, 255);
+    }
+    return K;
+}
+
+// Host wrapper so other translation units can use the kernel without -rdc.
+// `present` points at 8 zero-initialised unsigned words in device memory.
+cudaError_t launch_byte_presence(const uint8_t* p, long long nbytes, unsigned* present, int blocks, cudaStream_t st)
+{
+    if (nbytes > 0) byte_presence_kernel<<<blocks, 256, 0, st>>>(p, nbytes, present);
+    return cudaGetLastError();
 }
 
 }  // namespace tsta
@@ -84,32 +88,34 @@ __global__ void psa_encode_kernel(const __grid_constant__ EncodeArgs a)
 using namespace tsta;
 
 // ---------------------------------------------------------------------------------------
-// plan
+// plan: one long pair, device resident
 // ---------------------------------------------------------------------------------------
 struct tsta_psa_plan {
     int want_trace = 0;
     int device = 0;
+    int sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    tsta_params prm{};
+    PsaScoring sc{};
     int64_t n = 0, m = 0;
     int n_pad = 0, nbands = 0, C = 4;
     bool prmt = true;
     bool uploaded = false, ran = false;
     int launches = 0;
     std::vector<char> h_s0, h_s1;  // host copies for string emission
-    DevBuf d_s0, d_s1, d_qcode, d_rcode, d_rowtab, d_bnd, d_ctl, d_dirs, d_ops, d_lastrow;
-    // d_ctl layout (ints): [0] ticket, [1] out_max, [2..4] trace out, [8 ..] progress[nbands]
-    int* h_small = nullptr;  // pinned, 8 ints
+    DevBuf d_s0, d_s1, d_bnd, d_ctl, d_dirs, d_ops, d_lastrow;
+    // d_ctl layout (ints): [0] ticket, [1] out_max, [2..4] trace out, [8..15] presence,
+    //                      [16 ..] progress[nbands]
+    int* h_small = nullptr;  // pinned, 16 ints
 };
+constexpr int kCtlProgress = 16;
 
 static void plan_free(tsta_psa_plan* p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    p->d_s0.release(); p->d_s1.release(); p->d_qcode.release(); p->d_rcode.release();
-    p->d_rowtab.release(); p->d_bnd.release(); p->d_ctl.release(); p->d_dirs.release();
-    p->d_ops.release(); p->d_lastrow.release();
+    p->d_s0.release(); p->d_s1.release(); p->d_bnd.release(); p->d_ctl.release();
+    p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release();
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -117,16 +123,27 @@ static void plan_free(tsta_psa_plan* p)
 }
 
 template <int C, bool TRACE>
-static void launch_fill(const tsta_psa_plan* p, const PsaFillArgs& fa)
+static void launch_pair(const tsta_psa_plan* p, const PsaPairArgs& fa)
 {
-    if (p->prmt) psa_fill_kernel<C, TRACE, true><<<fa.nbands, 32, 0, p->stream>>>(fa);
-    else psa_fill_kernel<C, TRACE, false><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    if (p->prmt) psa_pair_kernel<C, TRACE, true><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    else psa_pair_kernel<C, TRACE, false><<<fa.nbands, 32, 0, p->stream>>>(fa);
+}
+
+// Lane strip width for one long pair: the pipeline runs at the speed of its slowest band,
+// so prefer at most one band (warp) per SM sub-partition (4 per SM) and widen the strips
+// when the read is long enough to need more.
+static int choose_strip(int64_t n, int sms)
+{
+    const int64_t slots = (int64_t)sms * 4;
+    if (n <= 32 * 4 * slots) return 4;
+    if (n <= 32 * 8 * slots) return 8;
+    return 16;
 }
 
 extern "C" {
 
 const char* tsta_last_error(void) { return g_last_error.c_str(); }
-const char* tsta_version(void) { return "tsta_b200 0.1 (sm_100a)"; }
+const char* tsta_version(void) { return "tsta_b200 0.2 (sm_100a)"; }
 
 int tsta_device_count(void)
 {
@@ -155,9 +172,10 @@ int tsta_psa_plan_create(tsta_psa_plan** out, int want_trace)
     if (!p) return set_error(TSTA_ENOMEM, "out of host memory");
     p->want_trace = want_trace ? 1 : 0;
     cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreate(&p->ev[k]);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_small, 8 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_small, 16 * sizeof(int));
     if (e != cudaSuccess) {
         plan_free(p);
         return set_error(TSTA_ECUDA, "plan creation failed: %s", cudaGetErrorString(e));
@@ -179,63 +197,44 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     // int32 headroom: doubled scores, worst step 2*127 per row/column
     if ((n + m) > (int64_t)4000000) return set_error(TSTA_EINVAL, "n+m=%lld exceeds the supported 4e6", (long long)(n + m));
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
-    p->prm = *prm;
+    p->sc.M = prm->M; p->sc.X = prm->X; p->sc.E = prm->E; p->sc.O = prm->O;
     p->n = n;
     p->m = m;
     p->uploaded = false;
     p->ran = false;
-    if (n == 0 || m == 0) {  // degenerate: nothing to fill (reference would not get here either)
+    p->h_s0.assign(s0, s0 + n);
+    p->h_s1.assign(s1, s1 + m);
+    if (n == 0 || m == 0) {  // degenerate: nothing to fill
         p->uploaded = true;
-        p->h_s0.assign(s0, s0 + n);
-        p->h_s1.assign(s1, s1 + m);
         return TSTA_OK;
     }
     const int S = p->want_trace ? 2 : 1;
-
-    // alphabet: distinct bytes of both reads -> codes 0..K-1 (comparison is raw-byte equality,
-    // psa.c:253 mm_cmpeq_epi8, so any byte-preserving relabelling is exact)
-    EncodeArgs ea{};
-    bool seen[256] = {false};
-    for (int64_t j = 0; j < n; j++) seen[(uint8_t)s0[j]] = true;
-    for (int64_t i = 0; i < m; i++) seen[(uint8_t)s1[i]] = true;
-    int K = 0;
-    for (int b = 0; b < 256; b++) if (seen[b]) ea.lut[b] = (uint8_t)K++;
-    if (K > 255) return set_error(TSTA_EINVAL, "more than 255 distinct symbols");
-    p->prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
-    ea.pad_code = p->prmt ? kPadCode : 255;
-
-    // lane strip width: narrow strips while the read is short enough that warps are scarce
-    p->C = (n <= 128 * 2368) ? 4 : 8;
+    p->C = choose_strip(n, p->sms);
     const int band_cols = 32 * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
     p->n_pad = p->nbands * band_cols;
 
     if (int rc = p->d_s0.reserve((size_t)n)) return rc;
     if (int rc = p->d_s1.reserve((size_t)m)) return rc;
-    if (int rc = p->d_qcode.reserve((size_t)p->n_pad)) return rc;
-    if (int rc = p->d_rcode.reserve((size_t)m)) return rc;
-    if (int rc = p->d_rowtab.reserve((size_t)m * sizeof(uint2))) return rc;
     if (int rc = p->d_bnd.reserve((size_t)p->nbands * (size_t)m * sizeof(int2))) return rc;
-    if (int rc = p->d_ctl.reserve((size_t)(8 + p->nbands) * sizeof(int))) return rc;
+    if (int rc = p->d_ctl.reserve((size_t)(kCtlProgress + p->nbands) * sizeof(int))) return rc;
     if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
     if (p->want_trace) {
         if (int rc = p->d_dirs.reserve((size_t)m * (size_t)(p->n_pad / 2))) return rc;
         if (int rc = p->d_ops.reserve((size_t)(n + m))) return rc;
     }
-    p->h_s0.assign(s0, s0 + n);
-    p->h_s1.assign(s1, s1 + m);
+    int* ctl = p->d_ctl.as<int>();
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_s0.p, s0, (size_t)n, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_s1.p, s1, (size_t)m, cudaMemcpyHostToDevice, p->stream));
-    ea.s0 = p->d_s0.as<uint8_t>();
-    ea.s1 = p->d_s1.as<uint8_t>();
-    ea.n = (int)n; ea.m = (int)m; ea.n_pad = p->n_pad;
-    ea.Ms = S * prm->M; ea.Xs = S * prm->X;
-    ea.qcode = p->d_qcode.as<uint8_t>();
-    ea.rcode = p->d_rcode.as<uint8_t>();
-    ea.rowtab = p->prmt ? p->d_rowtab.as<uint2>() : nullptr;
-    psa_encode_kernel<<<148, 256, 0, p->stream>>>(ea);
-    TSTA_CUDA_TRY(cudaGetLastError());
+    // alphabet: distinct bytes of both reads -> codes 0..K-1 (comparison is raw-byte equality,
+    // psa.c:253 mm_cmpeq_epi8, so any relabelling that keeps bytes distinct is exact)
+    TSTA_CUDA_TRY(cudaMemsetAsync(ctl + 8, 0, 8 * sizeof(int), p->stream));
+    TSTA_CUDA_TRY(launch_byte_presence(p->d_s0.as<uint8_t>(), n, reinterpret_cast<unsigned*>(ctl + 8), p->sms, p->stream));
+    TSTA_CUDA_TRY(launch_byte_presence(p->d_s1.as<uint8_t>(), m, reinterpret_cast<unsigned*>(ctl + 8), p->sms, p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small + 8, ctl + 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    const int K = build_lut(reinterpret_cast<unsigned*>(p->h_small + 8), p->sc.lut);
+    p->prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
     p->uploaded = true;
     return TSTA_OK;
 }
@@ -250,19 +249,19 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     int* ctl = p->d_ctl.as<int>();
     // ticket = 0, progress = 0; out_max = INT_MIN
-    TSTA_CUDA_TRY(cudaMemsetAsync(ctl, 0, (size_t)(8 + p->nbands) * sizeof(int), p->stream));
+    TSTA_CUDA_TRY(cudaMemsetAsync(ctl, 0, 8 * sizeof(int), p->stream));
+    TSTA_CUDA_TRY(cudaMemsetAsync(ctl + kCtlProgress, 0, (size_t)p->nbands * sizeof(int), p->stream));
     p->h_small[0] = INT_MIN;
     TSTA_CUDA_TRY(cudaMemcpyAsync(ctl + 1, p->h_small, sizeof(int), cudaMemcpyHostToDevice, p->stream));
 
-    PsaFillArgs fa{};
-    fa.qcode = p->d_qcode.as<uint8_t>();
-    fa.rowtab = p->d_rowtab.as<uint2>();
-    fa.rcode = p->d_rcode.as<uint8_t>();
-    fa.n = (int)p->n; fa.m = (int)p->m; fa.n_pad = p->n_pad; fa.nbands = p->nbands;
-    fa.M = p->prm.M; fa.X = p->prm.X; fa.E = p->prm.E; fa.O = p->prm.O;
+    PsaPairArgs fa{};
+    fa.sc = p->sc;
+    fa.s0 = p->d_s0.as<uint8_t>();
+    fa.s1 = p->d_s1.as<uint8_t>();
+    fa.n = (int)p->n; fa.m = (int)p->m; fa.nbands = p->nbands;
     fa.bnd = p->d_bnd.as<int2>();
     fa.bnd_stride = p->m;
-    fa.progress = ctl + 8;
+    fa.progress = ctl + kCtlProgress;
     fa.ticket = reinterpret_cast<unsigned*>(ctl);
     fa.dirs = p->d_dirs.as<uint8_t>();
     fa.dirs_stride = p->n_pad / 2;
@@ -271,9 +270,13 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
 
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     if (p->want_trace) {
-        if (p->C == 4) launch_fill<4, true>(p, fa); else launch_fill<8, true>(p, fa);
+        if (p->C == 4) launch_pair<4, true>(p, fa);
+        else if (p->C == 8) launch_pair<8, true>(p, fa);
+        else launch_pair<16, true>(p, fa);
     } else {
-        if (p->C == 4) launch_fill<4, false>(p, fa); else launch_fill<8, false>(p, fa);
+        if (p->C == 4) launch_pair<4, false>(p, fa);
+        else if (p->C == 8) launch_pair<8, false>(p, fa);
+        else launch_pair<16, false>(p, fa);
     }
     TSTA_CUDA_TRY(cudaGetLastError());
     p->launches++;

@@ -1,0 +1,232 @@
+// tsta_psa_batch.cu -- many independent pairs in one call (include/tsta_cuda.h: tsta_psa_batch).
+//
+// The reference aligns one pair per process (psa/psa.c:192-193 reads record 1 only); this
+// entry point is the batch front-end BASELINE.json's config 4 needs.  Per pair it computes
+// exactly what tsta_psa_align computes; pairs are independent, so persistent warps pull
+// whole pairs from a ticket and there is no inter-warp dependency.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "psa_fill.cuh"
+#include "psa_trace.cuh"
+
+namespace tsta {
+int check_params(const tsta_params* p);
+cudaError_t launch_byte_presence(const uint8_t* p, long long nbytes, unsigned* present, int blocks, cudaStream_t st);
+int build_lut(const unsigned present[8], uint8_t lut[256]);
+
+template <int C, bool TRACE, int WARPS>
+static void launch_batch(bool prmt, int blocks, cudaStream_t st, const PsaBatchArgs& a)
+{
+    if (prmt) psa_batch_kernel<C, TRACE, true, WARPS><<<blocks, 32 * WARPS, 0, st>>>(a);
+    else psa_batch_kernel<C, TRACE, false, WARPS><<<blocks, 32 * WARPS, 0, st>>>(a);
+}
+}  // namespace tsta
+
+using namespace tsta;
+
+namespace {
+struct Guard {  // frees everything on every exit path
+    std::vector<void*> dev;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Guard()
+    {
+        for (void* p : dev) cudaFree(p);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+    }
+    template <class T> int alloc(T** out, size_t count)
+    {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(TSTA_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        }
+        dev.push_back(p);
+        *out = static_cast<T*>(p);
+        return TSTA_OK;
+    }
+};
+constexpr int kBatchWarps = 4;
+}  // namespace
+
+extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
+                              const char* seqs0, const int64_t* off0, const int32_t* len0,
+                              const char* seqs1, const int64_t* off1, const int32_t* len1,
+                              int want_trace, int32_t* maxsorce, int32_t* corner,
+                              uint8_t* ops, const int64_t* ops_off, int32_t* alen,
+                              float* kernel_ms)
+{
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (int rc = check_params(prm)) return rc;
+    if (npairs < 0 || !maxsorce || !corner) return set_error(TSTA_EINVAL, "bad batch arguments");
+    if (npairs == 0) return TSTA_OK;
+    if (!seqs0 || !seqs1 || !off0 || !off1 || !len0 || !len1) return set_error(TSTA_EINVAL, "NULL batch input");
+    if (want_trace && (!ops || !ops_off || !alen)) return set_error(TSTA_EINVAL, "traceback requested without ops/ops_off/alen");
+    if (int rc = ensure_device()) return rc;
+
+    int64_t tot0 = 0, tot1 = 0, max0 = 0, max1 = 0, ops_total = 0;
+    for (int64_t k = 0; k < npairs; k++) {
+        if (len0[k] < len1[k] || len1[k] < 0 || off0[k] < 0 || off1[k] < 0)
+            return set_error(TSTA_EINVAL, "pair %lld: need len0 >= len1 >= 0 (the caller swaps, psa.c:194-199)", (long long)k);
+        if ((int64_t)len0[k] + len1[k] > 4000000) return set_error(TSTA_EINVAL, "pair %lld too long", (long long)k);
+        tot0 = std::max<int64_t>(tot0, off0[k] + len0[k]);
+        tot1 = std::max<int64_t>(tot1, off1[k] + len1[k]);
+        max0 = std::max<int64_t>(max0, len0[k]);
+        max1 = std::max<int64_t>(max1, len1[k]);
+        if (want_trace) ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
+    }
+    const int S = want_trace ? 2 : 1;
+    const int C = (max0 <= 128) ? 4 : 8;
+    const int band_cols = 32 * C;
+
+    int dev = 0, sms = 0;
+    TSTA_CUDA_TRY(cudaGetDevice(&dev));
+    TSTA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    Guard g;
+    TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+    TSTA_CUDA_TRY(cudaEventCreate(&g.e0));
+    TSTA_CUDA_TRY(cudaEventCreate(&g.e1));
+
+    uint8_t *d_s0, *d_s1;
+    long long *d_off0, *d_off1;
+    int *d_len0, *d_len1, *d_ms, *d_corner, *d_ctl;
+    if (int rc = g.alloc(&d_s0, (size_t)tot0)) return rc;
+    if (int rc = g.alloc(&d_s1, (size_t)tot1)) return rc;
+    if (int rc = g.alloc(&d_off0, (size_t)npairs)) return rc;
+    if (int rc = g.alloc(&d_off1, (size_t)npairs)) return rc;
+    if (int rc = g.alloc(&d_len0, (size_t)npairs)) return rc;
+    if (int rc = g.alloc(&d_len1, (size_t)npairs)) return rc;
+    if (int rc = g.alloc(&d_ms, (size_t)npairs)) return rc;
+    if (int rc = g.alloc(&d_corner, (size_t)npairs)) return rc;
+    if (int rc = g.alloc(&d_ctl, 16)) return rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0, seqs0, (size_t)tot0, cudaMemcpyHostToDevice, g.st));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1, seqs1, (size_t)tot1, cudaMemcpyHostToDevice, g.st));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_off0, off0, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1, off1, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0, len0, (size_t)npairs * 4, cudaMemcpyHostToDevice, g.st));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_len1, len1, (size_t)npairs * 4, cudaMemcpyHostToDevice, g.st));
+
+    // alphabet over the whole batch
+    TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 16 * sizeof(int), g.st));
+    TSTA_CUDA_TRY(launch_byte_presence(d_s0, tot0, reinterpret_cast<unsigned*>(d_ctl + 8), sms * 4, g.st));
+    TSTA_CUDA_TRY(launch_byte_presence(d_s1, tot1, reinterpret_cast<unsigned*>(d_ctl + 8), sms * 4, g.st));
+    unsigned present[8];
+    TSTA_CUDA_TRY(cudaMemcpyAsync(present, d_ctl + 8, sizeof present, cudaMemcpyDeviceToHost, g.st));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
+
+    PsaBatchArgs a{};
+    a.sc.M = prm->M; a.sc.X = prm->X; a.sc.E = prm->E; a.sc.O = prm->O;
+    const int K = build_lut(present, a.sc.lut);
+    const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
+
+    // persistent grid: ~24 warps per SM (register-limited), never more warps than pairs
+    int blocks = sms * 6;
+    blocks = (int)std::min<int64_t>(blocks, (npairs + kBatchWarps - 1) / kBatchWarps);
+    const long long nwarps = (long long)blocks * kBatchWarps;
+    int2* d_scratch;
+    int* d_lastrow;
+    if (int rc = g.alloc(&d_scratch, (size_t)nwarps * (size_t)std::max<int64_t>(max1, 1))) return rc;
+    if (int rc = g.alloc(&d_lastrow, (size_t)nwarps * band_cols)) return rc;
+
+    a.seqs0 = d_s0; a.seqs1 = d_s1;
+    a.off0 = d_off0; a.off1 = d_off1; a.len0 = d_len0; a.len1 = d_len1;
+    a.scratch = d_scratch; a.scratch_stride = std::max<int64_t>(max1, 1);
+    a.ticket = reinterpret_cast<unsigned long long*>(d_ctl);
+    a.lastrow = d_lastrow;
+
+    // traceback: direction matrices are large (len1 * ceil(len0/band)*band/2 bytes per pair),
+    // so pairs go through in slices that fit a fixed HBM budget
+    std::vector<long long> dirs_off;
+    uint8_t* d_dirs = nullptr;
+    long long* d_dirs_off = nullptr;
+    uint8_t* d_ops = nullptr;
+    long long* d_ops_off = nullptr;
+    int* d_alen = nullptr;
+    size_t dirs_budget = 0;
+    if (want_trace) {
+        size_t free_b = 0, total_b = 0;
+        TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        if (int rc = g.alloc(&d_ops, (size_t)ops_total)) return rc;
+        if (int rc = g.alloc(&d_ops_off, (size_t)npairs)) return rc;
+        if (int rc = g.alloc(&d_alen, (size_t)npairs)) return rc;
+        if (int rc = g.alloc(&d_dirs_off, (size_t)npairs)) return rc;
+        TSTA_CUDA_TRY(cudaMemcpyAsync(d_ops_off, ops_off, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
+        dirs_off.resize((size_t)npairs);
+        TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        dirs_budget = std::min<size_t>(free_b / 2, (size_t)48 << 30);
+    }
+    auto dirs_bytes = [&](int64_t k) -> size_t {
+        const size_t nb = (size_t)((len0[k] + band_cols - 1) / band_cols);
+        return (size_t)len1[k] * nb * (size_t)(band_cols / 2);
+    };
+
+    float total_ms = 0.f;
+    int64_t k0 = 0;
+    while (k0 < npairs) {
+        int64_t k1 = npairs;
+        size_t slice_bytes = 0;
+        if (want_trace) {
+            k1 = k0;
+            while (k1 < npairs) {
+                const size_t b = (dirs_bytes(k1) + 255) & ~(size_t)255;
+                if (k1 > k0 && slice_bytes + b > dirs_budget) break;
+                dirs_off[(size_t)k1] = (long long)slice_bytes;
+                slice_bytes += b;
+                k1++;
+            }
+            uint8_t* slice = nullptr;
+            cudaError_t e = cudaMalloc((void**)&slice, std::max<size_t>(slice_bytes, 256));
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(TSTA_ENOMEM, "direction matrices: cudaMalloc(%zu) failed", slice_bytes);
+            }
+            d_dirs = slice;
+            TSTA_CUDA_TRY(cudaMemcpyAsync(d_dirs_off + k0, dirs_off.data() + k0, (size_t)(k1 - k0) * 8,
+                                          cudaMemcpyHostToDevice, g.st));
+        }
+        a.off0 = d_off0 + k0; a.off1 = d_off1 + k0; a.len0 = d_len0 + k0; a.len1 = d_len1 + k0;
+        a.npairs = k1 - k0;
+        a.dirs = d_dirs; a.dirs_off = want_trace ? d_dirs_off + k0 : nullptr;
+        a.maxsorce = d_ms + k0; a.corner = d_corner + k0;
+        TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 8, g.st));
+        TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
+        if (want_trace) {
+            if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
+            else launch_batch<8, true, kBatchWarps>(prmt, blocks, g.st, a);
+            PsaBatchTraceArgs t{};
+            t.dirs = d_dirs; t.dirs_off = d_dirs_off + k0;
+            t.len0 = d_len0 + k0; t.len1 = d_len1 + k0; t.npairs = k1 - k0;
+            t.cols_per_band = band_cols;
+            t.ops = d_ops; t.ops_off = d_ops_off + k0; t.alen = d_alen + k0;
+            psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
+        } else {
+            if (C == 4) launch_batch<4, false, kBatchWarps>(prmt, blocks, g.st, a);
+            else launch_batch<8, false, kBatchWarps>(prmt, blocks, g.st, a);
+        }
+        cudaError_t le = cudaGetLastError();
+        TSTA_CUDA_TRY(cudaEventRecord(g.e1, g.st));
+        cudaError_t se = cudaStreamSynchronize(g.st);
+        if (want_trace && d_dirs) { cudaFree(d_dirs); d_dirs = nullptr; }
+        TSTA_CUDA_TRY(le);
+        TSTA_CUDA_TRY(se);
+        float ms = 0.f;
+        TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, g.e0, g.e1));
+        total_ms += ms;
+        k0 = k1;
+    }
+    TSTA_CUDA_TRY(cudaMemcpyAsync(maxsorce, d_ms, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(corner, d_corner, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
+    if (want_trace) {
+        TSTA_CUDA_TRY(cudaMemcpyAsync(alen, d_alen, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(ops, d_ops, (size_t)ops_total, cudaMemcpyDeviceToHost, g.st));
+    }
+    TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
+    if (kernel_ms) *kernel_ms = total_ms;
+    return TSTA_OK;
+}
