@@ -109,7 +109,7 @@ def test_many_symbols_uses_generic_compare_path(gpu):
     assert r.output_bytes() == o.output_bytes() and r.maxsorce == o.maxsorce
 
 
-@pytest.mark.parametrize("n,cols", [(160_000, 8), (303_200, 16)])
+@pytest.mark.parametrize("n,cols", [(120_000, 8), (303_200, 16)])
 def test_wide_strip_variants_long_s0(gpu, n, cols):
     """Longer s0 switches lanes to 8 / 16 columns; few rows keep the oracle fast."""
     x, y = synth.read_pair(n, 40, 42)

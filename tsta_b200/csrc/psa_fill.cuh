@@ -11,12 +11,13 @@
 //     t-k.  The right edge (H, F) of a lane's strip travels to lane k+1 with
 //     __shfl_up_sync -- the anti-diagonal wavefront at register granularity;
 //   * PIPE mode (one long pair): every band is its own warp.  Band b hands its right
-//     boundary column to band b+1 through a global (L2-resident) array in chunks of 32
-//     rows, published with a release store on a per-band progress counter and consumed
-//     after an acquire.  Bands take their index from an atomic ticket, so a waiting band
-//     only ever waits for a band that started earlier -- forward progress does not depend
-//     on the grid fitting on the chip.  CUDA streams + these counters replace
-//     threadPoolAdd() and the busy-wait barrier of psa.c:638;
+//     boundary column to band b+1 through a global (L2-resident) array, one 64-bit element
+//     per row that carries its own validity tag (data + epoch in a single store), so the
+//     hand-off needs no fence and no separate flag; the consumer prefetches a chunk ahead.
+//     Bands take their index from an atomic ticket, so a waiting band only ever waits for a
+//     band that started earlier -- forward progress does not depend on the grid fitting on
+//     the chip.  CUDA streams + these tags replace threadPoolAdd() and the busy-wait
+//     barrier of psa.c:638;
 //   * sequential mode (batches of independent pairs): one warp walks the bands of its
 //     pair one after the other, the boundary column parked in a per-warp scratch column.
 //
@@ -45,8 +46,9 @@
 namespace tsta {
 
 constexpr int kPadCode = 7;      // PRMT mode: column code that never matches a row
-constexpr int kChunkRows = 32;   // rows per hand-off chunk
-constexpr int kRing = 64;        // shared-memory ring depth in rows (>= 32 skew + 32 chunk)
+constexpr int kChunkRows = 32;   // rows per staging chunk
+constexpr int kDirRing = 64;     // direction ring depth in rows (>= 32 skew + 32 chunk)
+constexpr int kRowRing = 128;    // row-table ring depth (staged one chunk ahead)
 
 // Scoring + alphabet, shared by every kernel of the pairwise path.
 struct PsaScoring {
@@ -57,11 +59,37 @@ struct PsaScoring {
 // Per-warp shared-memory workspace.
 template <int C, bool TRACE>
 struct __align__(16) PsaWarpSmem {
-    uint8_t dir[TRACE ? kRing * (32 * C / 2) : 16];  // ring of packed direction rows
-    uint2 rowring[kRing];   // per-row substitution table (PRMT) / raw row byte in .x (generic)
-    int2 in[kChunkRows];    // left boundary (H|cF, F) of the current chunk
-    int2 out[kRing];        // right boundary produced by lane 31
+    uint8_t dir[TRACE ? kDirRing * (32 * C / 2) : 16];  // ring of packed direction rows
+    uint2 rowring[kRowRing];  // per-row substitution table (PRMT) / raw row byte in .x (generic)
+    int2 in[kChunkRows];      // left boundary (H|cF, F) of the current chunk
 };
+
+// Boundary column element, 8 bytes, written and read with ONE 64-bit access so that data and
+// validity tag can never be observed torn (the NCCL "LL" idea): no fences, no separate flag.
+//   low  word: H (TRACE: doubled, bit0 = cF of the next column)
+//   high word: bits 0-15 = F - H (always within [2(O+E), 0]), bits 16-31 = epoch tag (!= 0)
+__device__ __forceinline__ unsigned long long bnd_pack(int Hout, int Fout, bool trace, unsigned epoch)
+{
+    const int Hc = trace ? (Hout & ~1) : Hout;
+    const unsigned hi = ((unsigned)(Fout - Hc) & 0xffffu) | (epoch << 16);
+    return ((unsigned long long)hi << 32) | (unsigned)Hout;
+}
+__device__ __forceinline__ int2 bnd_unpack(unsigned long long v, bool trace)
+{
+    const int H = (int)(unsigned)v;
+    const int d = (int)(short)(unsigned short)(v >> 32);
+    return make_int2(H, (trace ? (H & ~1) : H) + d);
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // Everything one band sweep needs.
 struct PsaBand {
@@ -69,22 +97,14 @@ struct PsaBand {
     const uint8_t* s1;      // raw rows of this pair
     int n, m;
     int band, nbands;
-    const int2* bnd_in;     // [m] left boundary column (band > 0)
-    int2* bnd_out;          // [m] right boundary column (written when band+1 < nbands)
-    const int* wait_flag;   // PIPE: progress counter of band-1
-    int* post_flag;         // PIPE: progress counter of this band
+    const unsigned long long* bnd_in;   // [m] left boundary column (band > 0)
+    unsigned long long* bnd_out;        // [m] right boundary column (written when band+1 < nbands)
+    unsigned epoch;         // PIPE: tag that marks boundary elements of THIS run (1..65535)
     uint8_t* dirs;          // TRACE: [m][dirs_stride] packed codes of this pair
     long long dirs_stride;
     int* lastrow;           // H(m-1, j) goes to lastrow[j - lastrow_col0] (scaled units), or NULL
     int lastrow_col0;
 };
-
-__device__ __forceinline__ int ld_relaxed_gpu(const int* p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // Fills the 256-entry byte -> substitution-table map (PRMT mode).
 __device__ __forceinline__ void psa_build_tab(uint2* tab, const PsaScoring& sc, int S, int tid, int nthreads)
@@ -107,174 +127,220 @@ __device__ __forceinline__ void psa_build_tab(uint2* tab, const PsaScoring& sc, 
     }
 }
 
+// Per-lane register state of a band sweep.
+template <int C>
+struct PsaLane {
+    int Hup[C];          // H(i-1, j0+c)
+    int Eg[C];           // Eg(i, j0+c)   (TRACE: doubled, bit0 = opened)
+    uint32_t sel[C];     // PRMT selector (PRMT) or raw column byte / 256 for pad (generic)
+    int cEf[C];          // TRACE: cE(i, j0+c) as 0/8
+    int diag;            // H(i-1, j0-1)
+    int Hout, Fout;      // right edge produced by the previous step
+    int ms;              // running maximum
+    uint2 Tnext;         // substitution table of the next row (software prefetch)
+};
+
+// One wavefront step of one lane: row i of the lane's C columns.
+//   CHECK = false : steady state, every lane has a valid row (no predication at all)
+//   CHECK = true  : ramp-up / ramp-down chunks, lanes outside [0, m) keep their state
+// Schedule: the two shuffles and the shared-memory loads are issued first; everything that
+// does not depend on the incoming F (substitution, max(h, Eg), +O+E) fills their latency;
+// the serial part is one VIADDMNMX per cell (two ops in TRACE mode).
+template <int C, bool TRACE, bool PRMT, bool CHECK>
+__device__ __forceinline__ void psa_step(PsaLane<C>& L, const int i, const int s, const int m, const int lane,
+                                         const int Es, const int OEs, const int Kf, const int Ms, const int Xs,
+                                         PsaWarpSmem<C, TRACE>& sm, unsigned long long* bnd_out, const bool export_right,
+                                         const unsigned epoch)
+{
+    constexpr int kDirBytesPerLane = C / 2;
+    constexpr int kDirRowBytes = 32 * kDirBytesPerLane;
+    constexpr int kWords = (C + 7) / 8;
+
+    const int Hs = __shfl_up_sync(kFullMask, L.Hout, 1);
+    const int Fs = __shfl_up_sync(kFullMask, L.Fout, 1);
+    const int2 v0 = sm.in[s];                                  // broadcast: lane 0's boundary
+    const uint2 T = L.Tnext;
+    L.Tnext = sm.rowring[(i + 1) & (kRowRing - 1)];
+    const bool active = !CHECK || ((unsigned)i < (unsigned)m);
+
+    if (active) {
+        // ---- F-independent pre-work (uses only last step's state) ---------------------------
+        int hE[C], g[C], hs[C], Ec[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int sub = PRMT ? prmt(T.x, T.y, L.sel[c]) : (L.sel[c] == T.x ? Ms : Xs);
+            const int D = c == 0 ? L.diag : L.Hup[c - 1];
+            if (!TRACE) {
+                hE[c] = __viaddmax_s32(D, sub, L.Eg[c]);       // max(h, Eg)
+            } else {
+                hs[c] = D + sub;
+                Ec[c] = L.Eg[c] & ~1;
+                hE[c] = max(hs[c], Ec[c]);
+            }
+            g[c] = hE[c] + OEs;                                // max(h,Eg)+O+E  (TRACE: doubled, +1)
+        }
+        // ---- incoming edge ---------------------------------------------------------------
+        int Hin = lane == 0 ? v0.x : Hs;
+        int F = lane == 0 ? v0.y : Fs;
+        int cFv = 0;
+        if (TRACE) {
+            cFv = (Hin & 1) << 2;
+            Hin &= ~1;
+        }
+        L.diag = Hin;
+        // ---- serial chain + per-cell epilogue ----------------------------------------------
+        uint32_t word[kWords];
+#pragma unroll
+        for (int k = 0; k < kWords; k++) word[k] = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (!TRACE) {
+                const int Fc = F;
+                F = __viaddmax_s32(Fc, Es, g[c]);              // Fg(i, j+1): the only serial op
+                const int H = max(hE[c], Fc);
+                L.Eg[c] = __viaddmax_s32(L.Eg[c], Es, H + OEs); // the add issues on the FMA pipe (IMAD)
+                L.Hup[c] = H;
+            } else {
+                const int Fin = F;
+                const int Fc = Fin & ~1;
+                F = __viaddmax_s32(Fc, Kf, g[c]);              // max(2a, 2t+1) with t folded (Kf = max(2E, 2(O+E)+1))
+                const int H = max(hE[c], Fc);
+                int code = (H == Fc) ? 0 : 2;
+                code = (H == hs[c]) ? 1 : code;
+                code |= cFv | L.cEf[c];
+                word[c / 8] |= (uint32_t)code << (4 * (c & 7));
+                const int Tp = H + OEs;                        // 2(H+O+E)+1
+                cFv = (Fin + Es >= Tp) ? 4 : 0;                // cF of column j+1
+                L.cEf[c] = (L.Eg[c] + Es >= Tp) ? 8 : 0;       // cE of row i+1
+                L.Eg[c] = __viaddmax_s32(Ec[c], Es, Tp);
+                L.Hup[c] = H;
+            }
+        }
+        // running maximum; pad columns (last band) are included on purpose: with X<=0, E<=0,
+        // O<=0 (enforced by check_params) a pad cell never exceeds the real cells it derives
+        // from, and the reference includes them too (psa.c:333)
+#pragma unroll
+        for (int c = 0; c < C; c += 2) L.ms = __vimax3_s32(L.ms, L.Hup[c], L.Hup[c + 1]);
+        L.Hout = L.Hup[C - 1] | (TRACE ? (cFv >> 2) : 0);
+        L.Fout = F;
+        if (lane == 31 && export_right) st_relaxed_u64(bnd_out + i, bnd_pack(L.Hout, L.Fout, TRACE, epoch));
+        if (TRACE) {
+            uint8_t* dst = sm.dir + (i & (kDirRing - 1)) * kDirRowBytes + lane * kDirBytesPerLane;
+            if (C == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(word[0], word[kWords - 1]);
+            else if (C == 8) *reinterpret_cast<uint32_t*>(dst) = word[0];
+            else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word[0];
+        }
+    }
+}
+
 // One band of one pair.  Returns the lane-local running maximum (scaled units).
 template <int C, bool TRACE, bool PRMT, bool PIPE>
 __device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring& sc, const uint2* tab,
                                               PsaWarpSmem<C, TRACE>& sm, const int lane)
 {
     constexpr int S = TRACE ? 2 : 1;                    // score scale
-    constexpr int kDirBytesPerLane = C / 2;             // 4 bits per cell
-    constexpr int kDirRowBytes = 32 * kDirBytesPerLane; // bytes of one band row
-    constexpr int kWords = (C + 7) / 8;
+    constexpr int kDirRowBytes = 32 * C / 2;            // bytes of one band row of codes
     static_assert(C == 4 || C == 8 || C == 16, "lane strip width");
 
     const int m = b.m;
     const int Es = S * sc.E;
     const int OEs = S * (sc.O + sc.E) + (TRACE ? 1 : 0);  // TRACE: 2(O+E)+1, the "opened" form
+    const int Kf = max(Es, OEs);
     const int Ms = S * sc.M, Xs = S * sc.X;
     const int j0 = (b.band * 32 + lane) * C;
 
-    // ---- per-lane column state -----------------------------------------------------------
-    int Hup[C];          // H(i-1, j0+c)
-    int Eg[C];           // Eg(i, j0+c)   (TRACE: doubled, bit0 = opened)
-    uint32_t sel[C];     // PRMT selector (PRMT) or raw column byte / 256 for pad (generic)
-    int cEf[C];          // TRACE: cE(i, j0+c) as 0/8
+    PsaLane<C> L;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int j = j0 + c;
         if (PRMT) {
             const uint32_t code = j < b.n ? sc.lut[b.s0[j]] : (uint32_t)kPadCode;
-            sel[c] = code * 0x1111u | 0x8880u;
+            L.sel[c] = code * 0x1111u | 0x8880u;
         } else {
-            sel[c] = j < b.n ? (uint32_t)b.s0[j] : 256u;
+            L.sel[c] = j < b.n ? (uint32_t)b.s0[j] : 256u;
         }
-        const int hb = sc.O + (j + 1) * sc.E;             // H(-1, j)        psa.c:226
-        Hup[c] = S * hb;
-        Eg[c] = S * (hb + sc.O + sc.E) + (TRACE ? 1 : 0); // Eg(0, j), opened psa.c:222-224
-        cEf[c] = 0;
+        const int hb = sc.O + (j + 1) * sc.E;               // H(-1, j)        psa.c:226
+        L.Hup[c] = S * hb;
+        L.Eg[c] = S * (hb + sc.O + sc.E) + (TRACE ? 1 : 0); // Eg(0, j), opened psa.c:222-224
+        L.cEf[c] = 0;
     }
-    int diag = S * (j0 == 0 ? 0 : sc.O + j0 * sc.E);      // H(i-1, j0-1)
-    int ms = INT_MIN;
-    int Hout = 0, Fout = 0;                                // right edge of the previous step
+    L.diag = S * (j0 == 0 ? 0 : sc.O + j0 * sc.E);          // H(-1, j0-1)
+    L.ms = INT_MIN;
+    L.Hout = 0;
+    L.Fout = 0;
 
     const int nchunks = (m + 31 + kChunkRows - 1) / kChunkRows;
     const bool export_right = (b.band + 1 < b.nbands) && b.bnd_out != nullptr;
+    const unsigned epoch = PIPE ? b.epoch : 1u;
+
+    // ---- prologue: row tables of chunk 0, prefetch registers for chunk 1 / boundary chunk 0 ----
+    __syncwarp();
+    if (lane < m) {
+        const uint32_t raw = b.s1[lane];
+        sm.rowring[lane] = PRMT ? tab[raw] : make_uint2(raw, 0u);
+    }
+    uint32_t raw_next = (kChunkRows + lane < m) ? b.s1[kChunkRows + lane] : 0u;   // row of the NEXT chunk
+    unsigned long long bnd_next = 0;                                               // boundary of THIS chunk (prefetched)
+    if (b.band > 0 && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
+    __syncwarp();
+    L.Tnext = sm.rowring[(0 - lane) & (kRowRing - 1)];     // lane's first row is row 0 at step `lane`; harmless before
 
     for (int ch = 0; ch < nchunks; ch++) {
         const int t0 = ch * kChunkRows;
-        // ---- stage this chunk's rows: substitution tables and the left boundary -----------
-        __syncwarp();
-        if (t0 < m) {
+        // ---- stage: next chunk's row tables, this chunk's left boundary ----------------------
+        {
+            const int rown = t0 + kChunkRows + lane;       // row of the next chunk
+            if (rown < m) sm.rowring[rown & (kRowRing - 1)] = PRMT ? tab[raw_next] : make_uint2(raw_next, 0u);
+            const int rownn = rown + kChunkRows;
+            raw_next = rownn < m ? b.s1[rownn] : 0u;
             const int row = t0 + lane;
-            if (row < m) {
-                const uint32_t raw = b.s1[row];
-                sm.rowring[row & (kRing - 1)] = PRMT ? tab[raw] : make_uint2(raw, 0u);
-            }
             if (b.band > 0) {
                 if (PIPE) {
-                    const int need = min(m, t0 + kChunkRows);
-                    if (lane == 0) {
-                        while (ld_relaxed_gpu(b.wait_flag) < need) __nanosleep(32);
-                        __threadfence();  // acquire: order the boundary loads after the flag
+                    // warp-uniform spin (all lanes leave together, so the warp stays converged
+                    // for the shuffles of the step loop)
+                    while (!__all_sync(kFullMask, row >= m || (unsigned)(bnd_next >> 48) == epoch)) {
+                        __nanosleep(40);
+                        if (row < m && (unsigned)(bnd_next >> 48) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
                     }
-                    __syncwarp();
                 }
-                if (row < m) sm.in[lane] = __ldcg(b.bnd_in + row);
+                if (row < m) sm.in[lane] = bnd_unpack(bnd_next, TRACE);
             } else if (row < m) {
-                const int hb = sc.O + (row + 1) * sc.E;   // H(i, -1)   psa.c:228-231; Fg(i,0) opened
+                const int hb = sc.O + (row + 1) * sc.E;     // H(i, -1)   psa.c:228-231; Fg(i,0) opened
                 sm.in[lane] = make_int2(S * hb, S * (hb + sc.O + sc.E) + (TRACE ? 1 : 0));
             }
+            const int rowp = row + kChunkRows;             // prefetch the next chunk's boundary
+            if (b.band > 0 && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
         }
         __syncwarp();
 
+        if (t0 >= 31 && t0 + 31 < m) {
 #pragma unroll 2
-        for (int s = 0; s < kChunkRows; s++) {
-            const int i = t0 + s - lane;
-            int Hin = __shfl_up_sync(kFullMask, Hout, 1);
-            int Fin = __shfl_up_sync(kFullMask, Fout, 1);
-            if (lane == 0) {
-                const int2 v = sm.in[s];
-                Hin = v.x;
-                Fin = v.y;
-            }
-            if ((unsigned)i < (unsigned)m) {
-                const uint2 T = sm.rowring[i & (kRing - 1)];
-                int cFv = 0;
-                if (TRACE) {
-                    cFv = (Hin & 1) << 2;
-                    Hin &= ~1;
-                }
-                int D = diag;
-                diag = Hin;
-                int F = Fin;
-                uint32_t word[kWords];
-#pragma unroll
-                for (int k = 0; k < kWords; k++) word[k] = 0;
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const int sub = PRMT ? prmt(T.x, T.y, sel[c]) : (sel[c] == T.x ? Ms : Xs);
-                    if (!TRACE) {
-                        const int hE = __viaddmax_s32(D, sub, Eg[c]);   // max(h, Eg)
-                        D = Hup[c];
-                        const int g = hE + OEs;                         // independent of F
-                        const int H = max(hE, F);
-                        F = __viaddmax_s32(F, Es, g);                   // the only serial op per cell
-                        Eg[c] = __viaddmax_s32(Eg[c], Es, H + OEs);
-                        Hup[c] = H;
-                    } else {
-                        const int hs = D + sub;
-                        D = Hup[c];
-                        const int Ec = Eg[c] & ~1;
-                        const int Fc = F & ~1;
-                        const int H = __vimax3_s32(hs, Ec, Fc);
-                        int code = (H == Fc) ? 0 : 2;
-                        code = (H == hs) ? 1 : code;
-                        code |= cFv | cEf[c];
-                        word[c / 8] |= (uint32_t)code << (4 * (c & 7));
-                        const int Tp = H + OEs;                        // 2(H+O+E)+1
-                        cFv = (F + Es >= Tp) ? 4 : 0;                  // cF of column j+1
-                        cEf[c] = (Eg[c] + Es >= Tp) ? 8 : 0;           // cE of row i+1
-                        F = __viaddmax_s32(Fc, Es, Tp);
-                        Eg[c] = __viaddmax_s32(Ec, Es, Tp);
-                        Hup[c] = H;
-                    }
-                }
-                // running maximum; pad columns (last band) are included on purpose: with
-                // X<=0, E<=0, O<=0 (enforced by check_params) a pad cell never exceeds the
-                // real cells it derives from, and the reference includes them too (psa.c:333)
-#pragma unroll
-                for (int c = 0; c < C; c += 2) ms = __vimax3_s32(ms, Hup[c], Hup[c + 1]);
-                Hout = Hup[C - 1] | (TRACE ? (cFv >> 2) : 0);
-                Fout = F;
-                if (lane == 31) sm.out[i & (kRing - 1)] = make_int2(Hout, Fout);
-                if (TRACE) {
-                    uint8_t* dst = sm.dir + (i & (kRing - 1)) * kDirRowBytes + lane * kDirBytesPerLane;
-                    if (C == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(word[0], word[kWords - 1]);
-                    else if (C == 8) *reinterpret_cast<uint32_t*>(dst) = word[0];
-                    else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word[0];
-                }
-            }
+            for (int s = 0; s < kChunkRows; s++)
+                psa_step<C, TRACE, PRMT, false>(L, t0 + s - lane, s, m, lane, Es, OEs, Kf, Ms, Xs, sm, b.bnd_out,
+                                                export_right, epoch);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < kChunkRows; s++)
+                psa_step<C, TRACE, PRMT, true>(L, t0 + s - lane, s, m, lane, Es, OEs, Kf, Ms, Xs, sm, b.bnd_out,
+                                               export_right, epoch);
         }
 
-        // ---- publish the rows every lane has finished: [lo, hi) ---------------------------
+        // ---- flush the direction rows every lane has finished: [lo, hi) ----------------------
         __syncwarp();
-        const int hi = min(m, t0 + 1);
-        const int lo = ch == 0 ? 0 : min(m, t0 - kChunkRows + 1);
-        if (hi > lo) {
-            if (export_right) {
-                const int row = lo + lane;
-                if (row < hi) b.bnd_out[row] = sm.out[row & (kRing - 1)];
-            }
-            if (TRACE) {
-                // 16-byte units: kDirRowBytes/16 per row; lane handles units lane, lane+32, ...
-                constexpr int kUnitsPerRow = kDirRowBytes / 16;
-                const int units = (hi - lo) * kUnitsPerRow;
-                for (int u = lane; u < units; u += 32) {
-                    const int row = lo + u / kUnitsPerRow;
-                    const int part = u % kUnitsPerRow;
-                    const uint4 v = *reinterpret_cast<const uint4*>(
-                        sm.dir + (row & (kRing - 1)) * kDirRowBytes + part * 16);
-                    uint4* dst = reinterpret_cast<uint4*>(
-                        b.dirs + (long long)row * b.dirs_stride + (long long)b.band * kDirRowBytes + part * 16);
-                    __stcs(dst, v);
-                }
-            }
-            if (PIPE && export_right) {
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    st_release_gpu(b.post_flag, hi);
-                }
+        if (TRACE) {
+            const int hi = min(m, t0 + 1);
+            const int lo = ch == 0 ? 0 : min(m, t0 - kChunkRows + 1);
+            // 16-byte units: kDirRowBytes/16 per row; lane handles units lane, lane+32, ...
+            constexpr int kUnitsPerRow = kDirRowBytes / 16;
+            const int units = (hi - lo) * kUnitsPerRow;
+            for (int u = lane; u < units; u += 32) {
+                const int row = lo + u / kUnitsPerRow;
+                const int part = u % kUnitsPerRow;
+                const uint4 v = *reinterpret_cast<const uint4*>(
+                    sm.dir + (row & (kDirRing - 1)) * kDirRowBytes + part * 16);
+                uint4* dst = reinterpret_cast<uint4*>(
+                    b.dirs + (long long)row * b.dirs_stride + (long long)b.band * kDirRowBytes + part * 16);
+                __stcs(dst, v);
             }
         }
     }
@@ -282,9 +348,9 @@ __device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring
     // after the sweep Hup[] holds the last DP row
     if (b.lastrow) {
 #pragma unroll
-        for (int c = 0; c < C; c++) b.lastrow[j0 - b.lastrow_col0 + c] = Hup[c];
+        for (int c = 0; c < C; c++) b.lastrow[j0 - b.lastrow_col0 + c] = L.Hup[c];
     }
-    return ms;
+    return L.ms;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -295,9 +361,9 @@ struct PsaPairArgs {
     const uint8_t* s0;
     const uint8_t* s1;
     int n, m, nbands;
-    int2* bnd;              // [nbands][bnd_stride]
+    unsigned long long* bnd;  // [nbands][bnd_stride] packed boundary columns (zeroed at allocation)
     long long bnd_stride;
-    int* progress;          // [nbands]
+    unsigned epoch;         // tag of this run's boundary elements (1..65535, never reused before a re-zero)
     unsigned* ticket;
     uint8_t* dirs;
     long long dirs_stride;
@@ -322,8 +388,7 @@ __global__ void __launch_bounds__(32) psa_pair_kernel(const __grid_constant__ Ps
     b.band = band; b.nbands = a.nbands;
     b.bnd_in = a.bnd + (long long)(band - 1) * a.bnd_stride;
     b.bnd_out = a.bnd + (long long)band * a.bnd_stride;
-    b.wait_flag = a.progress + band - 1;
-    b.post_flag = a.progress + band;
+    b.epoch = a.epoch;
     b.dirs = a.dirs; b.dirs_stride = a.dirs_stride;
     b.lastrow = a.lastrow; b.lastrow_col0 = 0;
     int ms = psa_sweep_band<C, TRACE, PRMT, true>(b, a.sc, tab, sm, lane);
@@ -344,7 +409,7 @@ struct PsaBatchArgs {
     const int* len0;        // [npairs] (len0 >= len1)
     const int* len1;
     long long npairs;
-    int2* scratch;          // [total warps][scratch_stride] boundary column parking
+    unsigned long long* scratch;  // [total warps][scratch_stride] boundary column parking
     long long scratch_stride;
     unsigned long long* ticket;
     uint8_t* dirs;          // TRACE: packed codes of all pairs
@@ -364,7 +429,7 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch_kernel(const __grid_cons
     if (PRMT) psa_build_tab(tab, a.sc, S, threadIdx.x, 32 * WARPS);
     __syncthreads();
     const long long gw = (long long)blockIdx.x * WARPS + w;
-    int2* scratch = a.scratch + gw * a.scratch_stride;
+    unsigned long long* scratch = a.scratch + gw * a.scratch_stride;
     int* lastrow = a.lastrow + gw * (32 * C);
 
     while (true) {
@@ -377,8 +442,12 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch_kernel(const __grid_cons
         PsaBand b;
         b.s0 = a.seqs0 + a.off0[k]; b.s1 = a.seqs1 + a.off1[k];
         b.n = n; b.m = m; b.nbands = nbands;
-        b.bnd_in = scratch; b.bnd_out = scratch;   // in place: a row is read >= 31 steps before it is rewritten
-        b.wait_flag = nullptr; b.post_flag = nullptr;
+        // In place: band b prefetches row r of the column at the start of chunk r/32 - 1 and
+        // overwrites it (lane 31, step r+31) during chunk >= r/32, so every row is read before
+        // it is rewritten; __syncwarp at the top of each sweep orders band b's stores before
+        // band b+1's loads.
+        b.bnd_in = scratch; b.bnd_out = scratch;
+        b.epoch = 1u;
         b.dirs = TRACE ? a.dirs + a.dirs_off[k] : nullptr;
         b.dirs_stride = (long long)nbands * (32 * C / 2);
         b.lastrow_col0 = (nbands - 1) * 32 * C;

@@ -102,13 +102,12 @@ struct tsta_psa_plan {
     bool prmt = true;
     bool uploaded = false, ran = false;
     int launches = 0;
+    unsigned epoch = 0;            // boundary tag of the last run (see psa_fill.cuh: bnd_pack)
     std::vector<char> h_s0, h_s1;  // host copies for string emission
     DevBuf d_s0, d_s1, d_bnd, d_ctl, d_dirs, d_ops, d_lastrow;
-    // d_ctl layout (ints): [0] ticket, [1] out_max, [2..4] trace out, [8..15] presence,
-    //                      [16 ..] progress[nbands]
+    // d_ctl layout (ints): [0] ticket, [1] out_max, [2..4] trace out, [8..15] presence
     int* h_small = nullptr;  // pinned, 16 ints
 };
-constexpr int kCtlProgress = 16;
 
 static void plan_free(tsta_psa_plan* p)
 {
@@ -216,8 +215,15 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
 
     if (int rc = p->d_s0.reserve((size_t)n)) return rc;
     if (int rc = p->d_s1.reserve((size_t)m)) return rc;
-    if (int rc = p->d_bnd.reserve((size_t)p->nbands * (size_t)m * sizeof(int2))) return rc;
-    if (int rc = p->d_ctl.reserve((size_t)(kCtlProgress + p->nbands) * sizeof(int))) return rc;
+    {   // boundary columns: tagged elements, so fresh memory must start out all-zero (tag 0)
+        const size_t need = (size_t)p->nbands * (size_t)m * sizeof(unsigned long long);
+        if (need > p->d_bnd.cap) {
+            if (int rc = p->d_bnd.reserve(need + need / 4)) return rc;
+            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+            p->epoch = 0;
+        }
+    }
+    if (int rc = p->d_ctl.reserve(16 * sizeof(int))) return rc;
     if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
     if (p->want_trace) {
         if (int rc = p->d_dirs.reserve((size_t)m * (size_t)(p->n_pad / 2))) return rc;
@@ -248,9 +254,12 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     if (p->n == 0 || p->m == 0) { p->ran = true; return TSTA_OK; }
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     int* ctl = p->d_ctl.as<int>();
-    // ticket = 0, progress = 0; out_max = INT_MIN
+    // ticket = 0; out_max = INT_MIN; a fresh boundary tag for this run
     TSTA_CUDA_TRY(cudaMemsetAsync(ctl, 0, 8 * sizeof(int), p->stream));
-    TSTA_CUDA_TRY(cudaMemsetAsync(ctl + kCtlProgress, 0, (size_t)p->nbands * sizeof(int), p->stream));
+    if (++p->epoch > 0xffffu) {
+        TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+        p->epoch = 1;
+    }
     p->h_small[0] = INT_MIN;
     TSTA_CUDA_TRY(cudaMemcpyAsync(ctl + 1, p->h_small, sizeof(int), cudaMemcpyHostToDevice, p->stream));
 
@@ -259,9 +268,9 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     fa.s0 = p->d_s0.as<uint8_t>();
     fa.s1 = p->d_s1.as<uint8_t>();
     fa.n = (int)p->n; fa.m = (int)p->m; fa.nbands = p->nbands;
-    fa.bnd = p->d_bnd.as<int2>();
+    fa.bnd = p->d_bnd.as<unsigned long long>();
     fa.bnd_stride = p->m;
-    fa.progress = ctl + kCtlProgress;
+    fa.epoch = p->epoch;
     fa.ticket = reinterpret_cast<unsigned*>(ctl);
     fa.dirs = p->d_dirs.as<uint8_t>();
     fa.dirs_stride = p->n_pad / 2;

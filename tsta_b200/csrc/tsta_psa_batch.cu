@@ -129,7 +129,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     int blocks = sms * 6;
     blocks = (int)std::min<int64_t>(blocks, (npairs + kBatchWarps - 1) / kBatchWarps);
     const long long nwarps = (long long)blocks * kBatchWarps;
-    int2* d_scratch;
+    unsigned long long* d_scratch;
     int* d_lastrow;
     if (int rc = g.alloc(&d_scratch, (size_t)nwarps * (size_t)std::max<int64_t>(max1, 1))) return rc;
     if (int rc = g.alloc(&d_lastrow, (size_t)nwarps * band_cols)) return rc;
