@@ -46,7 +46,7 @@
 namespace tsta {
 
 constexpr int kPadCode = 7;      // PRMT mode: column code that never matches a row
-constexpr int kChunkRows = 32;   // rows per staging chunk
+constexpr int kMaxChunkRows = 32; // rows per staging chunk: template parameter CH (8, 16 or 32)
 constexpr int kDirRing = 64;     // direction ring depth in rows (>= 32 skew + 32 chunk)
 constexpr int kRowRing = 128;    // row-table ring depth (staged one chunk ahead)
 
@@ -61,17 +61,17 @@ template <int C, bool TRACE>
 struct __align__(16) PsaWarpSmem {
     uint8_t dir[TRACE ? kDirRing * (32 * C / 2) : 16];  // ring of packed direction rows
     uint2 rowring[kRowRing];  // per-row substitution table (PRMT) / raw row byte in .x (generic)
-    int2 in[kChunkRows];      // left boundary (H|cF, F) of the current chunk
+    int2 in[kMaxChunkRows];   // left boundary (H|cF, F) of the current chunk
 };
 
 // Boundary column element, 8 bytes, written and read with ONE 64-bit access so that data and
 // validity tag can never be observed torn (the NCCL "LL" idea): no fences, no separate flag.
 //   low  word: H (TRACE: doubled, bit0 = cF of the next column)
 //   high word: bits 0-15 = F - H (always within [2(O+E), 0]), bits 16-31 = epoch tag (!= 0)
-__device__ __forceinline__ unsigned long long bnd_pack(int Hout, int Fout, bool trace, unsigned epoch)
+__device__ __forceinline__ unsigned long long bnd_pack(int Hout, int Fout, bool trace, unsigned epoch_hi)
 {
     const int Hc = trace ? (Hout & ~1) : Hout;
-    const unsigned hi = ((unsigned)(Fout - Hc) & 0xffffu) | (epoch << 16);
+    const unsigned hi = ((unsigned)(Fout - Hc) & 0xffffu) | epoch_hi;   // epoch_hi = epoch << 16
     return ((unsigned long long)hi << 32) | (unsigned)Hout;
 }
 __device__ __forceinline__ int2 bnd_unpack(unsigned long long v, bool trace)
@@ -89,6 +89,34 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Shared-memory accesses of the step loop go through explicit 32-bit shared addresses: on
+// sm_100 the compiler otherwise re-derives the CTA's shared window (S2UR SR_CgaCtaId) inside
+// the loop, which lands on the step's critical path.
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y));
+}
+// Predicated (branch-free) tagged store of one boundary element.
+__device__ __forceinline__ void st_relaxed_u64_if(unsigned long long* p, unsigned long long v, bool doit)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.relaxed.gpu.global.b64 [%0], %1;\n\t}"
+                 ::"l"(p), "l"(v), "r"((unsigned)doit) : "memory");
 }
 
 // Everything one band sweep needs.
@@ -149,8 +177,8 @@ struct PsaLane {
 template <int C, bool TRACE, bool PRMT, bool CHECK>
 __device__ __forceinline__ void psa_step(PsaLane<C>& L, const int i, const int s, const int m, const int lane,
                                          const int Es, const int OEs, const int Kf, const int Ms, const int Xs,
-                                         PsaWarpSmem<C, TRACE>& sm, unsigned long long* bnd_out, const bool export_right,
-                                         const unsigned epoch)
+                                         const uint32_t in_addr, const uint32_t ring_addr, const uint32_t dir_addr,
+                                         unsigned long long* bnd_out, const bool store_right, const unsigned epoch_hi)
 {
     constexpr int kDirBytesPerLane = C / 2;
     constexpr int kDirRowBytes = 32 * kDirBytesPerLane;
@@ -158,9 +186,9 @@ __device__ __forceinline__ void psa_step(PsaLane<C>& L, const int i, const int s
 
     const int Hs = __shfl_up_sync(kFullMask, L.Hout, 1);
     const int Fs = __shfl_up_sync(kFullMask, L.Fout, 1);
-    const int2 v0 = sm.in[s];                                  // broadcast: lane 0's boundary
+    const uint2 v0 = lds_u2(in_addr + s * 8);                  // broadcast: lane 0's boundary
     const uint2 T = L.Tnext;
-    L.Tnext = sm.rowring[(i + 1) & (kRowRing - 1)];
+    L.Tnext = lds_u2(ring_addr + (((i + 1) & (kRowRing - 1)) << 3));
     const bool active = !CHECK || ((unsigned)i < (unsigned)m);
 
     if (active) {
@@ -180,8 +208,8 @@ __device__ __forceinline__ void psa_step(PsaLane<C>& L, const int i, const int s
             g[c] = hE[c] + OEs;                                // max(h,Eg)+O+E  (TRACE: doubled, +1)
         }
         // ---- incoming edge ---------------------------------------------------------------
-        int Hin = lane == 0 ? v0.x : Hs;
-        int F = lane == 0 ? v0.y : Fs;
+        int Hin = lane == 0 ? (int)v0.x : Hs;
+        int F = lane == 0 ? (int)v0.y : Fs;
         int cFv = 0;
         if (TRACE) {
             cFv = (Hin & 1) << 2;
@@ -223,24 +251,26 @@ __device__ __forceinline__ void psa_step(PsaLane<C>& L, const int i, const int s
         for (int c = 0; c < C; c += 2) L.ms = __vimax3_s32(L.ms, L.Hup[c], L.Hup[c + 1]);
         L.Hout = L.Hup[C - 1] | (TRACE ? (cFv >> 2) : 0);
         L.Fout = F;
-        if (lane == 31 && export_right) st_relaxed_u64(bnd_out + i, bnd_pack(L.Hout, L.Fout, TRACE, epoch));
+        st_relaxed_u64_if(bnd_out + i, bnd_pack(L.Hout, L.Fout, TRACE, epoch_hi), store_right);
         if (TRACE) {
-            uint8_t* dst = sm.dir + (i & (kDirRing - 1)) * kDirRowBytes + lane * kDirBytesPerLane;
-            if (C == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(word[0], word[kWords - 1]);
-            else if (C == 8) *reinterpret_cast<uint32_t*>(dst) = word[0];
-            else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word[0];
+            const uint32_t dst = dir_addr + (i & (kDirRing - 1)) * kDirRowBytes + lane * kDirBytesPerLane;
+            if (C == 16) sts_u2(dst, word[0], word[kWords - 1]);
+            else if (C == 8) sts_u32(dst, word[0]);
+            else sts_u16(dst, word[0]);
         }
     }
 }
 
 // One band of one pair.  Returns the lane-local running maximum (scaled units).
-template <int C, bool TRACE, bool PRMT, bool PIPE>
+template <int C, bool TRACE, bool PRMT, bool PIPE, int CH>
 __device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring& sc, const uint2* tab,
                                               PsaWarpSmem<C, TRACE>& sm, const int lane)
 {
     constexpr int S = TRACE ? 2 : 1;                    // score scale
     constexpr int kDirRowBytes = 32 * C / 2;            // bytes of one band row of codes
     static_assert(C == 4 || C == 8 || C == 16, "lane strip width");
+    static_assert(CH == 8 || CH == 16 || CH == 32, "chunk rows");
+    constexpr int kChunkRows = CH;
 
     const int m = b.m;
     const int Es = S * sc.E;
@@ -269,37 +299,44 @@ __device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring
     L.Hout = 0;
     L.Fout = 0;
 
-    const int nchunks = (m + 31 + kChunkRows - 1) / kChunkRows;
+    const int nchunks = (m + 31 + kChunkRows - 1) / kChunkRows;   // lane 31 finishes row m-1 at step m+30
     const bool export_right = (b.band + 1 < b.nbands) && b.bnd_out != nullptr;
     const unsigned epoch = PIPE ? b.epoch : 1u;
+    const unsigned epoch_hi = epoch << 16;
+    const bool store_right = export_right && lane == 31;
+    const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in);
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
+    const uint32_t dir_addr = (uint32_t)__cvta_generic_to_shared(sm.dir);
 
     // ---- prologue: row tables of chunk 0, prefetch registers for chunk 1 / boundary chunk 0 ----
     __syncwarp();
-    if (lane < m) {
+    const bool stager = lane < kChunkRows;                 // lanes that stage one row per chunk
+    if (stager && lane < m) {
         const uint32_t raw = b.s1[lane];
         sm.rowring[lane] = PRMT ? tab[raw] : make_uint2(raw, 0u);
     }
-    uint32_t raw_next = (kChunkRows + lane < m) ? b.s1[kChunkRows + lane] : 0u;   // row of the NEXT chunk
+    uint32_t raw_next = (stager && kChunkRows + lane < m) ? b.s1[kChunkRows + lane] : 0u;  // row of the NEXT chunk
     unsigned long long bnd_next = 0;                                               // boundary of THIS chunk (prefetched)
-    if (b.band > 0 && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
+    if (b.band > 0 && stager && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
     __syncwarp();
-    L.Tnext = sm.rowring[(0 - lane) & (kRowRing - 1)];     // lane's first row is row 0 at step `lane`; harmless before
+    L.Tnext = sm.rowring[0];                               // lane 0 starts at row 0; others re-prefetch before row 0
 
     for (int ch = 0; ch < nchunks; ch++) {
         const int t0 = ch * kChunkRows;
         // ---- stage: next chunk's row tables, this chunk's left boundary ----------------------
         {
+            const int mm = stager ? m : 0;                  // non-staging lanes see an empty range
             const int rown = t0 + kChunkRows + lane;       // row of the next chunk
-            if (rown < m) sm.rowring[rown & (kRowRing - 1)] = PRMT ? tab[raw_next] : make_uint2(raw_next, 0u);
+            if (rown < mm) sm.rowring[rown & (kRowRing - 1)] = PRMT ? tab[raw_next] : make_uint2(raw_next, 0u);
             const int rownn = rown + kChunkRows;
-            raw_next = rownn < m ? b.s1[rownn] : 0u;
-            const int row = t0 + lane;
+            raw_next = rownn < mm ? b.s1[rownn] : 0u;
+            const int row = stager ? t0 + lane : m;
             if (b.band > 0) {
                 if (PIPE) {
                     // warp-uniform spin (all lanes leave together, so the warp stays converged
                     // for the shuffles of the step loop)
                     while (!__all_sync(kFullMask, row >= m || (unsigned)(bnd_next >> 48) == epoch)) {
-                        __nanosleep(40);
+                        __nanosleep(20);
                         if (row < m && (unsigned)(bnd_next >> 48) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
                     }
                 }
@@ -309,27 +346,27 @@ __device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring
                 sm.in[lane] = make_int2(S * hb, S * (hb + sc.O + sc.E) + (TRACE ? 1 : 0));
             }
             const int rowp = row + kChunkRows;             // prefetch the next chunk's boundary
-            if (b.band > 0 && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
+            if (b.band > 0 && rowp < mm) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
         }
         __syncwarp();
 
-        if (t0 >= 31 && t0 + 31 < m) {
+        if (t0 >= 31 && t0 + kChunkRows - 1 < m) {
 #pragma unroll 2
             for (int s = 0; s < kChunkRows; s++)
-                psa_step<C, TRACE, PRMT, false>(L, t0 + s - lane, s, m, lane, Es, OEs, Kf, Ms, Xs, sm, b.bnd_out,
-                                                export_right, epoch);
+                psa_step<C, TRACE, PRMT, false>(L, t0 + s - lane, s, m, lane, Es, OEs, Kf, Ms, Xs, in_addr, ring_addr,
+                                                dir_addr, b.bnd_out, store_right, epoch_hi);
         } else {
 #pragma unroll 1
             for (int s = 0; s < kChunkRows; s++)
-                psa_step<C, TRACE, PRMT, true>(L, t0 + s - lane, s, m, lane, Es, OEs, Kf, Ms, Xs, sm, b.bnd_out,
-                                               export_right, epoch);
+                psa_step<C, TRACE, PRMT, true>(L, t0 + s - lane, s, m, lane, Es, OEs, Kf, Ms, Xs, in_addr, ring_addr,
+                                               dir_addr, b.bnd_out, store_right, epoch_hi);
         }
 
         // ---- flush the direction rows every lane has finished: [lo, hi) ----------------------
         __syncwarp();
         if (TRACE) {
-            const int hi = min(m, t0 + 1);
-            const int lo = ch == 0 ? 0 : min(m, t0 - kChunkRows + 1);
+            const int hi = min(m, max(0, t0 + kChunkRows - 31));
+            const int lo = min(m, max(0, t0 - 31));
             // 16-byte units: kDirRowBytes/16 per row; lane handles units lane, lane+32, ...
             constexpr int kUnitsPerRow = kDirRowBytes / 16;
             const int units = (hi - lo) * kUnitsPerRow;
@@ -371,7 +408,7 @@ struct PsaPairArgs {
     int* lastrow;           // [n_pad]
 };
 
-template <int C, bool TRACE, bool PRMT>
+template <int C, bool TRACE, bool PRMT, int CH>
 __global__ void __launch_bounds__(32) psa_pair_kernel(const __grid_constant__ PsaPairArgs a)
 {
     __shared__ PsaWarpSmem<C, TRACE> sm;
@@ -391,7 +428,7 @@ __global__ void __launch_bounds__(32) psa_pair_kernel(const __grid_constant__ Ps
     b.epoch = a.epoch;
     b.dirs = a.dirs; b.dirs_stride = a.dirs_stride;
     b.lastrow = a.lastrow; b.lastrow_col0 = 0;
-    int ms = psa_sweep_band<C, TRACE, PRMT, true>(b, a.sc, tab, sm, lane);
+    int ms = psa_sweep_band<C, TRACE, PRMT, true, CH>(b, a.sc, tab, sm, lane);
     ms = warp_max(ms);
     if (lane == 0) atomicMax(a.out_max, ms);
 }
@@ -456,7 +493,7 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch_kernel(const __grid_cons
             for (int band = 0; band < nbands; band++) {
                 b.band = band;
                 b.lastrow = (band == nbands - 1) ? lastrow : nullptr;
-                ms = max(ms, psa_sweep_band<C, TRACE, PRMT, false>(b, a.sc, tab, sm[w], lane));
+                ms = max(ms, psa_sweep_band<C, TRACE, PRMT, false, 32>(b, a.sc, tab, sm[w], lane));
             }
         }
         ms = warp_max(ms);

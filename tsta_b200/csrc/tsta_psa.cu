@@ -98,7 +98,7 @@ struct tsta_psa_plan {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     PsaScoring sc{};
     int64_t n = 0, m = 0;
-    int n_pad = 0, nbands = 0, C = 4;
+    int n_pad = 0, nbands = 0, C = 4, CH = 16;
     bool prmt = true;
     bool uploaded = false, ran = false;
     int launches = 0;
@@ -124,8 +124,17 @@ static void plan_free(tsta_psa_plan* p)
 template <int C, bool TRACE>
 static void launch_pair(const tsta_psa_plan* p, const PsaPairArgs& fa)
 {
-    if (p->prmt) psa_pair_kernel<C, TRACE, true><<<fa.nbands, 32, 0, p->stream>>>(fa);
-    else psa_pair_kernel<C, TRACE, false><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    // hand-off chunk: 16 rows keeps the inter-band lag short; 32 is kept for experiments
+    if (p->CH == 32) {
+        if (p->prmt) psa_pair_kernel<C, TRACE, true, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
+        else psa_pair_kernel<C, TRACE, false, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    } else if (p->CH == 8) {
+        if (p->prmt) psa_pair_kernel<C, TRACE, true, 8><<<fa.nbands, 32, 0, p->stream>>>(fa);
+        else psa_pair_kernel<C, TRACE, false, 8><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    } else {
+        if (p->prmt) psa_pair_kernel<C, TRACE, true, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
+        else psa_pair_kernel<C, TRACE, false, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    }
 }
 
 // Lane strip width for one long pair: the pipeline runs at the speed of its slowest band,
@@ -209,6 +218,10 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     }
     const int S = p->want_trace ? 2 : 1;
     p->C = choose_strip(n, p->sms);
+    p->CH = 16;
+    // tuning overrides for experiments (not part of the ABI)
+    if (const char* e = getenv("TSTA_PSA_C")) { const int c = atoi(e); if (c == 4 || c == 8 || c == 16) p->C = c; }
+    if (const char* e = getenv("TSTA_PSA_CH")) { const int c = atoi(e); if (c == 8 || c == 16 || c == 32) p->CH = c; }
     const int band_cols = 32 * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
     p->n_pad = p->nbands * band_cols;
