@@ -268,7 +268,8 @@ __device__ __forceinline__ int psa_sweep_band(const PsaBand& b, const PsaScoring
 {
     constexpr int S = TRACE ? 2 : 1;                    // score scale
     constexpr int kDirRowBytes = 32 * C / 2;            // bytes of one band row of codes
-    static_assert(C == 4 || C == 8 || C == 16, "lane strip width");
+    static_assert(C == 4 || C == 6 || C == 8 || C == 16, "lane strip width");
+    static_assert(!TRACE || C != 6, "traced strips must pack to whole 16-bit units");
     static_assert(CH == 8 || CH == 16 || CH == 32, "chunk rows");
     constexpr int kChunkRows = CH;
 

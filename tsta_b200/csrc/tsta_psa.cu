@@ -140,10 +140,11 @@ static void launch_pair(const tsta_psa_plan* p, const PsaPairArgs& fa)
 // Lane strip width for one long pair: the pipeline runs at the speed of its slowest band,
 // so prefer at most one band (warp) per SM sub-partition (4 per SM) and widen the strips
 // when the read is long enough to need more.
-static int choose_strip(int64_t n, int sms)
+static int choose_strip(int64_t n, int sms, bool trace)
 {
     const int64_t slots = (int64_t)sms * 4;
     if (n <= 32 * 4 * slots) return 4;
+    if (!trace && n <= 32 * 6 * slots) return 6;   // 6-column strips do not pack to whole direction words
     if (n <= 32 * 8 * slots) return 8;
     return 16;
 }
@@ -217,10 +218,10 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
         return TSTA_OK;
     }
     const int S = p->want_trace ? 2 : 1;
-    p->C = choose_strip(n, p->sms);
+    p->C = choose_strip(n, p->sms, p->want_trace != 0);
     p->CH = 16;
     // tuning overrides for experiments (not part of the ABI)
-    if (const char* e = getenv("TSTA_PSA_C")) { const int c = atoi(e); if (c == 4 || c == 8 || c == 16) p->C = c; }
+    if (const char* e = getenv("TSTA_PSA_C")) { const int c = atoi(e); if (c == 4 || c == 8 || c == 16 || (c == 6 && !p->want_trace)) p->C = c; }
     if (const char* e = getenv("TSTA_PSA_CH")) { const int c = atoi(e); if (c == 8 || c == 16 || c == 32) p->CH = c; }
     const int band_cols = 32 * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
@@ -297,6 +298,7 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
         else launch_pair<16, true>(p, fa);
     } else {
         if (p->C == 4) launch_pair<4, false>(p, fa);
+        else if (p->C == 6) launch_pair<6, false>(p, fa);
         else if (p->C == 8) launch_pair<8, false>(p, fa);
         else launch_pair<16, false>(p, fa);
     }
