@@ -1,0 +1,107 @@
+/* msa_driver.c -- see msa_driver.h */
+#include "msa_driver.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "fasta.h"
+
+static void print_usage(void)
+{
+    /* text of reference msa/msa.c:62-73 */
+    printf("-M                      the sorce of match [default: 2]\n");
+    printf("-X                      the sorce of dismatch [default: -5]\n");
+    printf("-E                      the sorce of extend-gap [default: -2]\n");
+    printf("-O                      the sorce of open-gap [default: -4]\n");
+    printf("-T                      the number of threads [default: 10]\n");
+    printf("-W                      the width of block(Multiplication of simd data width) [default: 16]\n");
+    printf("-i                      the input sequence(fasta format)\n");
+    printf("-o                      the output file [default: output.txt]\n");
+    printf("example:\n./TSTA_msa -i seq.fa -o output.txt\n");
+}
+
+/* control() without the tile loop (c-t-simd.c:979-1049) */
+static int align_read(poa_graph* g, const char* read, int num, const msa_params* p, const msa_backend* be)
+{
+    const int len = (int)strlen(read);
+    poa_csr csr;
+    poa_graph_export(g, p->E, p->O, &csr);
+    int32_t* lastsorce = (int32_t*)malloc((size_t)(csr.nrows + 1) * sizeof(int32_t));
+    poa_step* path = (poa_step*)malloc((size_t)(csr.nrows + len + 1) * sizeof(poa_step));
+    int rc = be->fill(be->ctx, &csr, read, len, p, lastsorce);
+    if (rc == 0) {
+        const int start = poa_graph_pick_start(g, lastsorce);
+        const int nsteps = be->walk(be->ctx, start, path);
+        if (nsteps < 0) rc = nsteps;
+        else poa_graph_fuse(g, read, num, path, nsteps);
+    }
+    free(path);
+    free(lastsorce);
+    poa_csr_free(&csr);
+    return rc;
+}
+
+int msa_main(int argc, char* argv[], const msa_backend* be)
+{
+    msa_params prm = {2, -5, -2, -4, 0};
+    int bS = 10, c;
+    const char *input = NULL, *output = "output.txt";
+    while ((c = getopt(argc, argv, "M:X:E:O:T:W:i:o:")) != -1) {
+        switch (c) {
+        case 'M': prm.M = (signed char)atoi(optarg); break;   /* the reference keeps these in a char (msa.c:21-24) */
+        case 'X': prm.X = (signed char)atoi(optarg); break;
+        case 'E': prm.E = (signed char)atoi(optarg); break;
+        case 'O': prm.O = (signed char)atoi(optarg); break;
+        case 'T': break;                                       /* threads: not used on the GPU */
+        case 'W': bS = atoi(optarg); break;
+        case 'i': input = optarg; break;
+        case 'o': output = optarg; break;
+        default: print_usage(); return 0;
+        }
+    }
+    if (input == NULL) {
+        printf("input file is not specified\n");
+        print_usage();
+        return 0;
+    }
+    /* tile edge of the reference build being matched: AVX-512 lanes (64) x -W (msa.c:114-116);
+     * TSTA_SIMD_BLOCK=16|32 selects the SSE/AVX2 reference builds' geometry instead */
+    int block = 64;
+    const char* eb = getenv("TSTA_SIMD_BLOCK");
+    if (eb && (atoi(eb) == 16 || atoi(eb) == 32 || atoi(eb) == 64)) block = atoi(eb);
+    prm.L = block * (bS > 0 ? bS : 1);
+
+    fasta_file f;
+    fasta_read(input, 0, &f);
+    const int n = (int)f.count;
+    fprintf(stderr, "seq_num: %d\n", n);                        /* msa.c:47 */
+    if (n == 0) { fprintf(stderr, "no FASTA record found\n"); return 1; }
+
+    poa_graph g;
+    poa_graph_init(&g, f.rec[0].seq, n);
+    int rc = 0;
+    for (int i = 1; i < n - 1 && rc == 0; i++) {                /* msa.c:130-141 */
+        rc = align_read(&g, f.rec[i].seq, i, &prm, be);
+        poa_graph_sort(&g, 0);
+        if (i % 100 == 0) printf("\r[%d/%d]", i, n);
+    }
+    if (rc == 0) {
+        printf("\r[%d/%d]", n, n);
+        printf("\n");
+        rc = align_read(&g, f.rec[n - 1].seq, n - 1, &prm, be);
+        poa_graph_sort(&g, 1);
+    }
+    if (rc != 0) {
+        fprintf(stderr, "TSTA_msa: %s\n", be->error ? be->error(be->ctx) : "alignment failed");
+        return 2;
+    }
+    FILE* res = fopen(output, "w");
+    if (!res) { fprintf(stderr, "cannot open %s\n", output); return 1; }
+    poa_graph_write(&g, res);
+    fclose(res);
+    poa_graph_free(&g);
+    fasta_free(&f);
+    return 0;
+}
