@@ -106,6 +106,42 @@ int  tsta_psa_batch(const tsta_params* p, int64_t npairs,
                     float* kernel_ms);
 
 /* ------------------------------------------------------------------------------------ */
+/* Sequence-to-graph alignment (TSTA_msa)                                                */
+/* ------------------------------------------------------------------------------------ */
+
+/* One traceback step as node_fuse() consumes it (msa/c-t-simd.c:751-956): the DP cell and
+ * what its effective `source` said there.  kind: 0 vertical to predecessor `pred`, 1 match and
+ * 2 mismatch (diagonal to predecessor `pred`), 3 horizontal (the read base gets a new node). */
+typedef struct tsta_poa_step {
+    int32_t row;      /* DP row = index into the caller's topological order (p->sort[]) */
+    int32_t col;      /* read position */
+    uint8_t kind;
+    uint8_t pred;     /* index into the row's predecessor list */
+    uint16_t reserved;
+} tsta_poa_step;
+
+typedef struct tsta_poa tsta_poa;   /* device buffers reused across the reads of one MSA job */
+int  tsta_poa_create(tsta_poa** ctx);
+void tsta_poa_destroy(tsta_poa* ctx);
+
+/* Fill the DP of one read against the graph (replaces msa/c-t-simd.c:1003-1043).  The graph
+ * comes in CSR form in ROW ORDER (= p->sort[] order): row r has predecessors
+ * pred_row[row_ptr[r] .. row_ptr[r+1]) -- ROW indices, in the node's pre[] order (ties pick
+ * the lowest index); a head (in == 0) has the single entry -1.  base[r] is the node's base,
+ * hneg1[r] = H(r,-1) (O+E for heads, else max over predecessors + E: c-t-simd.c:187,196-200).
+ * L is the reference's tile edge (SIMD lanes x -W), observable only through the late-head
+ * quirk.  lastsorce[r] receives H(r, len-1) for every row (the reference
+ * keeps it for sinks, c-t-simd.c:577-578). */
+int  tsta_poa_fill(tsta_poa* ctx, const tsta_params* p, int L, int nrows,
+                   const int32_t* row_ptr, const int32_t* pred_row, const uint8_t* base, const int32_t* hneg1,
+                   const char* read, int len, int32_t* lastsorce, float* kernel_ms);
+/* Walk the traceback of the last fill from (start_row, len-1) with the reference's forced
+ * continuation rules (c-t-simd.c:767-769, 776-782); path must hold nrows+len steps. */
+int  tsta_poa_walk(tsta_poa* ctx, int start_row, tsta_poa_step* path, int* nsteps, float* kernel_ms);
+/* Parity helper: the packed trace of the last fill, nrows x len uint16 (see csrc/poa_fill.cuh). */
+int  tsta_poa_debug_trace(tsta_poa* ctx, uint16_t* out_rows_by_len);
+
+/* ------------------------------------------------------------------------------------ */
 /* Measurement helpers                                                                   */
 /* ------------------------------------------------------------------------------------ */
 

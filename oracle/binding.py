@@ -180,3 +180,51 @@ def ref_psa(x: bytes, y: bytes, M=2, X=-5, E=-2, O=-4, T=4, W=10, trace=True, is
         ms = int(txt.strip().split("maxsorce=")[1])
         out = open(fo, "rb").read() if trace else None
     return ms, out
+
+
+# ----------------------------------------------------------------------------------------
+# POA oracle (oracle/poa_oracle.c)
+# ----------------------------------------------------------------------------------------
+POA_STEP = np.dtype([("row", "<i4"), ("col", "<i4"), ("kind", "u1"), ("pred", "u1"), ("pad", "<u2")])
+
+
+def poa_fill(row_ptr, pred_row, base, hneg1, read: bytes, M=2, X=-5, E=-2, O=-4, L=640):
+    """Oracle DP of `read` against a CSR graph in row order.
+    Returns (source, esource, fsource) int8 [nrows, len] and lastsorce int32 [nrows]."""
+    Lb = lib()
+    Lb.tsta_oracle_poa_fill.restype = C.c_int
+    Lb.tsta_oracle_poa_fill.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    pred_row = np.ascontiguousarray(pred_row, dtype=np.int32)
+    base = np.ascontiguousarray(base, dtype=np.uint8)
+    hneg1 = np.ascontiguousarray(hneg1, dtype=np.int32)
+    nrows, ln = len(base), len(read)
+    src = np.zeros((nrows, ln), dtype=np.int8)
+    es = np.zeros((nrows, ln), dtype=np.int8)
+    fs = np.zeros((nrows, ln), dtype=np.int8)
+    last = np.zeros(nrows, dtype=np.int32)
+    rc = Lb.tsta_oracle_poa_fill(nrows, row_ptr.ctypes.data, pred_row.ctypes.data, base.ctypes.data,
+                                 hneg1.ctypes.data, read, ln, M, X, E, O, L,
+                                 src.ctypes.data, es.ctypes.data, fs.ctypes.data, last.ctypes.data)
+    if rc != 0:
+        raise MemoryError("oracle POA fill failed")
+    return src, es, fs, last
+
+
+def poa_walk(row_ptr, pred_row, src, es, fs, start_row: int):
+    """Oracle traceback walk (modifies a copy of `src` like the reference does)."""
+    Lb = lib()
+    Lb.tsta_oracle_poa_walk.restype = C.c_int
+    Lb.tsta_oracle_poa_walk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p]
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    pred_row = np.ascontiguousarray(pred_row, dtype=np.int32)
+    nrows, ln = src.shape
+    s2 = src.copy()
+    path = np.zeros(nrows + ln + 1, dtype=POA_STEP)
+    n = Lb.tsta_oracle_poa_walk(nrows, row_ptr.ctypes.data, pred_row.ctypes.data, ln, s2.ctypes.data,
+                                np.ascontiguousarray(es).ctypes.data, np.ascontiguousarray(fs).ctypes.data,
+                                start_row, path.ctypes.data)
+    return path[:n]

@@ -1,0 +1,118 @@
+"""Parity of the CUDA POA path with the oracle (cell by cell on random DAGs) and, end to end
+through the TSTA_msa driver, with the real reference's outputs."""
+import hashlib
+import json
+import random
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tsta_b200 import synth
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "tsta_b200" / "_build"
+
+
+def random_dag(nrows, rnd, E, O, far=0.03, heads=0.01, maxin=4, backbone=None):
+    """A graph in topological row order shaped like a POA graph: mostly a chain, some short
+    and a few long-range extra predecessors, occasional extra heads."""
+    row_ptr, pred, base, hneg1 = [0], [], [], []
+    for r in range(nrows):
+        if r == 0 or rnd.random() < heads:
+            ps = [-1]
+        else:
+            ps = [r - 1] if rnd.random() < 0.9 else [max(0, r - rnd.randint(2, 4))]
+            k = rnd.choice([0, 0, 0, 1, 1, 2, maxin - 1])
+            for _ in range(k):
+                d = rnd.randint(2, 6) if rnd.random() > far else rnd.randint(20, 200)
+                q = max(0, r - d)
+                if q not in ps:
+                    ps.append(q)
+            rnd.shuffle(ps)
+        pred += ps
+        row_ptr.append(len(pred))
+        base.append(backbone[r % len(backbone)] if backbone and rnd.random() < 0.8 else rnd.choice(b"ACGT"))
+        hneg1.append(O + E if ps[0] < 0 else max(hneg1[p] for p in ps) + E)
+    return (np.array(row_ptr, np.int32), np.array(pred, np.int32), np.array(base, np.uint8), np.array(hneg1, np.int32))
+
+
+def expected_trace(src, es, fs):
+    """Pack the oracle's three matrices the way csrc/poa_fill.cuh documents."""
+    s = src.astype(np.int32) & 0x7f
+    f = fs.astype(np.int32)
+    fneg_prev = np.zeros_like(f, dtype=bool)
+    fneg_prev[:, 1:] = f[:, :-1] < 0
+    cH = (np.abs(f) == 1) | ((np.abs(f) == 2) & fneg_prev)
+    e = es.astype(np.int32)
+    eopen = np.abs(e) > 42
+    jstar = np.abs(e) - np.where(eopen, 43, 1)
+    return (s | (cH << 7) | (jstar << 8) | (eopen.astype(np.int32) << 14) | ((e < 0).astype(np.int32) << 15)).astype(np.uint16)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_fill_and_walk_on_random_dags(gpu, seed):
+    rnd = random.Random(seed)
+    poa = gpu.Poa()
+    for k in range(4):
+        M, X, E, O = rnd.choice([(2, -5, -2, -4), (2, -3, -2, -4), (1, -1, -1, 0), (2, -5, -2, 0), (1, -3, -1, -5)])
+        nrows = rnd.choice([1, 7, 40, 129, 300, 700])
+        ln = rnd.choice([1, 3, 127, 128, 129, 300, 513])
+        L = rnd.choice([64, 128, 640])
+        read = synth.random_read(ln, 50 * seed + k)
+        g = random_dag(nrows, rnd, E, O, backbone=read)
+        src, es, fs, last = ob.poa_fill(*g, read, M, X, E, O, L)
+        glast, _ = poa.fill(*g, read, M, X, E, O, L)
+        np.testing.assert_array_equal(glast, last)
+        np.testing.assert_array_equal(poa.trace(), expected_trace(src, es, fs))
+        for start in {nrows - 1, rnd.randrange(nrows)}:
+            want = ob.poa_walk(g[0], g[1], src, es, fs, start)
+            got, _ = poa.walk(start)
+            assert len(got) == len(want)
+            for fld in ("row", "col", "kind", "pred"):
+                np.testing.assert_array_equal(got[fld], want[fld])
+    poa.close()
+
+
+def test_long_graph_far_predecessors_and_wide_in_degree(gpu):
+    rnd = random.Random(99)
+    read = synth.random_read(1000, 5)
+    g = random_dag(3000, rnd, -2, -4, far=0.2, heads=0.003, maxin=12, backbone=read)
+    src, es, fs, last = ob.poa_fill(*g, read, L=640)
+    poa = gpu.Poa()
+    glast, _ = poa.fill(*g, read, L=640)
+    np.testing.assert_array_equal(glast, last)
+    np.testing.assert_array_equal(poa.trace(), expected_trace(src, es, fs))
+    want = ob.poa_walk(g[0], g[1], src, es, fs, 2999)
+    got, _ = poa.walk(2999)
+    assert len(got) == len(want) and (got["row"] == want["row"]).all() and (got["kind"] == want["kind"]).all()
+    poa.close()
+
+
+def run_msa(reads, prm, W, tmp_path):
+    fa, fo = tmp_path / "r.fa", tmp_path / "o.txt"
+    ob.write_fasta(fa, reads)
+    p = subprocess.run([str(BIN / "TSTA_msa"), "-M", str(prm[0]), "-X", str(prm[1]), "-E", str(prm[2]), "-O", str(prm[3]),
+                        "-W", str(W), "-T", "2", "-i", str(fa), "-o", str(fo)], capture_output=True, timeout=900)
+    assert p.returncode == 0, p.stderr
+    return fo.read_bytes(), p.stdout, p.stderr
+
+
+def test_msa_driver_example_golden(gpu, tmp_path):
+    g = json.load(open(GOLDEN / "msa_golden.json"))
+    reads = [r.encode() for r in g["example_reads"]]
+    for case in g["example"]:
+        out, so, se = run_msa(reads, case["params"], case["W"], tmp_path)
+        assert hashlib.md5(out).hexdigest() == case["out_md5"]
+        assert so.decode() == case["stdout"] and se.decode() == case["stderr"]
+
+
+def test_msa_driver_reference_fuzz_goldens(gpu, tmp_path):
+    g = json.load(open(GOLDEN / "msa_golden.json"))
+    for case in g["fuzz"]:
+        out, _, _ = run_msa([r.encode() for r in case["reads"]], case["params"], case["W"], tmp_path)
+        assert hashlib.md5(out).hexdigest() == case["out_md5"], case["name"]

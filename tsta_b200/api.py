@@ -258,3 +258,66 @@ def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4
     return BatchResult(ms, corner, kms.value,
                        swapped if swapped is not None else np.zeros(npairs, dtype=bool),
                        ops, ops_off, alen, pairs)
+
+
+# ------------------------------------------------------------------------------------------
+# POA (TSTA_msa hot path)
+# ------------------------------------------------------------------------------------------
+class PoaStep(C.Structure):
+    _fields_ = [("row", C.c_int32), ("col", C.c_int32), ("kind", C.c_uint8), ("pred", C.c_uint8),
+                ("reserved", C.c_uint16)]
+
+
+class Poa:
+    """Device context of the sequence-to-graph DP (tsta_poa_*)."""
+
+    def __init__(self):
+        L = load()
+        L.tsta_poa_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.tsta_poa_destroy.argtypes = [C.c_void_p]
+        L.tsta_poa_fill.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_float)]
+        L.tsta_poa_walk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.tsta_poa_debug_trace.argtypes = [C.c_void_p, C.c_void_p]
+        self._h = C.c_void_p()
+        _check(L.tsta_poa_create(C.byref(self._h)))
+        self.nrows = self.len = 0
+
+    def fill(self, row_ptr, pred_row, base, hneg1, read: bytes, M=2, X=-5, E=-2, O=-4, L=640):
+        """Returns (lastsorce[nrows] int32, kernel_ms)."""
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        pred_row = np.ascontiguousarray(pred_row, dtype=np.int32)
+        base = np.ascontiguousarray(base, dtype=np.uint8)
+        hneg1 = np.ascontiguousarray(hneg1, dtype=np.int32)
+        self.nrows, self.len = len(base), len(read)
+        last = np.zeros(self.nrows, dtype=np.int32)
+        ms = C.c_float()
+        p = Params(M, X, E, O)
+        _check(load().tsta_poa_fill(self._h, C.byref(p), L, self.nrows, row_ptr.ctypes.data, pred_row.ctypes.data,
+                                    base.ctypes.data, hneg1.ctypes.data, read, self.len, last.ctypes.data,
+                                    C.byref(ms)))
+        return last, ms.value
+
+    def walk(self, start_row: int):
+        """Returns (steps as a structured numpy array, kernel_ms)."""
+        path = np.zeros(self.nrows + self.len + 1, dtype=np.dtype(
+            [("row", "<i4"), ("col", "<i4"), ("kind", "u1"), ("pred", "u1"), ("reserved", "<u2")]))
+        n, ms = C.c_int(), C.c_float()
+        _check(load().tsta_poa_walk(self._h, start_row, path.ctypes.data, C.byref(n), C.byref(ms)))
+        return path[:n.value], ms.value
+
+    def trace(self) -> np.ndarray:
+        out = np.zeros((self.nrows, self.len), dtype=np.uint16)
+        _check(load().tsta_poa_debug_trace(self._h, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self._h:
+            load().tsta_poa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,176 @@
+// tsta_poa.cu -- C-ABI host side of the POA path (include/tsta_cuda.h: tsta_poa_*).
+//
+// Plays the role of control() between readseq() and node_fuse() (reference
+// msa/c-t-simd.c:979-1047): the per-node trace allocation (1003-1017) becomes one dense
+// device matrix, the tile loop (1019-1043) one kernel launch, and the trace walk of
+// node_fuse() (751-785) a second kernel that returns the compact path.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "poa_fill.cuh"
+
+namespace tsta {
+int check_params(const tsta_params* p);
+}
+using namespace tsta;
+
+struct tsta_poa {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    DevBuf d_rowptr, d_pred, d_base, d_hneg1, d_read, d_HE, d_trace, d_bnd, d_ctl, d_last, d_path;
+    unsigned epoch = 0;
+    int nrows = 0, len = 0, nbands = 0;
+    long long stride = 0;
+    bool filled = false;
+    int launches = 0;
+};
+
+static void poa_free(tsta_poa* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    DevBuf* bufs[] = {&p->d_rowptr, &p->d_pred, &p->d_base, &p->d_hneg1, &p->d_read, &p->d_HE,
+                      &p->d_trace, &p->d_bnd, &p->d_ctl, &p->d_last, &p->d_path};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" {
+
+int tsta_poa_create(tsta_poa** out)
+{
+    if (!out) return set_error(TSTA_EINVAL, "context pointer is NULL");
+    *out = nullptr;
+    if (int rc = ensure_device()) return rc;
+    tsta_poa* p = new (std::nothrow) tsta_poa();
+    if (!p) return set_error(TSTA_ENOMEM, "out of host memory");
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreate(&p->ev[k]);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(poa_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaSmem));
+    if (e != cudaSuccess) {
+        poa_free(p);
+        return set_error(TSTA_ECUDA, "POA context creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return TSTA_OK;
+}
+
+void tsta_poa_destroy(tsta_poa* p) { poa_free(p); }
+
+int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
+                  const int32_t* row_ptr, const int32_t* pred_row, const uint8_t* base, const int32_t* hneg1,
+                  const char* read, int len, int32_t* lastsorce, float* kernel_ms)
+{
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (!p) return set_error(TSTA_EINVAL, "context is NULL");
+    if (int rc = check_params(prm)) return rc;
+    if (nrows <= 0 || len <= 0 || !row_ptr || !pred_row || !base || !hneg1 || !read || !lastsorce)
+        return set_error(TSTA_EINVAL, "bad POA arguments");
+    const int nedges = row_ptr[nrows];
+    for (int r = 0; r < nrows; r++)
+        if (row_ptr[r + 1] - row_ptr[r] < 1 || row_ptr[r + 1] - row_ptr[r] > 41)
+            return set_error(TSTA_EINVAL, "row %d: in-degree must be 1..41 (reference limit: predecessor index < 42)", r);
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    p->filled = false;
+    const int band_cols = 32 * kPoaC;
+    p->nbands = (len + band_cols - 1) / band_cols;
+    p->stride = (long long)p->nbands * band_cols;
+    p->nrows = nrows;
+    p->len = len;
+
+    if (int rc = p->d_rowptr.reserve((size_t)(nrows + 1) * 4)) return rc;
+    if (int rc = p->d_pred.reserve((size_t)nedges * 4)) return rc;
+    if (int rc = p->d_base.reserve((size_t)nrows)) return rc;
+    if (int rc = p->d_hneg1.reserve((size_t)nrows * 4)) return rc;
+    if (int rc = p->d_read.reserve((size_t)len)) return rc;
+    if (int rc = p->d_last.reserve((size_t)nrows * 4)) return rc;
+    if (int rc = p->d_ctl.reserve(64)) return rc;
+    if (int rc = p->d_path.reserve((size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
+    {   // grow generously: the graph gains rows every round
+        const size_t cells = (size_t)nrows * (size_t)p->stride;
+        if (cells * sizeof(int2) > p->d_HE.cap) if (int rc = p->d_HE.reserve(cells * sizeof(int2) * 5 / 4)) return rc;
+        if (cells * 2 > p->d_trace.cap) if (int rc = p->d_trace.reserve(cells * 2 * 5 / 4)) return rc;
+        const size_t need = (size_t)p->nbands * (size_t)nrows * 8;
+        if (need > p->d_bnd.cap) {
+            if (int rc = p->d_bnd.reserve(need * 5 / 4)) return rc;
+            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+            p->epoch = 0;
+        }
+    }
+    if (++p->epoch > 0x7fffu) {
+        TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+        p->epoch = 1;
+    }
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_rowptr.p, row_ptr, (size_t)(nrows + 1) * 4, cudaMemcpyHostToDevice, p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_pred.p, pred_row, (size_t)nedges * 4, cudaMemcpyHostToDevice, p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_base.p, base, (size_t)nrows, cudaMemcpyHostToDevice, p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_hneg1.p, hneg1, (size_t)nrows * 4, cudaMemcpyHostToDevice, p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_read.p, read, (size_t)len, cudaMemcpyHostToDevice, p->stream));
+    TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.p, 0, 64, p->stream));
+
+    PoaFillArgs a{};
+    a.row_ptr = p->d_rowptr.as<int>(); a.pred_row = p->d_pred.as<int>();
+    a.base = p->d_base.as<uint8_t>(); a.hneg1 = p->d_hneg1.as<int>(); a.read = p->d_read.as<uint8_t>();
+    a.len = len; a.nrows = nrows; a.nbands = p->nbands; a.L = L;
+    a.M = prm->M; a.X = prm->X; a.E = prm->E; a.O = prm->O;
+    a.HE = p->d_HE.as<int2>(); a.stride = p->stride;
+    a.trace = p->d_trace.as<uint16_t>();
+    a.bnd = p->d_bnd.as<unsigned long long>(); a.epoch = p->epoch;
+    a.ticket = p->d_ctl.as<unsigned>();
+    a.lastsorce = p->d_last.as<int>();
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+    poa_fill_kernel<<<p->nbands, 32, sizeof(PoaSmem), p->stream>>>(a);
+    TSTA_CUDA_TRY(cudaGetLastError());
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(lastsorce, p->d_last.p, (size_t)nrows * 4, cudaMemcpyDeviceToHost, p->stream));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (kernel_ms) TSTA_CUDA_TRY(cudaEventElapsedTime(kernel_ms, p->ev[0], p->ev[1]));
+    p->filled = true;
+    p->launches = 1;
+    return TSTA_OK;
+}
+
+int tsta_poa_walk(tsta_poa* p, int start_row, tsta_poa_step* path, int* nsteps, float* kernel_ms)
+{
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (!p || !p->filled || !path || !nsteps) return set_error(TSTA_EINVAL, "POA walk before fill, or NULL argument");
+    if (start_row < 0 || start_row >= p->nrows) return set_error(TSTA_EINVAL, "start row out of range");
+    static_assert(sizeof(tsta_poa_step) == sizeof(PoaStep), "step layout");
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    PoaWalkArgs w{};
+    w.trace = p->d_trace.as<uint16_t>(); w.stride = p->stride;
+    w.row_ptr = p->d_rowptr.as<int>(); w.pred_row = p->d_pred.as<int>();
+    w.len = p->len; w.nrows = p->nrows; w.start_row = start_row;
+    w.path = p->d_path.as<PoaStep>();
+    w.nsteps = p->d_ctl.as<int>() + 4;
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+    poa_walk_kernel<<<1, kPoaWalkThreads, 0, p->stream>>>(w);
+    TSTA_CUDA_TRY(cudaGetLastError());
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+    int n = 0;
+    TSTA_CUDA_TRY(cudaMemcpyAsync(&n, w.nsteps, 4, cudaMemcpyDeviceToHost, p->stream));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (n < 0 || n > p->nrows + p->len) return set_error(TSTA_ECUDA, "walker returned an impossible path length %d", n);
+    if (n > 0) TSTA_CUDA_TRY(cudaMemcpy(path, p->d_path.p, (size_t)n * sizeof(PoaStep), cudaMemcpyDeviceToHost));
+    *nsteps = n;
+    if (kernel_ms) TSTA_CUDA_TRY(cudaEventElapsedTime(kernel_ms, p->ev[0], p->ev[1]));
+    p->launches = 2;
+    return TSTA_OK;
+}
+
+int tsta_poa_debug_trace(tsta_poa* p, uint16_t* out_rows_by_len)
+{
+    if (!p || !p->filled || !out_rows_by_len) return set_error(TSTA_EINVAL, "POA trace export before fill");
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    TSTA_CUDA_TRY(cudaMemcpy2D(out_rows_by_len, (size_t)p->len * 2, p->d_trace.p, (size_t)p->stride * 2,
+                               (size_t)p->len * 2, (size_t)p->nrows, cudaMemcpyDeviceToHost));
+    return TSTA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+/* tsta_msa_main.c -- TSTA_msa on B200: the reference's command line (msa/msa.c) with the
+ * sequence-to-graph DP and its traceback walk running in the CUDA library.  No CPU fallback. */
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "msa_driver.h"
+#include "tsta_cuda.h"
+
+typedef struct { tsta_poa* poa; } gctx;
+
+static int g_fill(void* c, const poa_csr* g, const char* read, int len, const msa_params* p, int32_t* lastsorce)
+{
+    gctx* x = (gctx*)c;
+    tsta_params prm = {p->M, p->X, p->E, p->O};
+    return tsta_poa_fill(x->poa, &prm, p->L, g->nrows, g->row_ptr, g->pred_row, g->base, g->hneg1,
+                         read, len, lastsorce, NULL);
+}
+
+static int g_walk(void* c, int start, poa_step* path)
+{
+    gctx* x = (gctx*)c;
+    int n = 0;
+    _Static_assert(sizeof(poa_step) == sizeof(tsta_poa_step), "path step layout");
+    int rc = tsta_poa_walk(x->poa, start, (tsta_poa_step*)path, &n, NULL);
+    return rc == TSTA_OK ? n : rc;
+}
+
+static const char* g_err(void* c) { (void)c; return tsta_last_error(); }
+
+int main(int argc, char* argv[])
+{
+    gctx x = {NULL};
+    msa_backend be = {&x, g_fill, g_walk, g_err};
+    /* the context is created lazily so that usage / missing-input paths need no GPU */
+    int need_gpu = 0;
+    for (int i = 1; i < argc; i++) if (argv[i][0] == '-' && argv[i][1] == 'i') need_gpu = 1;
+    if (need_gpu && tsta_poa_create(&x.poa) != TSTA_OK) {
+        fprintf(stderr, "TSTA_msa: %s\n", tsta_last_error());
+        return 2;
+    }
+    int rc = msa_main(argc, argv, &be);
+    if (x.poa) tsta_poa_destroy(x.poa);
+    return rc;
+}
