@@ -6,7 +6,19 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <time.h>
+
 #include "fasta.h"
+
+/* optional phase timing (TSTA_MSA_TIMING=1), printed to stderr at exit; off by default so the
+ * driver's stderr stays identical to the reference's */
+static double t_export, t_fill, t_walk, t_fuse, t_sort;
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static void print_usage(void)
 {
@@ -27,15 +39,23 @@ static int align_read(poa_graph* g, const char* read, int num, const msa_params*
 {
     const int len = (int)strlen(read);
     poa_csr csr;
+    double t0 = now_s();
     poa_graph_export(g, p->E, p->O, &csr);
+    t_export += now_s() - t0;
     int32_t* lastsorce = (int32_t*)malloc((size_t)(csr.nrows + 1) * sizeof(int32_t));
     poa_step* path = (poa_step*)malloc((size_t)(csr.nrows + len + 1) * sizeof(poa_step));
+    t0 = now_s();
     int rc = be->fill(be->ctx, &csr, read, len, p, lastsorce);
+    t_fill += now_s() - t0;
     if (rc == 0) {
         const int start = poa_graph_pick_start(g, lastsorce);
+        t0 = now_s();
         const int nsteps = be->walk(be->ctx, start, path);
+        t_walk += now_s() - t0;
+        t0 = now_s();
         if (nsteps < 0) rc = nsteps;
         else poa_graph_fuse(g, read, num, path, nsteps);
+        t_fuse += now_s() - t0;
     }
     free(path);
     free(lastsorce);
@@ -84,7 +104,9 @@ int msa_main(int argc, char* argv[], const msa_backend* be)
     int rc = 0;
     for (int i = 1; i < n - 1 && rc == 0; i++) {                /* msa.c:130-141 */
         rc = align_read(&g, f.rec[i].seq, i, &prm, be);
+        double t0 = now_s();
         poa_graph_sort(&g, 0);
+        t_sort += now_s() - t0;
         if (i % 100 == 0) printf("\r[%d/%d]", i, n);
     }
     if (rc == 0) {
@@ -101,6 +123,9 @@ int msa_main(int argc, char* argv[], const msa_backend* be)
     if (!res) { fprintf(stderr, "cannot open %s\n", output); return 1; }
     poa_graph_write(&g, res);
     fclose(res);
+    if (getenv("TSTA_MSA_TIMING"))
+        fprintf(stderr, "timing: export %.3f fill %.3f walk %.3f fuse %.3f sort %.3f s (rows %d)\n",
+                t_export, t_fill, t_walk, t_fuse, t_sort, g.len);
     poa_graph_free(&g);
     fasta_free(&f);
     return 0;

@@ -6,14 +6,18 @@
 #include "msa_driver.h"
 #include "tsta_cuda.h"
 
-typedef struct { tsta_poa* poa; } gctx;
+typedef struct { tsta_poa* poa; double fill_ms, walk_ms; double cells; } gctx;
 
 static int g_fill(void* c, const poa_csr* g, const char* read, int len, const msa_params* p, int32_t* lastsorce)
 {
     gctx* x = (gctx*)c;
     tsta_params prm = {p->M, p->X, p->E, p->O};
-    return tsta_poa_fill(x->poa, &prm, p->L, g->nrows, g->row_ptr, g->pred_row, g->base, g->hneg1,
-                         read, len, lastsorce, NULL);
+    float ms = 0.f;
+    int rc = tsta_poa_fill(x->poa, &prm, p->L, g->nrows, g->row_ptr, g->pred_row, g->base, g->hneg1,
+                           read, len, lastsorce, &ms);
+    x->fill_ms += ms;
+    x->cells += (double)g->nrows * (double)len;
+    return rc;
 }
 
 static int g_walk(void* c, int start, poa_step* path)
@@ -21,7 +25,9 @@ static int g_walk(void* c, int start, poa_step* path)
     gctx* x = (gctx*)c;
     int n = 0;
     _Static_assert(sizeof(poa_step) == sizeof(tsta_poa_step), "path step layout");
-    int rc = tsta_poa_walk(x->poa, start, (tsta_poa_step*)path, &n, NULL);
+    float ms = 0.f;
+    int rc = tsta_poa_walk(x->poa, start, (tsta_poa_step*)path, &n, &ms);
+    x->walk_ms += ms;
     return rc == TSTA_OK ? n : rc;
 }
 
@@ -29,7 +35,7 @@ static const char* g_err(void* c) { (void)c; return tsta_last_error(); }
 
 int main(int argc, char* argv[])
 {
-    gctx x = {NULL};
+    gctx x = {NULL, 0.0, 0.0, 0.0};
     msa_backend be = {&x, g_fill, g_walk, g_err};
     /* the context is created lazily so that usage / missing-input paths need no GPU */
     int need_gpu = 0;
@@ -39,6 +45,9 @@ int main(int argc, char* argv[])
         return 2;
     }
     int rc = msa_main(argc, argv, &be);
+    if (getenv("TSTA_MSA_TIMING"))
+        fprintf(stderr, "kernels: fill %.1f ms walk %.1f ms, %.3g node-cells, %.1f GCUPS (fill kernel)\n",
+                x.fill_ms, x.walk_ms, x.cells, x.fill_ms > 0 ? x.cells / x.fill_ms / 1e6 : 0.0);
     if (x.poa) tsta_poa_destroy(x.poa);
     return rc;
 }
