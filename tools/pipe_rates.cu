@@ -46,7 +46,7 @@ template <int OP> void run(const char* name)
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     double ops = (double)blocks * 256 * iters * 16 * 8;
-    printf("%-12s %.2f Tlaneop/s  (%.1f lanes/clk/SM at 1.965 GHz)\n", name, ops / best / 1e9, ops / best / 1e6 / 148 / 1.965e3);
+    printf("%-12s %.2f Tlaneop/s  (%.1f lanes/clk/SM at 1.965 GHz)\n", name, ops / best / 1e9, ops / (best * 1e-3) / 148 / 1.965e9);
 }
 
 int main()
