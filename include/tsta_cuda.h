@@ -89,6 +89,9 @@ int  tsta_psa_plan_lastrow(tsta_psa_plan* plan, int32_t* out_n);
 int  tsta_psa_plan_dirs(tsta_psa_plan* plan, uint8_t* out_m_by_n);
 /* Number of kernels the last run launched and the lane width it chose (for reporting). */
 int  tsta_psa_plan_info(tsta_psa_plan* plan, int* launches, int* cols_per_lane, int* bands);
+/* 1 when the last upload selected the packed int16x2 kernels (two cells per register; small
+ * alphabets and score ranges, csrc/psa_fill16.cuh), 0 for the int32 kernels. */
+int  tsta_psa_plan_packed(tsta_psa_plan* plan);
 void tsta_psa_plan_destroy(tsta_psa_plan* plan);
 
 /* Many independent pairs.  seqs0/seqs1 are concatenations; off*[k], len*[k] locate pair k

@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     L.tsta_psa_plan_dirs.argtypes = [C.c_void_p, C.c_void_p]
     L.tsta_psa_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tsta_psa_plan_destroy.argtypes = [C.c_void_p]
+    L.tsta_psa_plan_packed.argtypes = [C.c_void_p]
     L.tsta_set_device.argtypes = [C.c_int]
     L.tsta_measure_dpx_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if hasattr(L, "tsta_psa_batch"):
@@ -162,7 +163,8 @@ class PsaPlan:
     def info(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         _check(load().tsta_psa_plan_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"launches": a.value, "cols_per_lane": b.value, "bands": c.value}
+        return {"launches": a.value, "cols_per_lane": b.value, "bands": c.value,
+                "packed": bool(load().tsta_psa_plan_packed(self._h))}
 
     def close(self) -> None:
         if self._h:

@@ -1,0 +1,408 @@
+// psa_fill16.cuh -- the pairwise fill with TWO cells per 32-bit register (packed int16 x 2).
+//
+// Same decomposition as psa_fill.cuh (bands of columns, lanes skewed one row apart, tagged
+// boundary hand-off between bands) and the same recurrences (reference psa/psa.c:234-363), but
+// every register holds two independent cells, so one DPX instruction (VIADDMNMX.S16x2,
+// VIMNMX3.S16x2, VIADD.16x2; one PRMT for both substitution scores) advances two cells:
+//
+//   * a warp is 64 VIRTUAL lanes: physical lane k carries virtual lane k in the low halves
+//     and virtual lane k+32 in the high halves.  Virtual lane v owns C columns and works on
+//     row t - v at step t.  The right edge moves to the next virtual lane by ONE rotating
+//     shuffle: lane k receives lane k-1 (both halves at once), lane 0 receives lane 31's low
+//     half into its high half (virtual lane 31 -> 32) and the band's left boundary into its
+//     low half.  A band is therefore 64*C columns wide;
+//   * the reference keeps int8 DIFFERENCES against a moving int32 column (psa.c:291,329); here
+//     the int16 halves are scores relative to a warp-wide int32 `base` that is re-centred at
+//     every chunk of rows.  Neighbouring cells differ by at most M + |O+E| (affine-gap
+//     bound), all live cells of a warp lie within 64 rows x 64*C columns, so the span is
+//     bounded and the host only selects this kernel when it fits int16 with margin
+//     (psa16_fits).  Outside that domain the int32 kernels of psa_fill.cuh are used;
+//   * gap states are carried shifted by the open penalty (Et = Eg - (O+E), Ft = Fg - (O+E)),
+//     which makes every recurrence a single max(a + const, b):
+//         X  = H(i-1,j-1) + sub              VIADD.16x2
+//         hE = max(Et + (O+E), X)            VIADDMNMX.S16x2    = max(Eg, h)
+//         Ft'= max(Ft + E, hE)               VIADDMNMX.S16x2    the only serial op
+//         H  = max(Ft + (O+E), hE)           VIADDMNMX.S16x2
+//         Et'= max(Et + E, H)                VIADDMNMX.S16x2
+//   * boundary elements carry the ABSOLUTE scores modulo 2^16; the consumer re-centres them on
+//     its own base (exact, because the true value is within int16 of that base anyway).
+#pragma once
+#include "psa_fill.cuh"
+
+namespace tsta {
+
+constexpr int kRing16 = 128;          // row-table ring (rows)
+constexpr uint32_t kMin16x2 = 0x80008000u;
+constexpr int kPadLow = 15000;        // how far below its true value a pad column's diagonal input starts
+
+__device__ __forceinline__ uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+__device__ __forceinline__ uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
+__device__ __forceinline__ uint32_t prmtu(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// bitwise select: bits of a where m is set, bits of b elsewhere (one LOP3)
+__device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+// predicated tagged store of one boundary element given as two 32-bit halves
+__device__ __forceinline__ void st_relaxed_pair_if(unsigned long long* p, uint32_t lo, uint32_t hi, bool doit)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.b64 v, {%1, %2};\n\t"
+                 "@p st.relaxed.gpu.global.b64 [%0], v;\n\t}"
+                 ::"l"(p), "r"(lo), "r"(hi), "r"((unsigned)doit) : "memory");
+}
+template <class SM>
+__device__ __forceinline__ void ring16_put(SM& sm, int row, uint2 v)
+{
+    const int k = row & (kRing16 - 1);
+    sm.rowring[k] = v;
+    if (k < kMaxChunkRows) sm.rowring[kRing16 + k] = v;
+}
+
+// Per-warp shared-memory workspace of the packed sweep.
+template <int C, bool TRACE>
+struct __align__(16) PsaWarpSmem16 {
+    uint8_t dir[TRACE ? kDirRing * (64 * C / 2) : 16];   // ring of packed direction rows (64*C columns)
+    // [r & 127] = (table of row r, table of row r-32), 4 x int8 each; the first 32 entries are
+    // mirrored behind the ring so that "entry of row r0 + s" is ring[(r0 & 127) + s] with a
+    // compile-time s (no wrap inside a chunk)
+    uint2 rowring[kRing16 + kMaxChunkRows];
+    uint32_t in[kMaxChunkRows];  // left boundary of the current chunk: lo16 = H, hi16 = Ft, relative to base
+};
+
+// Per-lane register state.
+template <int C>
+struct PsaLane16 {
+    uint32_t Hup[C];     // H(i-1, .)            both halves relative to `base`
+    uint32_t Et[C];      // Eg(i, .) - (O+E)
+    uint32_t sel[C];     // PRMT selector: lo nibbles pick from the low row's table, hi from the high row's
+    uint32_t diag;       // H(i-1, j0-1)
+    uint32_t Hout, Fout; // right edge of the previous step (H, Ft)
+    uint32_t ms;         // running maximum since the last re-centring
+    uint2 Tnext;
+};
+
+// Does the packed form fit?  D1 = largest difference between neighbouring cells (M + |O+E|),
+// span = rows + columns a warp keeps live, S = score scale (2 with traceback).
+__host__ __device__ inline bool psa16_fits(int M, int X, int E, int O, int S, int C, int nsym)
+{
+    if (nsym > 4) return false;
+    const int aM = M < 0 ? -M : M, aX = X < 0 ? -X : X;
+    if (S * aM > 127 || S * aX > 127) return false;
+    const long long D1 = (long long)(M > 0 ? M : 0) - (O + E);          // |H(i,j) - H(i,j-1)| <= M + |O+E|
+    const long long span = 64LL * C + 64 + 2 * kMaxChunkRows + 16;      // columns + skew + chunk drift
+    // half of the int16 range: the other half is the head-room of kPadLow (see psa_sweep_band16)
+    return (long long)S * (D1 * span + aM + aX - 2LL * (O + E)) + 64 <= 15000;
+}
+
+// One wavefront step: row t-k of the low virtual lane and row t-k-32 of the high one.
+template <int C, bool TRACE, bool CHECK>
+__device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const int s, const int m, const int lane,
+                                           const uint32_t E2, const uint32_t OE2, const uint32_t selH, const uint32_t selF,
+                                           const int src_lane, const uint32_t in_addr, const uint32_t ring_next,
+                                           unsigned long long* bnd_row, const bool store_right,
+                                           const uint32_t outH, const uint32_t outF, const unsigned epoch)
+{
+    // in_addr: sm.in of this chunk; ring_next: ring entry of this lane's NEXT row at s = 0;
+    // bnd_row: boundary element of the row virtual lane 63 works on at s = 0
+    static_assert(!TRACE, "packed traceback fill comes with psa_step16t");
+    const uint32_t rH = __shfl_sync(kFullMask, L.Hout, src_lane);
+    const uint32_t rF = __shfl_sync(kFullMask, L.Fout, src_lane);
+    const uint32_t in = lds_u32(in_addr + s * 4);                 // broadcast: the band's left boundary
+    const uint2 T = L.Tnext;
+    L.Tnext = lds_u2(ring_next + s * 8);
+
+    // ---- F-independent pre-work -------------------------------------------------------------
+    uint32_t hE[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const uint32_t sub = prmtu(T.x, T.y, L.sel[c]);
+        const uint32_t X = vadd2(c == 0 ? L.diag : L.Hup[c - 1], sub);
+        hE[c] = vaddmax2(L.Et[c], OE2, X);                        // max(Eg, h)
+    }
+    const uint32_t Hin = prmtu(rH, in, selH);
+    uint32_t F = prmtu(rF, in, selF);
+
+    uint32_t mask = 0xffffffffu;
+    if (CHECK) {
+        const bool lo = (unsigned)(t - lane) < (unsigned)m, hi = (unsigned)(t - lane - 32) < (unsigned)m;
+        mask = (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
+    }
+    // ---- serial chain + epilogue ------------------------------------------------------------
+    uint32_t Hn[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const uint32_t Fc = F;
+        F = vaddmax2(Fc, E2, hE[c]);                              // Ft(i, j+1): the only serial op
+        Hn[c] = vaddmax2(Fc, OE2, hE[c]);                         // H = max(Fg, max(Eg, h))
+        const uint32_t En = vaddmax2(L.Et[c], E2, Hn[c]);
+        L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
+    }
+    uint32_t msn = L.ms;
+#pragma unroll
+    for (int c = 0; c + 1 < C; c += 2) msn = vmax3_2(msn, Hn[c], Hn[c + 1]);
+    if (C & 1) msn = __vmaxs2(msn, Hn[C - 1]);
+    if (CHECK) {
+#pragma unroll
+        for (int c = 0; c < C; c++) L.Hup[c] = bsel(mask, Hn[c], L.Hup[c]);
+        L.ms = bsel(mask, msn, L.ms);
+        L.diag = bsel(mask, Hin, L.diag);
+        L.Hout = bsel(mask, Hn[C - 1], L.Hout);
+        L.Fout = bsel(mask, F, L.Fout);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) L.Hup[c] = Hn[c];
+        L.ms = msn;
+        L.diag = Hin;
+        L.Hout = Hn[C - 1];
+        L.Fout = F;
+    }
+    // right edge of the band = high half of lane 31, row t-63; absolute scores modulo 2^16
+    {
+        const uint32_t e = prmtu(vadd2(L.Hout, outH), vadd2(L.Fout, outF), 0x7632u);
+        const bool doit = store_right && (!CHECK || (unsigned)(t - 63) < (unsigned)m);
+        st_relaxed_pair_if(bnd_row + s, e, epoch, doit);
+    }
+}
+
+// One band (64*C columns) of one pair.  Returns the band's maximum H in absolute units.
+template <int C, bool TRACE, bool PIPE, int CH>
+__device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScoring& sc, const uint32_t* tab4,
+                                                PsaWarpSmem16<C, TRACE>& sm, const int lane)
+{
+    constexpr int S = TRACE ? 2 : 1;
+    static_assert(CH == 16 || CH == 32, "chunk rows");
+    const int m = b.m;
+    const int Es = S * sc.E, OEs = S * (sc.O + sc.E);
+    const uint32_t E2 = dup16(Es), OE2 = dup16(OEs);
+    const int jlo = (b.band * 64 + lane) * C, jhi = jlo + 32 * C;
+
+    // ---- initial state: row -1 (psa.c:219-227), relative to base = H(-1, first column of the band)
+    int base = S * (sc.O + (b.band * 64 * C + 1) * sc.E);
+    PsaLane16<C> L;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int a = jlo + c, h = jhi + c;
+        const uint32_t cl = a < b.n ? sc.lut[b.s0[a]] : 8u;            // 8 = pad: sign byte of entry 0 (0 or -1)
+        const uint32_t chh = h < b.n ? 4u + sc.lut[b.s0[h]] : 12u;
+        const uint32_t nl = cl < 8u ? (cl | ((8u | cl) << 4)) : 0x88u;
+        const uint32_t nh = chh < 12u ? (chh | ((8u | chh) << 4)) : 0xccu;
+        L.sel[c] = nl | (nh << 8);
+        const int ha = S * (sc.O + (a + 1) * sc.E), hh = S * (sc.O + (h + 1) * sc.E);   // H(-1, j)
+        L.Et[c] = pack16(ha - base, hh - base);                    // Eg(0,j) = H(-1,j) + O + E (opened)
+        // Row -1 is only ever read as the DIAGONAL input of column j+1.  Pad columns (j >= n)
+        // score 0 or -1 instead of X (the PRMT table has no spare entry), so their diagonal
+        // input on row 0 starts kPadLow lower: every pad cell then stays below the real cell it
+        // derives from, and the running maximum may include pad cells (the reference includes
+        // its own pad columns too, psa.c:333).
+        L.Hup[c] = pack16(ha - base - (a + 1 >= b.n ? kPadLow : 0), hh - base - (h + 1 >= b.n ? kPadLow : 0));
+    }
+    {
+        const int da = S * (jlo == 0 ? 0 : sc.O + jlo * sc.E), dh = S * (sc.O + jhi * sc.E);   // H(-1, j0-1)
+        L.diag = pack16(da - base - (jlo >= b.n ? kPadLow : 0), dh - base - (jhi >= b.n ? kPadLow : 0));
+    }
+    L.ms = kMin16x2;
+    L.Hout = 0;
+    L.Fout = 0;
+    int ms32 = INT_MIN;
+
+    const int nsteps = m + 63;                                   // virtual lane 63 finishes row m-1 at step m+62
+    const int nchunks = (nsteps + CH - 1) / CH;
+    const bool export_right = (b.band + 1 < b.nbands) && b.bnd_out != nullptr;
+    const unsigned epoch = PIPE ? b.epoch : 1u;
+    const bool store_right = export_right && lane == 31;
+    const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in);
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
+    const uint32_t selH = lane == 0 ? 0x1054u : 0x3210u;         // lane 0: lo <- boundary H, hi <- lane 31's low half
+    const uint32_t selF = lane == 0 ? 0x1076u : 0x3210u;
+    const int src_lane = (lane + 31) & 31;
+    const int mrows = m + 32;                                    // rows whose table entry is read (high halves lag by 32)
+
+    // ---- prologue: row tables of chunk 0; prefetch for chunk 1 / boundary of chunk 0 -----------
+    __syncwarp();
+    const bool stager = lane < CH;
+    if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, 0u));   // rows < 32: no high row yet
+    uint32_t raw_next = (stager && CH + lane < m) ? b.s1[CH + lane] : 0xffffffffu;
+    unsigned long long bnd_next = 0;
+    if (b.band > 0 && stager && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
+    __syncwarp();
+    L.Tnext = sm.rowring[0];
+
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int t0 = ch * CH;
+        // ---- re-centre on lane 0's current row -------------------------------------------------
+        {
+            int delta = lo16(__shfl_sync(kFullMask, L.Et[0], 0));   // column j0 of the band is never a pad column
+            if (TRACE) delta &= ~1;
+            ms32 = max(ms32, max(lo16(L.ms), hi16(L.ms)) + base);   // (stale maxima of masked halves are harmless: they were real)
+            const uint32_t nd = dup16(-delta);
+#pragma unroll
+            for (int c = 0; c < C; c++) { L.Hup[c] = vadd2(L.Hup[c], nd); L.Et[c] = vadd2(L.Et[c], nd); }
+            L.diag = vadd2(L.diag, nd);
+            L.Hout = vadd2(L.Hout, nd);
+            L.Fout = vadd2(L.Fout, nd);
+            L.ms = kMin16x2;
+            base += delta;
+        }
+        // ---- stage: next chunk's row tables, this chunk's left boundary -------------------------
+        {
+            const int rown = t0 + CH + lane;                    // row of the next chunk
+            if (stager && rown < mrows) {
+                const uint32_t hi_tab = rown >= 32 ? sm.rowring[(rown - 32) & (kRing16 - 1)].x : 0u;
+                ring16_put(sm, rown, make_uint2(rown < m ? tab4[raw_next & 0xffu] : 0u, hi_tab));
+            }
+            const int rownn = rown + CH;
+            raw_next = (stager && rownn < m) ? b.s1[rownn] : 0u;
+            const int row = stager ? t0 + lane : m;
+            if (b.band > 0) {
+                if (PIPE) {
+                    while (!__all_sync(kFullMask, row >= m || (unsigned)(bnd_next >> 32) == epoch)) {
+                        __nanosleep(20);
+                        if (row < m && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
+                    }
+                }
+                // absolute modulo 2^16 -> relative to this warp's base; Ft = Fg - (O+E)
+                if (row < m) sm.in[lane] = vadd2((uint32_t)bnd_next, pack16(-base, -base - OEs));
+            } else if (row < m) {
+                const int hb = S * (sc.O + (row + 1) * sc.E) - base;   // H(i,-1); Fg(i,0) = H(i,-1)+O+E, so Ft = H(i,-1)
+                sm.in[lane] = pack16(hb, hb);
+            }
+            const int rowp = row + CH;
+            if (b.band > 0 && stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
+        }
+        __syncwarp();
+        const uint32_t outH = dup16(base), outF = dup16(base + OEs);
+        const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
+        unsigned long long* bnd_row = b.bnd_out + (t0 - 63);
+
+        if (t0 >= 63 && t0 + CH - 1 < m) {
+#pragma unroll
+            for (int s = 0; s < CH; s++)
+                psa_step16<C, TRACE, false>(L, t0 + s, s, m, lane, E2, OE2, selH, selF, src_lane, in_addr, ring_next,
+                                            bnd_row, store_right, outH, outF, epoch);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < CH; s++)
+                psa_step16<C, TRACE, true>(L, t0 + s, s, m, lane, E2, OE2, selH, selF, src_lane, in_addr, ring_next,
+                                           bnd_row, store_right, outH, outF, epoch);
+        }
+        __syncwarp();
+    }
+    ms32 = max(ms32, max(lo16(L.ms), hi16(L.ms)) + base);
+
+    if (b.lastrow) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            b.lastrow[jlo - b.lastrow_col0 + c] = lo16(L.Hup[c]) + base;
+            b.lastrow[jhi - b.lastrow_col0 + c] = hi16(L.Hup[c]) + base;
+        }
+    }
+    return ms32;
+}
+
+// 256-entry byte -> 4 x int8 substitution table (codes 0..3) for the packed PRMT.
+__device__ __forceinline__ void psa_build_tab4(uint32_t* tab4, const PsaScoring& sc, int S, int tid, int nthreads)
+{
+    const int Ms = S * sc.M, Xs = S * sc.X;
+    for (int bb = tid; bb < 256; bb += nthreads) {
+        const uint32_t c = sc.lut[bb];
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (uint32_t)(((uint32_t)k == c ? Ms : Xs) & 0xff) << (8 * k);
+        tab4[bb] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// one long pair: one warp (= one CTA) per band of 64*C columns
+// ---------------------------------------------------------------------------------------
+template <int C, bool TRACE, int CH>
+__global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ PsaPairArgs a)
+{
+    __shared__ PsaWarpSmem16<C, TRACE> sm;
+    __shared__ uint32_t tab4[256];
+    const int lane = threadIdx.x;
+    int band = 0;
+    if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
+    band = __shfl_sync(kFullMask, band, 0);
+    psa_build_tab4(tab4, a.sc, TRACE ? 2 : 1, lane, 32);
+    __syncwarp();
+
+    PsaBand b;
+    b.s0 = a.s0; b.s1 = a.s1; b.n = a.n; b.m = a.m;
+    b.band = band; b.nbands = a.nbands;
+    b.bnd_in = a.bnd + (long long)(band - 1) * a.bnd_stride;
+    b.bnd_out = a.bnd + (long long)band * a.bnd_stride;
+    b.epoch = a.epoch;
+    b.dirs = a.dirs; b.dirs_stride = a.dirs_stride;
+    b.lastrow = a.lastrow; b.lastrow_col0 = 0;
+    int ms = psa_sweep_band16<C, TRACE, true, CH>(b, a.sc, tab4, sm, lane);
+    ms = warp_max(ms);
+    if (lane == 0) atomicMax(a.out_max, ms);
+}
+
+// ---------------------------------------------------------------------------------------
+// a batch of independent pairs: persistent warps, one pair at a time per warp
+// ---------------------------------------------------------------------------------------
+template <int C, bool TRACE, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) psa_batch16_kernel(const __grid_constant__ PsaBatchArgs a)
+{
+    constexpr int S = TRACE ? 2 : 1;
+    __shared__ PsaWarpSmem16<C, TRACE> sm[WARPS];
+    __shared__ uint32_t tab4[256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    psa_build_tab4(tab4, a.sc, S, threadIdx.x, 32 * WARPS);
+    __syncthreads();
+    const long long gw = (long long)blockIdx.x * WARPS + w;
+    unsigned long long* scratch = a.scratch + gw * a.scratch_stride;
+    int* lastrow = a.lastrow + gw * (64 * C);
+
+    while (true) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(a.ticket, 1ull);
+        k = __shfl_sync(kFullMask, k, 0);
+        if (k >= (unsigned long long)a.npairs) break;
+        const int n = a.len0[k], m = a.len1[k];
+        const int nbands = (n + 64 * C - 1) / (64 * C);
+        PsaBand b;
+        b.s0 = a.seqs0 + a.off0[k]; b.s1 = a.seqs1 + a.off1[k];
+        b.n = n; b.m = m; b.nbands = nbands;
+        // in place: row r of the parked column is prefetched at chunk r/CH - 1 and rewritten at
+        // step r+63 (see psa_fill.cuh: psa_batch_kernel)
+        b.bnd_in = scratch; b.bnd_out = scratch;
+        b.epoch = 1u;
+        b.dirs = TRACE ? a.dirs + a.dirs_off[k] : nullptr;
+        b.dirs_stride = (long long)nbands * (64 * C / 2);
+        b.lastrow_col0 = (nbands - 1) * 64 * C;
+        int ms = INT_MIN;
+        if (m > 0) {
+            for (int band = 0; band < nbands; band++) {
+                b.band = band;
+                b.lastrow = (band == nbands - 1) ? lastrow : nullptr;
+                ms = max(ms, psa_sweep_band16<C, TRACE, false, 32>(b, a.sc, tab4, sm[w], lane));
+            }
+        }
+        ms = warp_max(ms);
+        __syncwarp();
+        if (lane == 0) {
+            const bool real = n > 0 && m > 0;
+            a.maxsorce[k] = real ? max(-100, ms / S) : -100;   // seed: psa.c:110,590
+            a.corner[k] = real ? __ldcg(lastrow + (n - 1) - b.lastrow_col0) / S : 0;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace tsta

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "psa_fill.cuh"
+#include "psa_fill16.cuh"
 #include "psa_trace.cuh"
 
 namespace tsta {
@@ -100,6 +101,8 @@ struct tsta_psa_plan {
     int64_t n = 0, m = 0;
     int n_pad = 0, nbands = 0, C = 4, CH = 16;
     bool prmt = true;
+    bool packed = false;           // int16 x 2 kernels (psa_fill16.cuh); else int32 (psa_fill.cuh)
+    int nsym = 0;
     bool uploaded = false, ran = false;
     int launches = 0;
     unsigned epoch = 0;            // boundary tag of the last run (see psa_fill.cuh: bnd_pack)
@@ -135,6 +138,22 @@ static void launch_pair(const tsta_psa_plan* p, const PsaPairArgs& fa)
         if (p->prmt) psa_pair_kernel<C, TRACE, true, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
         else psa_pair_kernel<C, TRACE, false, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
     }
+}
+
+template <int C, bool TRACE>
+static void launch_pair16(const tsta_psa_plan* p, const PsaPairArgs& fa)
+{
+    if (p->CH == 32) psa_pair16_kernel<C, TRACE, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    else psa_pair16_kernel<C, TRACE, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
+}
+
+// Packed kernels: 64*C columns per band; the smallest strip that keeps one band per SM
+// sub-partition, as below.
+static int choose_strip16(int64_t n, int sms)
+{
+    const int64_t slots = (int64_t)sms * 4;
+    for (int c : {2, 3, 4, 6}) if (n <= 64 * c * slots) return c;
+    return 8;
 }
 
 // Lane strip width for one long pair: the pipeline runs at the speed of its slowest band,
@@ -223,26 +242,9 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     // tuning overrides for experiments (not part of the ABI)
     if (const char* e = getenv("TSTA_PSA_C")) { const int c = atoi(e); if (c == 4 || c == 8 || c == 16 || (c == 6 && !p->want_trace)) p->C = c; }
     if (const char* e = getenv("TSTA_PSA_CH")) { const int c = atoi(e); if (c == 8 || c == 16 || c == 32) p->CH = c; }
-    const int band_cols = 32 * p->C;
-    p->nbands = (int)((n + band_cols - 1) / band_cols);
-    p->n_pad = p->nbands * band_cols;
-
     if (int rc = p->d_s0.reserve((size_t)n)) return rc;
     if (int rc = p->d_s1.reserve((size_t)m)) return rc;
-    {   // boundary columns: tagged elements, so fresh memory must start out all-zero (tag 0)
-        const size_t need = (size_t)p->nbands * (size_t)m * sizeof(unsigned long long);
-        if (need > p->d_bnd.cap) {
-            if (int rc = p->d_bnd.reserve(need + need / 4)) return rc;
-            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
-            p->epoch = 0;
-        }
-    }
     if (int rc = p->d_ctl.reserve(16 * sizeof(int))) return rc;
-    if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
-    if (p->want_trace) {
-        if (int rc = p->d_dirs.reserve((size_t)m * (size_t)(p->n_pad / 2))) return rc;
-        if (int rc = p->d_ops.reserve((size_t)(n + m))) return rc;
-    }
     int* ctl = p->d_ctl.as<int>();
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_s0.p, s0, (size_t)n, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_s1.p, s1, (size_t)m, cudaMemcpyHostToDevice, p->stream));
@@ -254,7 +256,36 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small + 8, ctl + 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
     const int K = build_lut(reinterpret_cast<unsigned*>(p->h_small + 8), p->sc.lut);
+    p->nsym = K;
     p->prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
+    // packed int16 kernels when the alphabet and the score range allow (psa16_fits)
+    p->packed = false;
+    if (!p->want_trace) {
+        int c16 = choose_strip16(n, p->sms);
+        if (const char* e = getenv("TSTA_PSA_C16")) { const int c = atoi(e); if (c == 2 || c == 3 || c == 4 || c == 6 || c == 8) c16 = c; }
+        const char* off = getenv("TSTA_PSA_PACKED");
+        if (!(off && atoi(off) == 0) && psa16_fits(prm->M, prm->X, prm->E, prm->O, S, c16, K)) {
+            p->packed = true;
+            p->C = c16;
+        }
+    }
+    const int band_cols = (p->packed ? 64 : 32) * p->C;
+    p->nbands = (int)((n + band_cols - 1) / band_cols);
+    p->n_pad = p->nbands * band_cols;
+
+    {   // boundary columns: tagged elements, so fresh memory must start out all-zero (tag 0)
+        const size_t need = (size_t)p->nbands * (size_t)m * sizeof(unsigned long long);
+        if (need > p->d_bnd.cap) {
+            if (int rc = p->d_bnd.reserve(need + need / 4)) return rc;
+            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+            p->epoch = 0;
+        }
+    }
+    if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
+    if (p->want_trace) {
+        if (int rc = p->d_dirs.reserve((size_t)m * (size_t)(p->n_pad / 2))) return rc;
+        if (int rc = p->d_ops.reserve((size_t)(n + m))) return rc;
+    }
     p->uploaded = true;
     return TSTA_OK;
 }
@@ -296,6 +327,12 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
         if (p->C == 4) launch_pair<4, true>(p, fa);
         else if (p->C == 8) launch_pair<8, true>(p, fa);
         else launch_pair<16, true>(p, fa);
+    } else if (p->packed) {
+        if (p->C == 2) launch_pair16<2, false>(p, fa);
+        else if (p->C == 3) launch_pair16<3, false>(p, fa);
+        else if (p->C == 4) launch_pair16<4, false>(p, fa);
+        else if (p->C == 6) launch_pair16<6, false>(p, fa);
+        else launch_pair16<8, false>(p, fa);
     } else {
         if (p->C == 4) launch_pair<4, false>(p, fa);
         else if (p->C == 6) launch_pair<6, false>(p, fa);
@@ -409,6 +446,8 @@ int tsta_psa_plan_info(tsta_psa_plan* p, int* launches, int* cols_per_lane, int*
     if (bands) *bands = p->nbands;
     return TSTA_OK;
 }
+
+int tsta_psa_plan_packed(tsta_psa_plan* p) { return p && p->packed ? 1 : 0; }
 
 void tsta_psa_result_free(tsta_psa_result* r)
 {

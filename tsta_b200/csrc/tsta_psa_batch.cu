@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "psa_fill.cuh"
+#include "psa_fill16.cuh"
 #include "psa_trace.cuh"
 
 namespace tsta {
@@ -81,8 +82,6 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         if (want_trace) ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
     }
     const int S = want_trace ? 2 : 1;
-    const int C = (max0 <= 128) ? 4 : 8;
-    const int band_cols = 32 * C;
 
     int dev = 0, sms = 0;
     TSTA_CUDA_TRY(cudaGetDevice(&dev));
@@ -124,6 +123,13 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     a.sc.M = prm->M; a.sc.X = prm->X; a.sc.E = prm->E; a.sc.O = prm->O;
     const int K = build_lut(present, a.sc.lut);
     const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
+    // packed int16 kernels (psa_fill16.cuh) when alphabet and score range allow; 64*C columns per band
+    const int C16 = (max0 <= 128) ? 2 : (max0 <= 256 ? 4 : 8);
+    const char* off16 = getenv("TSTA_PSA_PACKED");
+    const bool packed = !want_trace && !(off16 && atoi(off16) == 0) &&
+                        psa16_fits(prm->M, prm->X, prm->E, prm->O, S, C16, K);
+    const int C = packed ? C16 : ((max0 <= 128) ? 4 : 8);
+    const int band_cols = (packed ? 64 : 32) * C;
 
     // persistent grid: ~24 warps per SM (register-limited), never more warps than pairs
     int blocks = sms * 6;
@@ -205,6 +211,10 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
             t.cols_per_band = band_cols;
             t.ops = d_ops; t.ops_off = d_ops_off + k0; t.alen = d_alen + k0;
             psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
+        } else if (packed) {
+            if (C == 2) psa_batch16_kernel<2, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            else if (C == 4) psa_batch16_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            else psa_batch16_kernel<8, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
         } else {
             if (C == 4) launch_batch<4, false, kBatchWarps>(prmt, blocks, g.st, a);
             else launch_batch<8, false, kBatchWarps>(prmt, blocks, g.st, a);
