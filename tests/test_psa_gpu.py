@@ -109,15 +109,17 @@ def test_many_symbols_uses_generic_compare_path(gpu):
     assert r.output_bytes() == o.output_bytes() and r.maxsorce == o.maxsorce
 
 
-@pytest.mark.parametrize("n,cols", [(120_000, 8), (303_200, 16)])
-def test_wide_strip_variants_long_s0(gpu, n, cols):
-    """Longer s0 switches lanes to 8 / 16 columns; few rows keep the oracle fast."""
+@pytest.mark.parametrize("n,cols,packed", [(120_000, 8, False), (303_200, 16, False), (120_000, 4, True), (303_200, 8, True)])
+def test_wide_strip_variants_long_s0(gpu, n, cols, packed, monkeypatch):
+    """Longer s0 switches lanes to wider strips (int32: 8 / 16 columns, packed: 4 / 8); few
+    rows keep the oracle fast."""
+    monkeypatch.setenv("TSTA_PSA_PACKED", "1" if packed else "0")
     x, y = synth.read_pair(n, 40, 42)
     o = ob.psa(x, y, want_lastrow=True)
     plan = gpu.PsaPlan(True)
     plan.upload(x, y)
     plan.run()
-    assert plan.info()["cols_per_lane"] == cols
+    assert plan.info()["cols_per_lane"] == cols and plan.info()["packed"] == packed
     r = plan.fetch()
     assert (r.maxsorce, r.corner) == (o.maxsorce, o.corner)
     np.testing.assert_array_equal(plan.lastrow(), o.lastrow)

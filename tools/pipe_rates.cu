@@ -25,6 +25,13 @@ __global__ void __launch_bounds__(256) k(int iters, int seed, int* sink)
                 if (OP == 7) a[i] = __viaddmax_s16x2(a[i], s, f + i);      // packed
                 if (OP == 8) asm volatile("mad.lo.s32 %0, %0, 1, %1;" : "+r"(a[i]) : "r"(s + i)); // IMAD as add
                 if (OP == 9) a[i] = (a[i] > f + i + u) ? s : a[i];        // ISETP+SEL
+                if (OP == 10) a[i] = __vadd2(a[i], s + i);                 // VIADD.16x2
+                if (OP == 11) a[i] = __vmaxs2(a[i], f + i + u);            // VIMNMX.S16x2
+                if (OP == 12) a[i] = __vimax3_s16x2(a[i], f + i, s + u);   // VIMNMX3.S16x2
+                if (OP == 13) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(s + i), "r"(f));  // LOP3 (xor3)
+                if (OP == 14) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(s), "r"(f + i));     // IMAD
+                if (OP == 15) asm volatile("add.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(s + i));                   // IADD
+                if (OP == 16) asm volatile("shl.b32 %0, %0, 1;" : "+r"(a[i]));                                 // SHF/IMAD.SHL
             }
         }
     }
@@ -53,5 +60,7 @@ int main()
 {
     run<0>("viaddmax"); run<1>("vimnmx"); run<2>("vimnmx3"); run<3>("iadd"); run<4>("prmt");
     run<5>("imad"); run<6>("lop3"); run<7>("viaddmax16x2"); run<8>("imad_add"); run<9>("isetp+sel");
+    run<10>("viadd16x2"); run<11>("vimnmx16x2"); run<12>("vimnmx3_16x2"); run<13>("lop3_asm"); run<14>("imad_asm");
+    run<15>("iadd_asm"); run<16>("shl_asm");
     return 0;
 }

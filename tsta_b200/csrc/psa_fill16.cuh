@@ -26,6 +26,19 @@
 //         Et'= max(Et + E, H)                VIADDMNMX.S16x2
 //   * boundary elements carry the ABSOLUTE scores modulo 2^16; the consumer re-centres them on
 //     its own base (exact, because the true value is within int16 of that base anyway).
+//
+// Traceback variant (TRACE): scores are carried times FOUR, which frees two low bits per value.
+//   * the three candidates of H are tagged with their tie-break priority (psa.c:294-298: diagonal
+//     beats F beats E): H' = max3(4h+3, 4Fg+2, 4Eg+1) -- ONE VIMNMX3.S16x2 -- and the winner's tag
+//     is the `back` code (3 diagonal, 2 left, 1 up);
+//   * gap states carry "opened, not extended" in bit 1 (the reference's fback/eback == +-2):
+//     with a = gap+E and t = H+O+E the next state is max(4a, 4t+2);
+//   * the reference's rule "keep extending" (trace(), psa.c:450-459; cF/cE of SURVEY.md 8c) is
+//     4a + 2*opened >= 4t+2, which is bit 0 of max(state + 4E + 1, 4t+2): one more VIADDMNMX each
+//     for E and F, no compare/select at all;
+//   * the 4-bit codes of a lane's C columns are assembled with IMADs (FMA pipe) and leave through
+//     a shared-memory ring indexed by STEP (one store per step, no address arithmetic); the flush
+//     that writes whole rows to HBM with 128-bit stores does the lane -> row transposition.
 #pragma once
 #include "psa_fill.cuh"
 
@@ -33,7 +46,7 @@ namespace tsta {
 
 constexpr int kRing16 = 128;          // row-table ring (rows)
 constexpr uint32_t kMin16x2 = 0x80008000u;
-constexpr int kPadLow = 15000;        // how far below its true value a pad column's diagonal input starts
+constexpr int kDirSteps = 128;        // TRACE: ring of per-step direction words (steps)
 
 __device__ __forceinline__ uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
@@ -74,7 +87,9 @@ __device__ __forceinline__ void ring16_put(SM& sm, int row, uint2 v)
 // Per-warp shared-memory workspace of the packed sweep.
 template <int C, bool TRACE>
 struct __align__(16) PsaWarpSmem16 {
-    uint8_t dir[TRACE ? kDirRing * (64 * C / 2) : 16];   // ring of packed direction rows (64*C columns)
+    // TRACE: [step & 127][lane] direction words of one step: C <= 4: one word (low 16 bits = the
+    // low virtual lane's C codes, high 16 bits = the high one's); C == 8: two words (low, high)
+    uint32_t dirw[TRACE ? kDirSteps * 32 * (C == 8 ? 2 : 1) : 4];
     // [r & 127] = (table of row r, table of row r-32), 4 x int8 each; the first 32 entries are
     // mirrored behind the ring so that "entry of row r0 + s" is ring[(r0 & 127) + s] with a
     // compile-time s (no wrap inside a chunk)
@@ -92,101 +107,215 @@ struct PsaLane16 {
     uint32_t Hout, Fout; // right edge of the previous step (H, Ft)
     uint32_t ms;         // running maximum since the last re-centring
     uint2 Tnext;
+    uint32_t cEb[C];     // TRACE: bit 0 / bit 16 = cE of the NEXT row of this column
 };
 
 // Does the packed form fit?  D1 = largest difference between neighbouring cells (M + |O+E|),
 // span = rows + columns a warp keeps live, S = score scale (2 with traceback).
+__host__ __device__ inline int psa16_pad_low(int M, int X, int E, int O, int S)
+{
+    // how far below its true value the diagonal input of a pad column starts on row 0 (see
+    // psa_sweep_band16): enough to stay below "real neighbour + X" whatever the pad's own score is
+    const int aM = M < 0 ? -M : M, aX = X < 0 ? -X : X;
+    return S * (aM + aX - 2 * (O + E) + 2);
+}
 __host__ __device__ inline bool psa16_fits(int M, int X, int E, int O, int S, int C, int nsym)
 {
     if (nsym > 4) return false;
     const int aM = M < 0 ? -M : M, aX = X < 0 ? -X : X;
-    if (S * aM > 127 || S * aX > 127) return false;
+    if (S * aM + 3 > 127 || S * aX + 3 > 127) return false;
     const long long D1 = (long long)(M > 0 ? M : 0) - (O + E);          // |H(i,j) - H(i,j-1)| <= M + |O+E|
     const long long span = 64LL * C + 64 + 2 * kMaxChunkRows + 16;      // columns + skew + chunk drift
-    // half of the int16 range: the other half is the head-room of kPadLow (see psa_sweep_band16)
-    return (long long)S * (D1 * span + aM + aX - 2LL * (O + E)) + 64 <= 15000;
+    return (long long)S * (D1 * span + aM + aX - 2LL * (O + E)) + psa16_pad_low(M, X, E, O, S) + 64 <= 30000;
 }
 
+// Scoring constants of a sweep, packed in both halves.
+struct PsaConst16 {
+    uint32_t E2;      // score-only: E;    TRACE: 4E-1
+    uint32_t OE2;     // score-only: O+E;  TRACE: 4(O+E)+2 ("opened")
+    uint32_t Kf2;     // TRACE: max(4E, 4(O+E)+2) - 2
+    uint32_t E1;      // TRACE: 4E+1
+};
+constexpr uint32_t kM1 = 0x00010001u, kM2 = 0x00020002u, kM3 = 0x00030003u;
+
 // One wavefront step: row t-k of the low virtual lane and row t-k-32 of the high one.
+//   in_addr   sm.in of this chunk (entry s = the band's left boundary of row t)
+//   ring_next ring entry of this lane's NEXT row at s = 0
+//   bnd_row   boundary element of the row virtual lane 63 works on at s = 0
+//   dir_addr  TRACE: this lane's direction word of step s = 0 in the step ring
 template <int C, bool TRACE, bool CHECK>
 __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const int s, const int m, const int lane,
-                                           const uint32_t E2, const uint32_t OE2, const uint32_t selH, const uint32_t selF,
+                                           const PsaConst16& k, const uint32_t selH, const uint32_t selF,
                                            const int src_lane, const uint32_t in_addr, const uint32_t ring_next,
                                            unsigned long long* bnd_row, const bool store_right,
-                                           const uint32_t outH, const uint32_t outF, const unsigned epoch)
+                                           const uint32_t outHF, const unsigned epoch, const uint32_t dir_addr)
 {
-    // in_addr: sm.in of this chunk; ring_next: ring entry of this lane's NEXT row at s = 0;
-    // bnd_row: boundary element of the row virtual lane 63 works on at s = 0
-    static_assert(!TRACE, "packed traceback fill comes with psa_step16t");
     const uint32_t rH = __shfl_sync(kFullMask, L.Hout, src_lane);
     const uint32_t rF = __shfl_sync(kFullMask, L.Fout, src_lane);
     const uint32_t in = lds_u32(in_addr + s * 4);                 // broadcast: the band's left boundary
     const uint2 T = L.Tnext;
     L.Tnext = lds_u2(ring_next + s * 8);
 
-    // ---- F-independent pre-work -------------------------------------------------------------
-    uint32_t hE[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        const uint32_t sub = prmtu(T.x, T.y, L.sel[c]);
-        const uint32_t X = vadd2(c == 0 ? L.diag : L.Hup[c - 1], sub);
-        hE[c] = vaddmax2(L.Et[c], OE2, X);                        // max(Eg, h)
-    }
-    const uint32_t Hin = prmtu(rH, in, selH);
-    uint32_t F = prmtu(rF, in, selF);
-
     uint32_t mask = 0xffffffffu;
     if (CHECK) {
         const bool lo = (unsigned)(t - lane) < (unsigned)m, hi = (unsigned)(t - lane - 32) < (unsigned)m;
         mask = (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
     }
-    // ---- serial chain + epilogue ------------------------------------------------------------
     uint32_t Hn[C];
+    uint32_t Hin, F;
+
+    if constexpr (!TRACE) {
+        // ---- F-independent pre-work ---------------------------------------------------------
+        uint32_t hE[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-        const uint32_t Fc = F;
-        F = vaddmax2(Fc, E2, hE[c]);                              // Ft(i, j+1): the only serial op
-        Hn[c] = vaddmax2(Fc, OE2, hE[c]);                         // H = max(Fg, max(Eg, h))
-        const uint32_t En = vaddmax2(L.Et[c], E2, Hn[c]);
-        L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
+        for (int c = 0; c < C; c++) {
+            const uint32_t sub = prmtu(T.x, T.y, L.sel[c]);
+            const uint32_t X = vadd2(c == 0 ? L.diag : L.Hup[c - 1], sub);
+            hE[c] = vaddmax2(L.Et[c], k.OE2, X);                  // max(Eg, h)
+        }
+        Hin = prmtu(rH, in, selH);
+        F = prmtu(rF, in, selF);
+        // ---- serial chain + epilogue --------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t Fc = F;
+            F = vaddmax2(Fc, k.E2, hE[c]);                        // Ft(i, j+1): the only serial op
+            Hn[c] = vaddmax2(Fc, k.OE2, hE[c]);                   // H = max(Fg, max(Eg, h))
+            const uint32_t En = vaddmax2(L.Et[c], k.E2, Hn[c]);
+            L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
+        }
+    } else {
+        // ---- F-independent pre-work ---------------------------------------------------------
+        // tags in the two low bits: 4h+3 (the table entries carry the +3), 4Fg+2, 4Eg+1
+        uint32_t hEt[C], Ec1[C], g[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t hs3 = vadd2(c == 0 ? L.diag : L.Hup[c - 1], prmtu(T.x, T.y, L.sel[c]));
+            Ec1[c] = (L.Et[c] & ~kM3) | kM1;                      // L.Et holds the flagged Eg state here
+            hEt[c] = __vmaxs2(hs3, Ec1[c]);                       // max(h, Eg), diagonal wins ties
+            g[c] = vadd2(hEt[c] & ~kM3, k.OE2);                   // 4(max(h,Eg)+O+E)+2
+        }
+        const uint32_t Hraw = prmtu(rH, in, selH);                // bit 0 / 16: cF of this lane's first column
+        Hin = Hraw & ~kM3;
+        F = prmtu(rF, in, selF);                                  // flagged Fg state
+        uint32_t f1 = Hraw & kM1;
+        // ---- serial chain + epilogue --------------------------------------------------------
+        uint32_t acc[(C + 3) / 4];
+#pragma unroll
+        for (int q = 0; q < (C + 3) / 4; q++) acc[q] = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t Fin = F;
+            const uint32_t Fc2 = Fin | kM2;                       // 4Fg+2
+            F = vaddmax2(Fc2, k.Kf2, g[c]);                       // max(4a, 4t+2)   (Kf2 holds Kf - 2)
+            const uint32_t Hp = __vmaxs2(hEt[c], Fc2);            // winner tagged 3 / 2 / 1: psa.c:294-298
+            Hn[c] = Hp & ~kM3;
+            const uint32_t T2 = vadd2(Hn[c], k.OE2);              // 4(H+O+E)+2
+            const uint32_t En = vaddmax2(Ec1[c], k.E2, T2);       // (E2 holds 4E - 1)
+            const uint32_t WE = vaddmax2(L.Et[c], k.E1, T2);      // bit 0: extending Eg wins or ties-after-open
+            const uint32_t WF = vaddmax2(Fin, k.E1, T2);          // same for Fg: cF of column j+1
+            // code = back | cF << 2 | cE << 3, at nibble c of each half
+            const uint32_t x = f1 * 4u + (Hp & kM3) + L.cEb[c] * 8u;
+            acc[c / 4] += x << (4 * (c & 3));
+            f1 = WF & kM1;
+            const uint32_t e1 = WE & kM1;
+            L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
+            L.cEb[c] = CHECK ? bsel(mask, e1, L.cEb[c]) : e1;
+        }
+        // direction words of this step -> step ring (garbage of inactive halves is never flushed)
+        if (C == 8) sts_u2(dir_addr + s * 256, prmtu(acc[0], acc[1], 0x5410u), prmtu(acc[0], acc[1], 0x7632u));
+        else sts_u32(dir_addr + s * 128, acc[0]);
+        // the cF flag of the next lane's first column rides in bit 0 of the H hand-off
+        L.Hout = f1;                                              // merged below
     }
     uint32_t msn = L.ms;
 #pragma unroll
     for (int c = 0; c + 1 < C; c += 2) msn = vmax3_2(msn, Hn[c], Hn[c + 1]);
     if (C & 1) msn = __vmaxs2(msn, Hn[C - 1]);
+    const uint32_t Ho = TRACE ? (Hn[C - 1] | L.Hout) : Hn[C - 1];
     if (CHECK) {
 #pragma unroll
         for (int c = 0; c < C; c++) L.Hup[c] = bsel(mask, Hn[c], L.Hup[c]);
         L.ms = bsel(mask, msn, L.ms);
         L.diag = bsel(mask, Hin, L.diag);
-        L.Hout = bsel(mask, Hn[C - 1], L.Hout);
+        L.Hout = bsel(mask, Ho, TRACE ? 0u : L.Hout);
         L.Fout = bsel(mask, F, L.Fout);
     } else {
 #pragma unroll
         for (int c = 0; c < C; c++) L.Hup[c] = Hn[c];
         L.ms = msn;
         L.diag = Hin;
-        L.Hout = Hn[C - 1];
+        L.Hout = Ho;
         L.Fout = F;
     }
-    // right edge of the band = high half of lane 31, row t-63; absolute scores modulo 2^16
+    // right edge of the band = high halves of lane 31, row t-63: (H | Fg << 16) absolute modulo 2^16
     {
-        const uint32_t e = prmtu(vadd2(L.Hout, outH), vadd2(L.Fout, outF), 0x7632u);
+        const uint32_t e = vadd2(prmtu(L.Hout, L.Fout, 0x7632u), outHF);
         const bool doit = store_right && (!CHECK || (unsigned)(t - 63) < (unsigned)m);
         st_relaxed_pair_if(bnd_row + s, e, epoch, doit);
     }
 }
 
-// One band (64*C columns) of one pair.  Returns the band's maximum H in absolute units.
+// Writes the finished direction rows [lo, hi) of one band from the step ring to HBM: row r of
+// virtual lane v was produced at step r + v.  16-byte units, lane u handles units u, u+32, ...
+template <int C>
+__device__ __forceinline__ void psa_flush_dirs16(const uint32_t* dirw, const PsaBand& b, int lo, int hi, int lane)
+{
+    constexpr int kRowBytes = 32 * C;                   // 64*C columns, 4 bits each
+    constexpr int kUnits = kRowBytes / 16;
+    constexpr int kW = C == 8 ? 2 : 1;                  // words per lane per step
+    const int units = (hi - lo) * kUnits;
+    for (int u = lane; u < units; u += 32) {
+        const int r = lo + u / kUnits, part = u % kUnits;
+        uint32_t w[4];
+        if (C == 8) {           // 4 bytes per virtual lane: 4 virtual lanes per unit
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int v = part * 4 + q;
+                w[q] = dirw[(((r + v) & (kDirSteps - 1)) * 32 + (v & 31)) * kW + (v >> 5)];
+            }
+        } else if (C == 4) {    // 2 bytes per virtual lane: 8 per unit
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int v0 = part * 8 + 2 * q, v1 = v0 + 1;
+                const uint32_t a = dirw[((r + v0) & (kDirSteps - 1)) * 32 + (v0 & 31)];
+                const uint32_t c = dirw[((r + v1) & (kDirSteps - 1)) * 32 + (v1 & 31)];
+                const uint32_t la = (v0 >> 5) ? (a >> 16) : (a & 0xffffu), lc = (v1 >> 5) ? (c >> 16) : (c & 0xffffu);
+                w[q] = la | (lc << 16);
+            }
+        } else {                // C == 2: 1 byte per virtual lane: 16 per unit
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int v = part * 16 + 4 * q + e;
+                    const uint32_t a = dirw[((r + v) & (kDirSteps - 1)) * 32 + (v & 31)];
+                    x |= (((v >> 5) ? (a >> 16) : a) & 0xffu) << (8 * e);
+                }
+                w[q] = x;
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(b.dirs + (long long)r * b.dirs_stride + (long long)b.band * kRowBytes + part * 16);
+        __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+}
+
+// One band (64*C columns) of one pair.  Returns the band's maximum H in absolute (scaled) units.
 template <int C, bool TRACE, bool PIPE, int CH>
 __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScoring& sc, const uint32_t* tab4,
                                                 PsaWarpSmem16<C, TRACE>& sm, const int lane)
 {
-    constexpr int S = TRACE ? 2 : 1;
+    constexpr int S = TRACE ? 4 : 1;
     static_assert(CH == 16 || CH == 32, "chunk rows");
+    static_assert(!TRACE || C == 2 || C == 4 || C == 8, "traced strips pack to 8 / 16 / 32 bits per virtual lane");
     const int m = b.m;
-    const int Es = S * sc.E, OEs = S * (sc.O + sc.E);
-    const uint32_t E2 = dup16(Es), OE2 = dup16(OEs);
+    const int Es = S * sc.E, OEs = S * (sc.O + sc.E) + (TRACE ? 2 : 0);
+    PsaConst16 k;
+    // TRACE folds the candidates' tags into the constants: Eg+1 extends by 4E-1, Fg+2 by Kf-2
+    k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.Kf2 = dup16(max(Es, OEs) - 2); k.E1 = dup16(Es + 1);
+    const int shiftOE = TRACE ? 0 : OEs;                         // score-only: gap states are carried minus (O+E)
+    const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, S);
     const int jlo = (b.band * 64 + lane) * C, jhi = jlo + 32 * C;
 
     // ---- initial state: row -1 (psa.c:219-227), relative to base = H(-1, first column of the band)
@@ -201,17 +330,20 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         const uint32_t nh = chh < 12u ? (chh | ((8u | chh) << 4)) : 0xccu;
         L.sel[c] = nl | (nh << 8);
         const int ha = S * (sc.O + (a + 1) * sc.E), hh = S * (sc.O + (h + 1) * sc.E);   // H(-1, j)
-        L.Et[c] = pack16(ha - base, hh - base);                    // Eg(0,j) = H(-1,j) + O + E (opened)
+        // Eg(0,j) = H(-1,j) + O + E, opened.  score-only: stored minus (O+E); TRACE: flagged
+        const int eo = OEs - shiftOE;
+        L.Et[c] = pack16(ha + eo - base, hh + eo - base);
+        L.cEb[c] = 0;
         // Row -1 is only ever read as the DIAGONAL input of column j+1.  Pad columns (j >= n)
         // score 0 or -1 instead of X (the PRMT table has no spare entry), so their diagonal
-        // input on row 0 starts kPadLow lower: every pad cell then stays below the real cell it
-        // derives from, and the running maximum may include pad cells (the reference includes
-        // its own pad columns too, psa.c:333).
-        L.Hup[c] = pack16(ha - base - (a + 1 >= b.n ? kPadLow : 0), hh - base - (h + 1 >= b.n ? kPadLow : 0));
+        // input on row 0 starts `padlow` lower: every pad cell then stays below the real cell
+        // it derives from, and the running maximum may include pad cells (the reference
+        // includes its own pad columns too, psa.c:333).
+        L.Hup[c] = pack16(ha - base - (a + 1 >= b.n ? padlow : 0), hh - base - (h + 1 >= b.n ? padlow : 0));
     }
     {
         const int da = S * (jlo == 0 ? 0 : sc.O + jlo * sc.E), dh = S * (sc.O + jhi * sc.E);   // H(-1, j0-1)
-        L.diag = pack16(da - base - (jlo >= b.n ? kPadLow : 0), dh - base - (jhi >= b.n ? kPadLow : 0));
+        L.diag = pack16(da - base - (jlo >= b.n ? padlow : 0), dh - base - (jhi >= b.n ? padlow : 0));
     }
     L.ms = kMin16x2;
     L.Hout = 0;
@@ -225,6 +357,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     const bool store_right = export_right && lane == 31;
     const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in);
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
+    const uint32_t dirw_addr = (uint32_t)__cvta_generic_to_shared(sm.dirw) + lane * (C == 8 ? 8 : 4);
     const uint32_t selH = lane == 0 ? 0x1054u : 0x3210u;         // lane 0: lo <- boundary H, hi <- lane 31's low half
     const uint32_t selF = lane == 0 ? 0x1076u : 0x3210u;
     const int src_lane = (lane + 31) & 31;
@@ -245,7 +378,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         // ---- re-centre on lane 0's current row -------------------------------------------------
         {
             int delta = lo16(__shfl_sync(kFullMask, L.Et[0], 0));   // column j0 of the band is never a pad column
-            if (TRACE) delta &= ~1;
+            if (TRACE) delta &= ~3;
             ms32 = max(ms32, max(lo16(L.ms), hi16(L.ms)) + base);   // (stale maxima of masked halves are harmless: they were real)
             const uint32_t nd = dup16(-delta);
 #pragma unroll
@@ -273,32 +406,48 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
                         if (row < m && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
                     }
                 }
-                // absolute modulo 2^16 -> relative to this warp's base; Ft = Fg - (O+E)
-                if (row < m) sm.in[lane] = vadd2((uint32_t)bnd_next, pack16(-base, -base - OEs));
+                // absolute modulo 2^16 -> relative to this warp's base (score-only: Ft = Fg - (O+E))
+                if (row < m) sm.in[lane] = vadd2((uint32_t)bnd_next, pack16(-base, -base - shiftOE));
             } else if (row < m) {
-                const int hb = S * (sc.O + (row + 1) * sc.E) - base;   // H(i,-1); Fg(i,0) = H(i,-1)+O+E, so Ft = H(i,-1)
-                sm.in[lane] = pack16(hb, hb);
+                const int hb = S * (sc.O + (row + 1) * sc.E) - base;   // H(i,-1); Fg(i,0) = H(i,-1)+O+E, opened
+                sm.in[lane] = pack16(hb, hb + OEs - shiftOE);
             }
             const int rowp = row + CH;
             if (b.band > 0 && stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
         }
         __syncwarp();
-        const uint32_t outH = dup16(base), outF = dup16(base + OEs);
+        const uint32_t outHF = pack16(base, base + shiftOE);      // relative (H, F state) -> absolute
         const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
         unsigned long long* bnd_row = b.bnd_out + (t0 - 63);
+        const uint32_t dir_addr = dirw_addr + (t0 & (kDirSteps - 1)) * (C == 8 ? 256 : 128);
 
         if (t0 >= 63 && t0 + CH - 1 < m) {
+            // score-only: the whole chunk is unrolled (every address becomes an immediate);
+            // the traced step is four times as long, so it is unrolled just enough to overlap
+            // neighbouring steps without outgrowing the instruction cache
+            if constexpr (!TRACE) {
 #pragma unroll
-            for (int s = 0; s < CH; s++)
-                psa_step16<C, TRACE, false>(L, t0 + s, s, m, lane, E2, OE2, selH, selF, src_lane, in_addr, ring_next,
-                                            bnd_row, store_right, outH, outF, epoch);
+                for (int s = 0; s < CH; s++)
+                    psa_step16<C, TRACE, false>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                bnd_row, store_right, outHF, epoch, dir_addr);
+            } else {
+#pragma unroll 2
+                for (int s = 0; s < CH; s++)
+                    psa_step16<C, TRACE, false>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                bnd_row, store_right, outHF, epoch, dir_addr);
+            }
         } else {
 #pragma unroll 1
             for (int s = 0; s < CH; s++)
-                psa_step16<C, TRACE, true>(L, t0 + s, s, m, lane, E2, OE2, selH, selF, src_lane, in_addr, ring_next,
-                                           bnd_row, store_right, outH, outF, epoch);
+                psa_step16<C, TRACE, true>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                           bnd_row, store_right, outHF, epoch, dir_addr);
         }
         __syncwarp();
+        if (TRACE) {
+            // rows every virtual lane has finished: [t0 - 63, t0 + CH - 63)
+            psa_flush_dirs16<C>(sm.dirw, b, min(m, max(0, t0 - 63)), min(m, max(0, t0 + CH - 63)), lane);
+            __syncwarp();
+        }
     }
     ms32 = max(ms32, max(lo16(L.ms), hi16(L.ms)) + base);
 
@@ -315,7 +464,8 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
 // 256-entry byte -> 4 x int8 substitution table (codes 0..3) for the packed PRMT.
 __device__ __forceinline__ void psa_build_tab4(uint32_t* tab4, const PsaScoring& sc, int S, int tid, int nthreads)
 {
-    const int Ms = S * sc.M, Xs = S * sc.X;
+    // traced (S == 4): the entries carry the diagonal candidate's tie-break tag (+3)
+    const int Ms = S * sc.M + (S == 4 ? 3 : 0), Xs = S * sc.X + (S == 4 ? 3 : 0);
     for (int bb = tid; bb < 256; bb += nthreads) {
         const uint32_t c = sc.lut[bb];
         uint32_t v = 0;
@@ -337,7 +487,7 @@ __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ 
     int band = 0;
     if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
     band = __shfl_sync(kFullMask, band, 0);
-    psa_build_tab4(tab4, a.sc, TRACE ? 2 : 1, lane, 32);
+    psa_build_tab4(tab4, a.sc, TRACE ? 4 : 1, lane, 32);
     __syncwarp();
 
     PsaBand b;
@@ -359,7 +509,7 @@ __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ 
 template <int C, bool TRACE, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) psa_batch16_kernel(const __grid_constant__ PsaBatchArgs a)
 {
-    constexpr int S = TRACE ? 2 : 1;
+    constexpr int S = TRACE ? 4 : 1;
     __shared__ PsaWarpSmem16<C, TRACE> sm[WARPS];
     __shared__ uint32_t tab4[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

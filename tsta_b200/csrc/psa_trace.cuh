@@ -25,7 +25,11 @@ struct PsaTraceArgs {
     int n, m;
     uint8_t* ops;            // [n + m] moves in walk order
     int* out;                // out[0] = number of moves written, out[1] = final i, out[2] = final j
+    int enc;                 // back code: 0 = (1 diagonal, 0 left, 2 up), 1 = (3 diagonal, 2 left, 1 up)
 };
+
+// `back` bits of a packed code -> move (1 diagonal, 0 left, 2 up) for either encoding
+__device__ __forceinline__ int psa_back_move(int c, int enc) { return enc ? ((0x48 >> (2 * (c & 3))) & 3) : (c & 3); }
 
 static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const PsaTraceArgs a)
 {
@@ -66,7 +70,7 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const P
             while (i > ilim && i >= 0 && j >= jlim) {
                 const uint8_t byte = tile[(i0 - i) * kTraceBytes + ((j >> 1) - wb0)];
                 const int c = (j & 1) ? (byte >> 4) : (byte & 15);
-                const int d = forced >= 0 ? forced : (c & 3);
+                const int d = forced >= 0 ? forced : psa_back_move(c, a.enc);
                 a.ops[nops++] = (uint8_t)d;
                 if (d == 1) { i--; j--; forced = -1; }
                 else if (d == 0) { forced = (c & 4) ? 0 : -1; j--; }
@@ -102,6 +106,7 @@ struct PsaBatchTraceArgs {
     uint8_t* ops;
     const long long* ops_off;
     int* alen;
+    int enc;                     // see PsaTraceArgs
 };
 
 static __global__ void __launch_bounds__(128) psa_batch_trace_kernel(const PsaBatchTraceArgs a)
@@ -116,7 +121,7 @@ static __global__ void __launch_bounds__(128) psa_batch_trace_kernel(const PsaBa
     while (i >= 0 && j >= 0) {
         const uint8_t byte = __ldcs(d + (long long)i * stride + (j >> 1));
         const int c = (j & 1) ? (byte >> 4) : (byte & 15);
-        const int mv = forced >= 0 ? forced : (c & 3);
+        const int mv = forced >= 0 ? forced : psa_back_move(c, a.enc);
         ops[-(nops++)] = (uint8_t)mv;
         if (mv == 1) { i--; j--; forced = -1; }
         else if (mv == 0) { forced = (c & 4) ? 0 : -1; j--; }

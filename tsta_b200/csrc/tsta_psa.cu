@@ -102,6 +102,7 @@ struct tsta_psa_plan {
     int n_pad = 0, nbands = 0, C = 4, CH = 16;
     bool prmt = true;
     bool packed = false;           // int16 x 2 kernels (psa_fill16.cuh); else int32 (psa_fill.cuh)
+    int scale = 1;                 // score scale of the device results (1 score-only, 2 int32 traced, 4 packed traced)
     int nsym = 0;
     bool uploaded = false, ran = false;
     int launches = 0;
@@ -143,15 +144,20 @@ static void launch_pair(const tsta_psa_plan* p, const PsaPairArgs& fa)
 template <int C, bool TRACE>
 static void launch_pair16(const tsta_psa_plan* p, const PsaPairArgs& fa)
 {
-    if (p->CH == 32) psa_pair16_kernel<C, TRACE, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
-    else psa_pair16_kernel<C, TRACE, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    // 32-row hand-off chunks: fewer re-centrings / stagings per row beat the shorter inter-band lag of 16
+    if (p->CH == 16) psa_pair16_kernel<C, TRACE, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    else psa_pair16_kernel<C, TRACE, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
 }
 
 // Packed kernels: 64*C columns per band; the smallest strip that keeps one band per SM
-// sub-partition, as below.
-static int choose_strip16(int64_t n, int sms)
+// sub-partition, as below.  Traced strips pack to whole 8/16/32-bit direction words.
+static int choose_strip16(int64_t n, int sms, bool trace)
 {
     const int64_t slots = (int64_t)sms * 4;
+    if (trace) {
+        for (int c : {2, 4}) if (n <= 64 * c * slots) return c;
+        return 8;
+    }
     for (int c : {2, 3, 4, 6}) if (n <= 64 * c * slots) return c;
     return 8;
 }
@@ -238,7 +244,7 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     }
     const int S = p->want_trace ? 2 : 1;
     p->C = choose_strip(n, p->sms, p->want_trace != 0);
-    p->CH = 16;
+    p->CH = 0;   // 0 = the kernel family's default (16 rows for int32, 32 for packed)
     // tuning overrides for experiments (not part of the ABI)
     if (const char* e = getenv("TSTA_PSA_C")) { const int c = atoi(e); if (c == 4 || c == 8 || c == 16 || (c == 6 && !p->want_trace)) p->C = c; }
     if (const char* e = getenv("TSTA_PSA_CH")) { const int c = atoi(e); if (c == 8 || c == 16 || c == 32) p->CH = c; }
@@ -260,15 +266,20 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     p->prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
     // packed int16 kernels when the alphabet and the score range allow (psa16_fits)
     p->packed = false;
-    if (!p->want_trace) {
-        int c16 = choose_strip16(n, p->sms);
-        if (const char* e = getenv("TSTA_PSA_C16")) { const int c = atoi(e); if (c == 2 || c == 3 || c == 4 || c == 6 || c == 8) c16 = c; }
+    {
+        const bool tr = p->want_trace != 0;
+        int c16 = choose_strip16(n, p->sms, tr);
+        if (const char* e = getenv("TSTA_PSA_C16")) {
+            const int c = atoi(e);
+            if (c == 2 || c == 4 || c == 8 || (!tr && (c == 3 || c == 6))) c16 = c;
+        }
         const char* off = getenv("TSTA_PSA_PACKED");
-        if (!(off && atoi(off) == 0) && psa16_fits(prm->M, prm->X, prm->E, prm->O, S, c16, K)) {
+        if (!(off && atoi(off) == 0) && psa16_fits(prm->M, prm->X, prm->E, prm->O, tr ? 4 : 1, c16, K)) {
             p->packed = true;
             p->C = c16;
         }
     }
+    p->scale = p->packed && p->want_trace ? 4 : S;
     const int band_cols = (p->packed ? 64 : 32) * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
     p->n_pad = p->nbands * band_cols;
@@ -323,7 +334,11 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     fa.lastrow = p->d_lastrow.as<int>();
 
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
-    if (p->want_trace) {
+    if (p->want_trace && p->packed) {
+        if (p->C == 2) launch_pair16<2, true>(p, fa);
+        else if (p->C == 4) launch_pair16<4, true>(p, fa);
+        else launch_pair16<8, true>(p, fa);
+    } else if (p->want_trace) {
         if (p->C == 4) launch_pair<4, true>(p, fa);
         else if (p->C == 8) launch_pair<8, true>(p, fa);
         else launch_pair<16, true>(p, fa);
@@ -349,6 +364,7 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
         ta.n = fa.n; ta.m = fa.m;
         ta.ops = p->d_ops.as<uint8_t>();
         ta.out = ctl + 2;
+        ta.enc = p->packed ? 1 : 0;
         psa_trace_kernel<<<1, kTraceThreads, 0, p->stream>>>(ta);
         TSTA_CUDA_TRY(cudaGetLastError());
         p->launches++;
@@ -368,7 +384,7 @@ int tsta_psa_plan_fetch(tsta_psa_plan* p, tsta_psa_result* out)
     if (!p->ran) return set_error(TSTA_EINVAL, "plan has not been run");
     memset(out, 0, sizeof *out);
     const int64_t n = p->n, m = p->m;
-    const int S = p->want_trace ? 2 : 1;
+    const int S = p->scale;
     std::vector<uint8_t> ops;
     int64_t nops = 0, fi = m - 1, fj = n - 1;
     out->maxsorce = -100;  // reference seed, psa.c:110,590
@@ -418,7 +434,7 @@ int tsta_psa_plan_lastrow(tsta_psa_plan* p, int32_t* out)
     if (p->n == 0 || p->m == 0) return TSTA_OK;
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     TSTA_CUDA_TRY(cudaMemcpy(out, p->d_lastrow.p, (size_t)p->n * sizeof(int), cudaMemcpyDeviceToHost));
-    if (p->want_trace) for (int64_t j = 0; j < p->n; j++) out[j] /= 2;
+    if (p->scale > 1) for (int64_t j = 0; j < p->n; j++) out[j] /= p->scale;
     return TSTA_OK;
 }
 
@@ -433,7 +449,9 @@ int tsta_psa_plan_dirs(tsta_psa_plan* p, uint8_t* out)
     for (int64_t i = 0; i < p->m; i++)
         for (int64_t j = 0; j < p->n; j++) {
             const uint8_t b = packed[(size_t)i * stride + (size_t)(j >> 1)];
-            out[(size_t)i * p->n + j] = (j & 1) ? (b >> 4) : (b & 15);
+            uint8_t c = (j & 1) ? (b >> 4) : (b & 15);
+            if (p->packed) c = (uint8_t)((c & 12) | ((0x48 >> (2 * (c & 3))) & 3));   // packed kernels tag diagonal/left/up as 3/2/1
+            out[(size_t)i * p->n + j] = c;
         }
     return TSTA_OK;
 }

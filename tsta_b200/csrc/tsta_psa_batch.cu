@@ -124,10 +124,12 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     const int K = build_lut(present, a.sc.lut);
     const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
     // packed int16 kernels (psa_fill16.cuh) when alphabet and score range allow; 64*C columns per band
-    const int C16 = (max0 <= 128) ? 2 : (max0 <= 256 ? 4 : 8);
+    // (traced: at most 4 columns per virtual lane, the direction ring of wider strips would
+    // not leave room for enough warps per SM)
+    const int C16 = (max0 <= 128) ? 2 : ((max0 <= 256 || want_trace) ? 4 : 8);
     const char* off16 = getenv("TSTA_PSA_PACKED");
-    const bool packed = !want_trace && !(off16 && atoi(off16) == 0) &&
-                        psa16_fits(prm->M, prm->X, prm->E, prm->O, S, C16, K);
+    const bool packed = !(off16 && atoi(off16) == 0) &&
+                        psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, C16, K);
     const int C = packed ? C16 : ((max0 <= 128) ? 4 : 8);
     const int band_cols = (packed ? 64 : 32) * C;
 
@@ -203,9 +205,13 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 8, g.st));
         TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
         if (want_trace) {
-            if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
+            if (packed) {   // two warps per CTA: the step ring of direction words is 16 KB per warp
+                if (C == 2) psa_batch16_kernel<2, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
+                else psa_batch16_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
+            } else if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
             else launch_batch<8, true, kBatchWarps>(prmt, blocks, g.st, a);
             PsaBatchTraceArgs t{};
+            t.enc = packed ? 1 : 0;
             t.dirs = d_dirs; t.dirs_off = d_dirs_off + k0;
             t.len0 = d_len0 + k0; t.len1 = d_len1 + k0; t.npairs = k1 - k0;
             t.cols_per_band = band_cols;
