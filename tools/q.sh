@@ -1,2 +1,3 @@
-for c in 3 4; do echo "C16=$c"; TSTA_PSA_C16=$c timeout 120 python tools/profile_one.py 100000 x 4; done
-TSTA_PSA_C16=6 timeout 120 python tools/profile_one.py 200000 x 4
+timeout 900 python -m pytest tests/test_psa_gpu.py -x -q 2>&1 | tail -5
+timeout 120 python tools/profile_one.py 100000 trace 4
+timeout 120 python tools/profile_one.py 200000 trace 4

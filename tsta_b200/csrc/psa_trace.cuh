@@ -17,7 +17,12 @@ namespace tsta {
 
 constexpr int kTraceRows = 128;        // window height (rows)
 constexpr int kTraceBytes = 256;       // window width in bytes (= 512 columns)
-constexpr int kTraceThreads = 256;
+constexpr int kTraceThreads = 32 + 256;   // warp 0 walks, 8 warps stage the next window
+constexpr int kTraceWindowBytes = kTraceRows * kTraceBytes;   // 32 KB per buffer
+constexpr int kTraceApron = 8 * kTraceBytes;                  // readable rows in front of a buffer (a block may reach above the window)
+constexpr int kTraceBufStride = kTraceWindowBytes + kTraceApron;
+constexpr int kTraceSmemBytes = 2 * kTraceBufStride;
+constexpr int kTraceBlkRows = 8;       // the walker keeps 8 rows x 16 columns of codes in registers
 
 struct PsaTraceArgs {
     const uint8_t* dirs;
@@ -26,64 +31,167 @@ struct PsaTraceArgs {
     uint8_t* ops;            // [n + m] moves in walk order
     int* out;                // out[0] = number of moves written, out[1] = final i, out[2] = final j
     int enc;                 // back code: 0 = (1 diagonal, 0 left, 2 up), 1 = (3 diagonal, 2 left, 1 up)
+    long long* dbg;          // optional: walker cycles, total cycles, windows, prefetch hits
 };
 
 // `back` bits of a packed code -> move (1 diagonal, 0 left, 2 up) for either encoding
 __device__ __forceinline__ int psa_back_move(int c, int enc) { return enc ? ((0x48 >> (2 * (c & 3))) & 3) : (c & 3); }
 
+// Window placement: rows [R0, R0+128), columns [C0, C0+512) with the cell (i, j) in the last
+// rows / the last 32 columns.  C0 is a multiple of 32 columns (16-byte global units).
+__device__ __forceinline__ void psa_trace_place(int i, int j, int& R0, int& C0)
+{
+    R0 = max(0, i + 1 - kTraceRows);
+    C0 = max(0, ((j + 32) & ~31) - 2 * kTraceBytes);
+}
+
+// Stages one window row-major into shared memory (coalesced 16-byte loads, conflict-free 16-byte
+// stores).  All loads of a thread are issued before the first is used, so a window costs about one
+// HBM round trip.  Codes are normalised to tag form (3 diagonal, 2 left, 1 up) on the way.
+__device__ __forceinline__ void psa_trace_stage(const PsaTraceArgs& a, uint8_t* buf, int R0, int C0, int tid, int nthreads)
+{
+    constexpr int kUnitsPerRow = kTraceBytes / 16;
+    constexpr int kUnits = kTraceRows * kUnitsPerRow;     // 2048
+    constexpr int kBatch = 4;
+    for (int u0 = tid; u0 < kUnits; u0 += kBatch * nthreads) {
+        uint4 v[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            const int u = u0 + b * nthreads;
+            const int r = u / kUnitsPerRow, q = u % kUnitsPerRow;
+            const int row = R0 + r;
+            const long long off = (long long)(C0 >> 1) + q * 16;
+            v[b] = make_uint4(0, 0, 0, 0);
+            if (u < kUnits && row < a.m && off < a.dirs_stride)
+                v[b] = __ldcs(reinterpret_cast<const uint4*>(a.dirs + (long long)row * a.dirs_stride + off));
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            const int u = u0 + b * nthreads;
+            if (u >= kUnits) break;
+            uint32_t w[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!a.enc)   // int32 kernels: back = 1 diagonal / 0 left / 2 up  ->  tags 3 / 2 / 1
+                    w[k] = (w[k] & 0xccccccccu) | (~w[k] & 0x22222222u) | (((w[k] >> 1) | w[k]) & 0x11111111u);
+                // a tag of 0 never comes out of a fill; turn it into a diagonal so that even a
+                // corrupt matrix cannot stall the walk
+                w[k] |= (~(w[k] | (w[k] >> 1)) & 0x11111111u) * 3u;
+            }
+            *reinterpret_cast<uint4*>(buf + (size_t)u * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned trace_bsel(unsigned m, unsigned a, unsigned b)   // m ? a : b, bitwise
+{
+    unsigned d;
+    asm volatile("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
+    return d;
+}
+
+// One thread walks (3-state automaton of oracle/psa_oracle.c) while the other warps already
+// stage the window the path is expected to enter next: the walk is serial by nature
+// (n+m dependent steps), so everything else is kept off its critical path.
 static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const PsaTraceArgs a)
 {
-    __shared__ __align__(16) uint8_t tile[kTraceRows * kTraceBytes];
+    extern __shared__ __align__(16) uint8_t trace_smem[];      // two window buffers, each behind an apron
     __shared__ int s_i, s_j, s_forced, s_nops;
+    const int tid = threadIdx.x;
 
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         s_i = a.m - 1;
         s_j = a.n - 1;
-        s_forced = -1;
+        s_forced = 0;
         s_nops = 0;
     }
+    __syncthreads();
+    int cur = 0, R0, C0;
+    long long dbg_walk = 0, dbg_total0 = clock64();
+    int dbg_windows = 0, dbg_hits = 0;
+    psa_trace_place(s_i, s_j, R0, C0);
+    psa_trace_stage(a, trace_smem + kTraceApron, R0, C0, tid, kTraceThreads);
     __syncthreads();
 
     while (true) {
         const int i0 = s_i, j0 = s_j;
         if (i0 < 0 || j0 < 0) break;
-        // window: rows (i0 - kTraceRows, i0], bytes [wb0, wb0 + kTraceBytes), 16-byte aligned,
-        // placed so that the current column is at its right end
-        const int jb = j0 >> 1;
-        int wb0 = ((jb + 16) & ~15) - kTraceBytes;
-        if (wb0 < 0) wb0 = 0;
-        constexpr int kUnitsPerRow = kTraceBytes / 16;
-        for (int u = threadIdx.x; u < kTraceRows * kUnitsPerRow; u += kTraceThreads) {
-            const int r = u / kUnitsPerRow, q = u % kUnitsPerRow;
-            const int row = i0 - r;
-            const long long off = (long long)wb0 + q * 16;
-            if (row >= 0 && off < a.dirs_stride) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.dirs + (long long)row * a.dirs_stride + off));
-                *reinterpret_cast<uint4*>(tile + r * kTraceBytes + q * 16) = v;
+        // where the path is expected to leave this window: through the top, about one column per row
+        int NR0, NC0;
+        psa_trace_place(R0 - 1, max(0, j0 - (i0 - R0 + 1) + 2 * kTraceBytes / 4), NR0, NC0);
+        if (tid >= 32) {
+            if (R0 > 0) psa_trace_stage(a, trace_smem + kTraceApron + (cur ^ 1) * kTraceBufStride, NR0, NC0, tid - 32, kTraceThreads - 32);
+        } else if (tid == 0) {
+            const long long dbg_t0 = clock64();
+            dbg_windows++;
+            const uint8_t* win = trace_smem + kTraceApron + cur * kTraceBufStride;
+            // Moves in tag form: 3 diagonal, 2 left, 1 up; forced state 0 free, 2 / 1 forced left / up.
+            // The walk is ONE dependent chain, so the inner loop avoids predicates (a compare
+            // feeding a select costs ~13 cycles): the walker keeps 8 rows x 16 columns of codes
+            // in registers with the CURRENT row always in r[0] -- an up move shifts the rows
+            // down by bit-selects, a left move lowers the shift count -- the forced state is an
+            // AND mask and an OR value for the next code, and its successor comes out of a
+            // 64-bit shift LUT.
+            int i = i0, j = j0, nops = s_nops;
+            const unsigned st0 = (unsigned)s_forced;
+            unsigned fm = st0 ? 0u : 3u, fv = st0;
+            // next (mask << 2 | value) by index cFcE * 4 + move:  free (12) unless the move was a
+            // gap and the cell says "keep extending" (left & cF -> 2, up & cE -> 1)
+            const unsigned long long kNext = 0xC21CC2CCCC1CCCCCull;
+            while (i >= R0 && j >= C0) {
+                const int j16 = j & ~15;
+                const uint8_t* p = win + (i - R0) * kTraceBytes + ((j16 - C0) >> 1);
+                unsigned rl[kTraceBlkRows], rh[kTraceBlkRows];
+#pragma unroll
+                for (int k = 0; k < kTraceBlkRows; k++) {       // rows i, i-1, ... (the apron absorbs rows above the window)
+                    const uint2 v = *reinterpret_cast<const uint2*>(p - k * kTraceBytes);
+                    rl[k] = v.x; rh[k] = v.y;
+                }
+                const int rows = min(kTraceBlkRows, i - R0 + 1);
+                int rem = rows, pos = 4 * (j - j16);
+                do {
+                    const unsigned c = (unsigned)((((unsigned long long)rh[0] << 32) | rl[0]) >> pos);   // low nibble = code
+                    const unsigned mvt = (c & fm) | fv;                          // forced, or the cell's own back tag
+                    const unsigned q16 = ((c << 3) & 32u) | ((c << 1) & 16u);    // (cF << 1 | cE) * 16
+                    const unsigned e = (unsigned)(kNext >> (q16 + 4u * mvt));
+                    fm = (e >> 2) & 3u;
+                    fv = e & 3u;
+                    a.ops[nops++] = (uint8_t)((0x48u >> (2 * mvt)) & 3u);        // 1 diagonal, 0 left, 2 up
+                    const unsigned up = mvt & 1u, um = 0u - up;
+#pragma unroll
+                    for (int k = 0; k + 1 < kTraceBlkRows; k++) {
+                        rl[k] = trace_bsel(um, rl[k + 1], rl[k]);
+                        rh[k] = trace_bsel(um, rh[k + 1], rh[k]);
+                    }
+                    rem -= (int)up;
+                    pos -= 4 * (int)(mvt >> 1);
+                } while (((rem - 1) | pos) >= 0);
+                i -= rows - rem;
+                j = j16 + (pos >> 2);
             }
+            const int forced = (int)fv;
+            s_i = i; s_j = j; s_forced = forced; s_nops = nops;
+            dbg_walk += clock64() - dbg_t0;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int i = i0, j = j0, forced = s_forced, nops = s_nops;
-            const int ilim = i0 - kTraceRows;  // exclusive
-            const int jlim = wb0 * 2;          // inclusive lowest column in the window
-            while (i > ilim && i >= 0 && j >= jlim) {
-                const uint8_t byte = tile[(i0 - i) * kTraceBytes + ((j >> 1) - wb0)];
-                const int c = (j & 1) ? (byte >> 4) : (byte & 15);
-                const int d = forced >= 0 ? forced : psa_back_move(c, a.enc);
-                a.ops[nops++] = (uint8_t)d;
-                if (d == 1) { i--; j--; forced = -1; }
-                else if (d == 0) { forced = (c & 4) ? 0 : -1; j--; }
-                else { forced = (c & 8) ? 2 : -1; i--; }
-            }
-            s_i = i; s_j = j; s_forced = forced; s_nops = nops;
+        const int i1 = s_i, j1 = s_j;
+        if (i1 < 0 || j1 < 0) break;
+        if (R0 > 0 && i1 >= NR0 && i1 < NR0 + kTraceRows && j1 >= NC0 && j1 < NC0 + 2 * kTraceBytes) {
+            cur ^= 1; R0 = NR0; C0 = NC0;                       // the prefetched window fits
+            dbg_hits++;
+        } else {
+            psa_trace_place(i1, j1, R0, C0);
+            psa_trace_stage(a, trace_smem + kTraceApron + cur * kTraceBufStride, R0, C0, tid, kTraceThreads);
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         a.out[0] = s_nops;
         a.out[1] = s_i;
         a.out[2] = s_j;
+        if (a.dbg) {
+            a.dbg[0] = dbg_walk; a.dbg[1] = clock64() - dbg_total0; a.dbg[2] = dbg_windows; a.dbg[3] = dbg_hits;
+        }
     }
 }
 

@@ -15,6 +15,7 @@
 namespace tsta {
 
 thread_local std::string g_last_error;
+long long* g_trace_dbg = nullptr;   // TSTA_TRACE_DEBUG=1: cycle counters of the traceback kernel
 
 int ensure_device()
 {
@@ -365,12 +366,24 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
         ta.ops = p->d_ops.as<uint8_t>();
         ta.out = ctl + 2;
         ta.enc = p->packed ? 1 : 0;
-        psa_trace_kernel<<<1, kTraceThreads, 0, p->stream>>>(ta);
+        if (getenv("TSTA_TRACE_DEBUG")) { if (!tsta::g_trace_dbg) cudaMalloc(&tsta::g_trace_dbg, 64); ta.dbg = tsta::g_trace_dbg; }
+        static bool trace_attr = false;
+        if (!trace_attr) {
+            TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
+            trace_attr = true;
+        }
+        psa_trace_kernel<<<1, kTraceThreads, kTraceSmemBytes, p->stream>>>(ta);
         TSTA_CUDA_TRY(cudaGetLastError());
         p->launches++;
     }
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
+        long long h[4] = {0, 0, 0, 0};
+        using tsta::g_trace_dbg;
+        if (g_trace_dbg) { cudaMemcpy(h, g_trace_dbg, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "trace dbg: walk %lld cyc, total %lld cyc, windows %lld, hits %lld\n", h[0], h[1], h[2], h[3]); }
+    }
     float ms = 0.f;
     if (fill_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); *fill_ms = ms; }
     if (trace_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); *trace_ms = ms; }
