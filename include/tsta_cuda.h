@@ -82,6 +82,9 @@ int  tsta_psa_plan_create(tsta_psa_plan** plan, int want_trace);
 int  tsta_psa_plan_upload(tsta_psa_plan* plan, const tsta_params* p,
                           const char* s0, int64_t n, const char* s1, int64_t m);
 int  tsta_psa_plan_run(tsta_psa_plan* plan, float* fill_ms, float* trace_ms);
+/* run = launch (asynchronous: enqueue the kernels on the plan's stream) + wait (synchronise, timings) */
+int  tsta_psa_plan_launch(tsta_psa_plan* plan);
+int  tsta_psa_plan_wait(tsta_psa_plan* plan, float* fill_ms, float* trace_ms);
 int  tsta_psa_plan_fetch(tsta_psa_plan* plan, tsta_psa_result* out);
 /* Debug / parity helpers: last DP row H(m-1, 0..n-1) and the packed direction codes
  * (one byte per cell: back | cF<<2 | cE<<3, row-major m x n). */
@@ -93,6 +96,24 @@ int  tsta_psa_plan_info(tsta_psa_plan* plan, int* launches, int* cols_per_lane, 
  * alphabets and score ranges, csrc/psa_fill16.cuh), 0 for the int32 kernels. */
 int  tsta_psa_plan_packed(tsta_psa_plan* plan);
 void tsta_psa_plan_destroy(tsta_psa_plan* plan);
+
+/* One long pair spread over several GPUs as COLUMN SLICES (score-only): GPU g
+ * holds columns [col0, col0 + n_slice) of s0 and all of s1, and its last band stores the right
+ * boundary column (the reference's V[] / F[], psa/psa.c:355-356) straight into the next GPU's
+ * memory over NVLink, as the same tagged 64-bit elements that bands use inside one GPU.  All
+ * slices are launched together (one process or thread per GPU); slice g only ever waits for
+ * slice g-1.  Every slice but the last must be a multiple of 1536 columns.
+ *   upload_slice      like upload, for one slice (has_left / has_right: neighbours exist)
+ *   inbox_handle      CUDA IPC handle of this slice's left-boundary inbox (has_left slices)
+ *   connect_right     open the right neighbour's inbox handle (another process)
+ *   connect_right_local  same, when both plans live in this process
+ * Every slice must be run the same number of times (the run counter is the elements' tag).
+ * fetch() returns the slice's own maximum (combine with max) and, on the last slice, the corner. */
+int  tsta_psa_plan_upload_slice(tsta_psa_plan* plan, const tsta_params* p, const char* s0_slice, int64_t n_slice,
+                                int64_t col0, int64_t n_total, const char* s1, int64_t m, int has_left, int has_right);
+int  tsta_psa_plan_inbox_handle(tsta_psa_plan* plan, unsigned char handle[64]);
+int  tsta_psa_plan_connect_right(tsta_psa_plan* plan, const unsigned char handle[64]);
+int  tsta_psa_plan_connect_right_local(tsta_psa_plan* plan, tsta_psa_plan* right);
 
 /* Many independent pairs.  seqs0/seqs1 are concatenations; off*[k], len*[k] locate pair k
  * (len0[k] >= len1[k], caller swaps).  Outputs are arrays of npairs entries.  When

@@ -61,6 +61,13 @@ def load() -> C.CDLL:
     L.tsta_psa_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tsta_psa_plan_destroy.argtypes = [C.c_void_p]
     L.tsta_psa_plan_packed.argtypes = [C.c_void_p]
+    L.tsta_psa_plan_launch.argtypes = [C.c_void_p]
+    L.tsta_psa_plan_wait.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.tsta_psa_plan_upload_slice.argtypes = [C.c_void_p, C.POINTER(Params), C.c_char_p, C.c_int64, C.c_int64, C.c_int64,
+                                             C.c_char_p, C.c_int64, C.c_int, C.c_int]
+    L.tsta_psa_plan_inbox_handle.argtypes = [C.c_void_p, C.c_char_p]
+    L.tsta_psa_plan_connect_right.argtypes = [C.c_void_p, C.c_char_p]
+    L.tsta_psa_plan_connect_right_local.argtypes = [C.c_void_p, C.c_void_p]
     L.tsta_set_device.argtypes = [C.c_int]
     L.tsta_measure_dpx_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if hasattr(L, "tsta_psa_batch"):
@@ -139,6 +146,32 @@ class PsaPlan:
         p = Params(M, X, E, O)
         _check(load().tsta_psa_plan_upload(self._h, C.byref(p), s0, self.n, s1, self.m))
 
+    def upload_slice(self, s0: bytes, s1: bytes, col0: int, ncols: int, M=2, X=-5, E=-2, O=-4) -> None:
+        """Columns [col0, col0+ncols) of the pair (s0 longer, already ordered) on this plan's GPU."""
+        self.n, self.m = ncols, len(s1)
+        p = Params(M, X, E, O)
+        _check(load().tsta_psa_plan_upload_slice(self._h, C.byref(p), s0[col0:col0 + ncols], ncols, col0, len(s0),
+                                                 s1, len(s1), int(col0 > 0), int(col0 + ncols < len(s0))))
+
+    def inbox_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(load().tsta_psa_plan_inbox_handle(self._h, buf))
+        return buf.raw
+
+    def connect_right(self, handle: bytes) -> None:
+        _check(load().tsta_psa_plan_connect_right(self._h, handle))
+
+    def connect_right_local(self, right: "PsaPlan") -> None:
+        _check(load().tsta_psa_plan_connect_right_local(self._h, right._h))
+
+    def launch(self) -> None:
+        _check(load().tsta_psa_plan_launch(self._h))
+
+    def wait(self):
+        f, t = C.c_float(), C.c_float()
+        _check(load().tsta_psa_plan_wait(self._h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
     def run(self):
         """Launch fill (+ traceback); returns (fill_ms, trace_ms) from CUDA events."""
         f, t = C.c_float(), C.c_float()
@@ -176,6 +209,21 @@ class PsaPlan:
             self.close()
         except Exception:
             pass
+
+
+def slice_columns(n: int, parts: int, granule: int = 1536):
+    """Column slices of one long pair for `parts` GPUs: every slice but the last is a multiple of
+    `granule` columns (a whole number of bands for every strip width).  Returns [(col0, ncols)];
+    fewer than `parts` entries when the read is too short to give every GPU a slice."""
+    if n <= 0 or parts <= 0:
+        return []
+    width = -(-(-(-n // parts)) // granule) * granule
+    out, c = [], 0
+    while c < n:
+        w = min(width, n - c)
+        out.append((c, w))
+        c += w
+    return out
 
 
 def measure_dpx_peak():

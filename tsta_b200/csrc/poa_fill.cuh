@@ -38,7 +38,17 @@ constexpr int kPoaBndRing = 64;     // boundary ring (rows)
 constexpr int kPoaTrRing = 64;      // trace ring (rows)
 constexpr int kPoaNegInf = -1000000000;
 
+// Row descriptor, built on the host from the CSR graph and staged through shared memory a chunk
+// ahead of the wavefront, so that the inner loop never waits for a dependent global load:
+//   x: base | in-degree << 8 | flags << 16      y, z, w: six predecessor distances (r - p), 16 bit each
+constexpr unsigned kPoaHead = 1u;        // in == 0: the single "predecessor" is the virtual row
+constexpr unsigned kPoaKeep = 2u;        // some successor is further away than the history ring: also store (H, Eout) in HBM
+constexpr unsigned kPoaSlow = 4u;        // more than six predecessors or a distance >= 65536: read the CSR lists instead
+constexpr int kPoaInline = 6;
+constexpr int kPoaDescRing = 64;
+
 struct PoaFillArgs {
+    const uint4* desc;        // [nrows] row descriptors
     const int* row_ptr;       // [nrows+1]
     const int* pred_row;      // [nedges], -1 = virtual predecessor of a head
     const uint8_t* base;      // [nrows]
@@ -59,6 +69,7 @@ struct PoaSmem {
     int2 hist[kPoaHist][32][kPoaC];          // (H, Eout) of the last kPoaHist rows, per lane
     uint16_t tr[kPoaTrRing][32 * kPoaC];     // trace ring
     int2 bring[kPoaBndRing];                 // left boundary (H(r, j0-1), Fg(r, j0)) by row
+    uint4 desc[kPoaDescRing];                // row descriptors
     uint8_t bneg[kPoaBndRing];               // fsource(r, j0-1) < 0
 };
 
@@ -94,10 +105,20 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
     const int nchunks = (R + 31 + kPoaChunk - 1) / kPoaChunk;
     unsigned long long pre_b = 0;
     if (band > 0 && lane < kPoaChunk && lane < R) pre_b = ld_relaxed_u64(bnd_in + lane);
+    // descriptors: lanes 16..31 stage rows [t0+16, t0+32) at the top of chunk t0 (one chunk ahead)
+    if (lane < kPoaChunk && lane < R) sm.desc[lane] = __ldg(a.desc + lane);
+    uint4 pre_d = make_uint4(0, 0, 0, 0);
+    if (lane >= 16 && lane - 16 + kPoaChunk < R) pre_d = __ldg(a.desc + (lane - 16 + kPoaChunk));
 
     for (int ch = 0; ch < nchunks; ch++) {
         const int t0 = ch * kPoaChunk;
-        // ---- stage the left boundary of rows [t0, t0+chunk) -------------------------------------
+        // ---- stage next chunk's descriptors, this chunk's left boundary --------------------------
+        if (lane >= 16) {
+            const int rown = t0 + kPoaChunk + (lane - 16);
+            if (rown < R) sm.desc[rown & (kPoaDescRing - 1)] = pre_d;
+            const int rownn = rown + kPoaChunk;
+            if (rownn < R) pre_d = __ldg(a.desc + rownn);
+        }
         {
             const int row = lane < kPoaChunk ? t0 + lane : R;
             if (band > 0) {
@@ -135,11 +156,11 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     F = v.y;
                     fneg_left = sm.bneg[r & (kPoaBndRing - 1)];
                 }
-                const int e0 = __ldg(a.row_ptr + r);
-                const int npre = __ldg(a.row_ptr + r + 1) - e0;
-                const int b = __ldg(a.base + r);
-                const int p0 = __ldg(a.pred_row + e0);
-                const bool head = p0 < 0;
+                const uint4 dsc = sm.desc[r & (kPoaDescRing - 1)];
+                const int b = (int)(dsc.x & 0xffu);
+                const int npre = (int)((dsc.x >> 8) & 0xffu);
+                const unsigned flags = dsc.x >> 16;
+                const bool head = flags & kPoaHead;
                 const bool late = head && L > 0 && r >= L;
 
                 int bd[C], bdj[C], be[C], bej[C], beH[C];
@@ -155,8 +176,15 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 } else {
 #pragma unroll
                     for (int c = 0; c < C; c++) { bd[c] = kPoaNegInf; bdj[c] = 0; be[c] = kPoaNegInf; bej[c] = 0; beH[c] = 0; }
+                    const int e0 = (flags & kPoaSlow) ? __ldg(a.row_ptr + r) : 0;
+                    unsigned dw = dsc.y;
                     for (int j = 0; j < npre; j++) {
-                        const int p = __ldg(a.pred_row + e0 + j);
+                        int p;
+                        if (flags & kPoaSlow) p = __ldg(a.pred_row + e0 + j);
+                        else {
+                            p = r - (int)(dw & 0xffffu);
+                            dw = (j & 1) ? (j == 1 ? dsc.z : dsc.w) : (dw >> 16);
+                        }
                         int2 v[C];
                         int Hd0;
                         if (r - p <= kPoaNear) {
@@ -164,8 +192,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 #pragma unroll
                             for (int c = 0; c < C; c++) v[c] = sm.hist[slot][lane][c];
                             if (lane > 0) Hd0 = sm.hist[slot][lane - 1][C - 1].x;
-                            else if (band > 0) Hd0 = sm.bring[p & (kPoaBndRing - 1)].x;
-                            else Hd0 = __ldg(a.hneg1 + p);
+                            else Hd0 = sm.bring[p & (kPoaBndRing - 1)].x;              // (band 0: H(p,-1))
                         } else {
                             const int2* src = a.HE + (long long)p * a.stride + j0;
 #pragma unroll
@@ -215,8 +242,10 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     int2* g = a.HE + (long long)r * a.stride + j0;
 #pragma unroll
                     for (int c = 0; c < C; c++) sm.hist[slot][lane][c] = outv[c];
-                    *reinterpret_cast<int4*>(g) = make_int4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
-                    *reinterpret_cast<int4*>(g + 2) = make_int4(outv[2].x, outv[2].y, outv[3].x, outv[3].y);
+                    if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
+                        *reinterpret_cast<int4*>(g) = make_int4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
+                        *reinterpret_cast<int4*>(g + 2) = make_int4(outv[2].x, outv[2].y, outv[3].x, outv[3].y);
+                    }
                     *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) =
                         make_uint2((uint32_t)tw[0] | ((uint32_t)tw[1] << 16), (uint32_t)tw[2] | ((uint32_t)tw[3] << 16));
                 }

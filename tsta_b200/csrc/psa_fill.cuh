@@ -83,7 +83,7 @@ __device__ __forceinline__ int2 bnd_unpack(unsigned long long v, bool trace)
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");   // sys: the producer may be a peer GPU
     return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
@@ -132,6 +132,11 @@ struct PsaBand {
     long long dirs_stride;
     int* lastrow;           // H(m-1, j) goes to lastrow[j - lastrow_col0] (scaled units), or NULL
     int lastrow_col0;
+    // column slice of a pair that is spread over several GPUs (packed score-only kernels):
+    // s0 / n / band indices are local to the slice, col_off is the slice's first global column
+    int col_off = 0;
+    bool has_left = false;  // band 0 gets its left boundary from bnd_in (the neighbour GPU's stores)
+    bool has_right = false; // the last band exports its right boundary to bnd_out (peer memory)
 };
 
 // Fills the 256-entry byte -> substitution-table map (PRMT mode).
@@ -407,6 +412,11 @@ struct PsaPairArgs {
     long long dirs_stride;
     int* out_max;           // atomicMax target (scaled units)
     int* lastrow;           // [n_pad]
+    // multi-GPU column slices (psa_fill16.cuh): global column of the slice, the tagged column
+    // the left neighbour GPU writes into this GPU's memory, the right neighbour's inbox (peer pointer)
+    int col_off;
+    const unsigned long long* inbox;
+    unsigned long long* outbox;
 };
 
 template <int C, bool TRACE, bool PRMT, int CH>

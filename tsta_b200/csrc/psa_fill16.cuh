@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b) { r
 __device__ __forceinline__ void st_relaxed_pair_if(unsigned long long* p, uint32_t lo, uint32_t hi, bool doit)
 {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.b64 v, {%1, %2};\n\t"
-                 "@p st.relaxed.gpu.global.b64 [%0], v;\n\t}"
+                 "@p st.relaxed.sys.global.b64 [%0], v;\n\t}"
                  ::"l"(p), "r"(lo), "r"(hi), "r"((unsigned)doit) : "memory");
 }
 template <class SM>
@@ -319,7 +319,8 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     const int jlo = (b.band * 64 + lane) * C, jhi = jlo + 32 * C;
 
     // ---- initial state: row -1 (psa.c:219-227), relative to base = H(-1, first column of the band)
-    int base = S * (sc.O + (b.band * 64 * C + 1) * sc.E);
+    const int goff = b.col_off;                                  // global column of the slice (0 unless multi-GPU)
+    int base = S * (sc.O + (goff + b.band * 64 * C + 1) * sc.E);
     PsaLane16<C> L;
 #pragma unroll
     for (int c = 0; c < C; c++) {
@@ -329,7 +330,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         const uint32_t nl = cl < 8u ? (cl | ((8u | cl) << 4)) : 0x88u;
         const uint32_t nh = chh < 12u ? (chh | ((8u | chh) << 4)) : 0xccu;
         L.sel[c] = nl | (nh << 8);
-        const int ha = S * (sc.O + (a + 1) * sc.E), hh = S * (sc.O + (h + 1) * sc.E);   // H(-1, j)
+        const int ha = S * (sc.O + (goff + a + 1) * sc.E), hh = S * (sc.O + (goff + h + 1) * sc.E);   // H(-1, j)
         // Eg(0,j) = H(-1,j) + O + E, opened.  score-only: stored minus (O+E); TRACE: flagged
         const int eo = OEs - shiftOE;
         L.Et[c] = pack16(ha + eo - base, hh + eo - base);
@@ -342,7 +343,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         L.Hup[c] = pack16(ha - base - (a + 1 >= b.n ? padlow : 0), hh - base - (h + 1 >= b.n ? padlow : 0));
     }
     {
-        const int da = S * (jlo == 0 ? 0 : sc.O + jlo * sc.E), dh = S * (sc.O + jhi * sc.E);   // H(-1, j0-1)
+        const int da = S * (goff + jlo == 0 ? 0 : sc.O + (goff + jlo) * sc.E), dh = S * (sc.O + (goff + jhi) * sc.E);   // H(-1, j0-1)
         L.diag = pack16(da - base - (jlo >= b.n ? padlow : 0), dh - base - (jhi >= b.n ? padlow : 0));
     }
     L.ms = kMin16x2;
@@ -352,7 +353,8 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
 
     const int nsteps = m + 63;                                   // virtual lane 63 finishes row m-1 at step m+62
     const int nchunks = (nsteps + CH - 1) / CH;
-    const bool export_right = (b.band + 1 < b.nbands) && b.bnd_out != nullptr;
+    const bool export_right = (b.band + 1 < b.nbands || b.has_right) && b.bnd_out != nullptr;
+    const bool import_left = b.band > 0 || b.has_left;
     const unsigned epoch = PIPE ? b.epoch : 1u;
     const bool store_right = export_right && lane == 31;
     const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in);
@@ -369,7 +371,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, 0u));   // rows < 32: no high row yet
     uint32_t raw_next = (stager && CH + lane < m) ? b.s1[CH + lane] : 0xffffffffu;
     unsigned long long bnd_next = 0;
-    if (b.band > 0 && stager && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
+    if (import_left && stager && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
     __syncwarp();
     L.Tnext = sm.rowring[0];
 
@@ -399,7 +401,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             const int rownn = rown + CH;
             raw_next = (stager && rownn < m) ? b.s1[rownn] : 0u;
             const int row = stager ? t0 + lane : m;
-            if (b.band > 0) {
+            if (import_left) {
                 if (PIPE) {
                     while (!__all_sync(kFullMask, row >= m || (unsigned)(bnd_next >> 32) == epoch)) {
                         __nanosleep(20);
@@ -413,7 +415,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
                 sm.in[lane] = pack16(hb, hb + OEs - shiftOE);
             }
             const int rowp = row + CH;
-            if (b.band > 0 && stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
+            if (import_left && stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
         }
         __syncwarp();
         const uint32_t outHF = pack16(base, base + shiftOE);      // relative (H, F state) -> absolute
@@ -493,8 +495,11 @@ __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ 
     PsaBand b;
     b.s0 = a.s0; b.s1 = a.s1; b.n = a.n; b.m = a.m;
     b.band = band; b.nbands = a.nbands;
-    b.bnd_in = a.bnd + (long long)(band - 1) * a.bnd_stride;
-    b.bnd_out = a.bnd + (long long)band * a.bnd_stride;
+    b.col_off = a.col_off;
+    b.has_left = a.inbox != nullptr;
+    b.has_right = a.outbox != nullptr;
+    b.bnd_in = band == 0 ? a.inbox : a.bnd + (long long)(band - 1) * a.bnd_stride;
+    b.bnd_out = (band == a.nbands - 1 && a.outbox) ? a.outbox : a.bnd + (long long)band * a.bnd_stride;
     b.epoch = a.epoch;
     b.dirs = a.dirs; b.dirs_stride = a.dirs_stride;
     b.lastrow = a.lastrow; b.lastrow_col0 = 0;

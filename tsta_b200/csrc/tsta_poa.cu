@@ -19,7 +19,8 @@ struct tsta_poa {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    DevBuf d_rowptr, d_pred, d_base, d_hneg1, d_read, d_HE, d_trace, d_bnd, d_ctl, d_last, d_path;
+    DevBuf d_rowptr, d_pred, d_base, d_hneg1, d_read, d_HE, d_trace, d_bnd, d_ctl, d_last, d_path, d_desc;
+    std::vector<uint4> h_desc;
     unsigned epoch = 0;
     int nrows = 0, len = 0, nbands = 0;
     long long stride = 0;
@@ -32,7 +33,7 @@ static void poa_free(tsta_poa* p)
     if (!p) return;
     cudaSetDevice(p->device);
     DevBuf* bufs[] = {&p->d_rowptr, &p->d_pred, &p->d_base, &p->d_hneg1, &p->d_read, &p->d_HE,
-                      &p->d_trace, &p->d_bnd, &p->d_ctl, &p->d_last, &p->d_path};
+                      &p->d_trace, &p->d_bnd, &p->d_ctl, &p->d_last, &p->d_path, &p->d_desc};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -78,12 +79,34 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
             return set_error(TSTA_EINVAL, "row %d: in-degree must be 1..41 (reference limit: predecessor index < 42)", r);
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     p->filled = false;
+    // row descriptors (see poa_fill.cuh): base, in-degree, flags, up to six predecessor distances
+    p->h_desc.assign((size_t)nrows, make_uint4(0, 0, 0, 0));
+    for (int r = 0; r < nrows; r++) {
+        const int e0 = row_ptr[r], np = row_ptr[r + 1] - e0;
+        unsigned flags = 0, d[kPoaInline] = {0, 0, 0, 0, 0, 0};
+        if (pred_row[e0] < 0) flags |= kPoaHead;
+        else {
+            if (np > kPoaInline) flags |= kPoaSlow;
+            for (int j = 0; j < np; j++) {
+                const int pr = pred_row[e0 + j];
+                if (pr < 0 || pr >= r) return set_error(TSTA_EINVAL, "row %d: predecessor %d is not an earlier row", r, pr);
+                const int dist = r - pr;
+                if (dist > kPoaNear) p->h_desc[(size_t)pr].x |= kPoaKeep << 16;
+                if (dist >= 65536) flags |= kPoaSlow;
+                else if (j < kPoaInline) d[j] = (unsigned)dist;
+            }
+        }
+        uint4& q = p->h_desc[(size_t)r];
+        q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16);
+        q.y = d[0] | (d[1] << 16); q.z = d[2] | (d[3] << 16); q.w = d[4] | (d[5] << 16);
+    }
     const int band_cols = 32 * kPoaC;
     p->nbands = (len + band_cols - 1) / band_cols;
     p->stride = (long long)p->nbands * band_cols;
     p->nrows = nrows;
     p->len = len;
 
+    if (int rc = p->d_desc.reserve((size_t)nrows * sizeof(uint4))) return rc;
     if (int rc = p->d_rowptr.reserve((size_t)(nrows + 1) * 4)) return rc;
     if (int rc = p->d_pred.reserve((size_t)nedges * 4)) return rc;
     if (int rc = p->d_base.reserve((size_t)nrows)) return rc;
@@ -107,6 +130,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
         p->epoch = 1;
     }
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_desc.p, p->h_desc.data(), (size_t)nrows * sizeof(uint4), cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_rowptr.p, row_ptr, (size_t)(nrows + 1) * 4, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_pred.p, pred_row, (size_t)nedges * 4, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_base.p, base, (size_t)nrows, cudaMemcpyHostToDevice, p->stream));
@@ -115,6 +139,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.p, 0, 64, p->stream));
 
     PoaFillArgs a{};
+    a.desc = p->d_desc.as<uint4>();
     a.row_ptr = p->d_rowptr.as<int>(); a.pred_row = p->d_pred.as<int>();
     a.base = p->d_base.as<uint8_t>(); a.hneg1 = p->d_hneg1.as<int>(); a.read = p->d_read.as<uint8_t>();
     a.len = len; a.nrows = nrows; a.nbands = p->nbands; a.L = L;

@@ -104,6 +104,13 @@ struct tsta_psa_plan {
     bool prmt = true;
     bool packed = false;           // int16 x 2 kernels (psa_fill16.cuh); else int32 (psa_fill.cuh)
     int scale = 1;                 // score scale of the device results (1 score-only, 2 int32 traced, 4 packed traced)
+    // column slice of a pair spread over several GPUs (tsta_psa_plan_upload_slice)
+    int64_t col0 = 0, n_total = 0;
+    bool has_left = false, has_right = false;
+    DevBuf d_inbox;                // [m] tagged boundary elements written by the left neighbour GPU
+    size_t inbox_rows = 0;
+    unsigned long long* outbox = nullptr;   // the right neighbour's inbox, opened through CUDA IPC
+    bool outbox_open = false;
     int nsym = 0;
     bool uploaded = false, ran = false;
     int launches = 0;
@@ -119,7 +126,8 @@ static void plan_free(tsta_psa_plan* p)
     if (!p) return;
     cudaSetDevice(p->device);
     p->d_s0.release(); p->d_s1.release(); p->d_bnd.release(); p->d_ctl.release();
-    p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release();
+    p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release(); p->d_inbox.release();
+    if (p->outbox_open) cudaIpcCloseMemHandle(p->outbox);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -221,8 +229,69 @@ int tsta_psa_plan_create(tsta_psa_plan** out, int want_trace)
 
 void tsta_psa_plan_destroy(tsta_psa_plan* p) { plan_free(p); }
 
+static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0, int64_t n, const char* s1, int64_t m,
+                       int64_t col0, int64_t n_total, bool has_left, bool has_right);
+
 int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
                          const char* s0, int64_t n, const char* s1, int64_t m)
+{
+    return plan_upload(p, prm, s0, n, s1, m, 0, n, false, false);
+}
+
+int tsta_psa_plan_upload_slice(tsta_psa_plan* p, const tsta_params* prm, const char* s0_slice, int64_t n_slice,
+                               int64_t col0, int64_t n_total, const char* s1, int64_t m, int has_left, int has_right)
+{
+    if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
+    if (p->want_trace) return set_error(TSTA_EINVAL, "column slices are score-only (the traceback of a sliced pair is not built yet)");
+    if (n_slice <= 0 || m <= 0 || col0 < 0 || col0 + n_slice > n_total || (has_left != 0) != (col0 > 0) ||
+        (has_right != 0) != (col0 + n_slice < n_total))
+        return set_error(TSTA_EINVAL, "bad slice: columns [%lld, %lld) of %lld", (long long)col0, (long long)(col0 + n_slice), (long long)n_total);
+    if (n_total < m) return set_error(TSTA_EINVAL, "s0 must be the longer read");
+    return plan_upload(p, prm, s0_slice, n_slice, s1, m, col0, n_total, has_left != 0, has_right != 0);
+}
+
+int tsta_psa_plan_inbox_handle(tsta_psa_plan* p, unsigned char handle[64])
+{
+    if (!p || !handle || !p->d_inbox.p) return set_error(TSTA_EINVAL, "plan has no inbox (upload a slice with has_left first)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    cudaIpcMemHandle_t h;
+    TSTA_CUDA_TRY(cudaIpcGetMemHandle(&h, p->d_inbox.p));
+    memcpy(handle, &h, 64);
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_connect_right(tsta_psa_plan* p, const unsigned char handle[64])
+{
+    if (!p || !handle) return set_error(TSTA_EINVAL, "NULL argument");
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    if (p->outbox_open) { cudaIpcCloseMemHandle(p->outbox); p->outbox_open = false; p->outbox = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* ptr = nullptr;
+    TSTA_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->outbox = static_cast<unsigned long long*>(ptr);
+    p->outbox_open = true;
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_connect_right_local(tsta_psa_plan* p, tsta_psa_plan* right)
+{
+    // same process, both plans on devices with peer access (or the same device)
+    if (!p || !right || !right->d_inbox.p) return set_error(TSTA_EINVAL, "right plan has no inbox");
+    if (p->device != right->device) {
+        TSTA_CUDA_TRY(cudaSetDevice(p->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(right->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) TSTA_CUDA_TRY(e);
+        cudaGetLastError();
+    }
+    p->outbox = right->d_inbox.as<unsigned long long>();
+    p->outbox_open = false;
+    return TSTA_OK;
+}
+
+static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0, int64_t n, const char* s1, int64_t m,
+                       int64_t col0, int64_t n_total, bool has_left, bool has_right)
 {
     if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
     if (int rc = check_params(prm)) return rc;
@@ -230,8 +299,9 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     if (n < m) return set_error(TSTA_EINVAL, "s0 must be the longer read (n=%lld < m=%lld); swap like psa.c:194-199",
                                 (long long)n, (long long)m);
     // int32 headroom: doubled scores, worst step 2*127 per row/column
-    if ((n + m) > (int64_t)4000000) return set_error(TSTA_EINVAL, "n+m=%lld exceeds the supported 4e6", (long long)(n + m));
+    if ((n_total + m) > (int64_t)4000000) return set_error(TSTA_EINVAL, "n+m=%lld exceeds the supported 4e6", (long long)(n_total + m));
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    p->col0 = col0; p->n_total = n_total; p->has_left = has_left; p->has_right = has_right;
     p->sc.M = prm->M; p->sc.X = prm->X; p->sc.E = prm->E; p->sc.O = prm->O;
     p->n = n;
     p->m = m;
@@ -284,6 +354,16 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
     const int band_cols = (p->packed ? 64 : 32) * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
     p->n_pad = p->nbands * band_cols;
+    if (has_left || has_right) {
+        if (!p->packed) return set_error(TSTA_EINVAL, "column slices need the packed kernels (alphabet of <= 4 symbols, small scores)");
+        if (has_right && n % band_cols != 0)
+            return set_error(TSTA_EINVAL, "a slice with a right neighbour must be a multiple of %d columns (got %lld)", band_cols, (long long)n);
+        if (has_left && (size_t)m > p->inbox_rows) {
+            if (int rc = p->d_inbox.reserve((size_t)m * sizeof(unsigned long long))) return rc;
+            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_inbox.p, 0, p->d_inbox.cap, p->stream));
+            p->inbox_rows = (size_t)m;
+        }
+    }
 
     {   // boundary columns: tagged elements, so fresh memory must start out all-zero (tag 0)
         const size_t need = (size_t)p->nbands * (size_t)m * sizeof(unsigned long long);
@@ -304,11 +384,36 @@ int tsta_psa_plan_upload(tsta_psa_plan* p, const tsta_params* prm,
 
 int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
 {
+    if (int rc = tsta_psa_plan_launch(p)) return rc;
+    return tsta_psa_plan_wait(p, fill_ms, trace_ms);
+}
+
+int tsta_psa_plan_wait(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
+{
     if (!p || !p->uploaded) return set_error(TSTA_EINVAL, "plan has no uploaded pair");
     if (fill_ms) *fill_ms = 0.f;
     if (trace_ms) *trace_ms = 0.f;
-    p->launches = 0;
     if (p->n == 0 || p->m == 0) { p->ran = true; return TSTA_OK; }
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
+        long long h[4] = {0, 0, 0, 0};
+        using tsta::g_trace_dbg;
+        if (g_trace_dbg) { cudaMemcpy(h, g_trace_dbg, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "trace dbg: walk %lld cyc, total %lld cyc, windows %lld, hits %lld\n", h[0], h[1], h[2], h[3]); }
+    }
+    float ms = 0.f;
+    if (fill_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); *fill_ms = ms; }
+    if (trace_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); *trace_ms = ms; }
+    p->ran = true;
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_launch(tsta_psa_plan* p)
+{
+    if (!p || !p->uploaded) return set_error(TSTA_EINVAL, "plan has no uploaded pair");
+    p->launches = 0;
+    if (p->n == 0 || p->m == 0) return TSTA_OK;
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     int* ctl = p->d_ctl.as<int>();
     // ticket = 0; out_max = INT_MIN; a fresh boundary tag for this run
@@ -333,6 +438,10 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     fa.dirs_stride = p->n_pad / 2;
     fa.out_max = ctl + 1;
     fa.lastrow = p->d_lastrow.as<int>();
+    fa.col_off = (int)p->col0;
+    fa.inbox = p->has_left ? p->d_inbox.as<unsigned long long>() : nullptr;
+    fa.outbox = p->has_right ? p->outbox : nullptr;
+    if (p->has_right && !p->outbox) return set_error(TSTA_EINVAL, "slice has a right neighbour but tsta_psa_plan_connect_right was not called");
 
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     if (p->want_trace && p->packed) {
@@ -377,17 +486,6 @@ int tsta_psa_plan_run(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
         p->launches++;
     }
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
-    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
-    if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
-        long long h[4] = {0, 0, 0, 0};
-        using tsta::g_trace_dbg;
-        if (g_trace_dbg) { cudaMemcpy(h, g_trace_dbg, 32, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "trace dbg: walk %lld cyc, total %lld cyc, windows %lld, hits %lld\n", h[0], h[1], h[2], h[3]); }
-    }
-    float ms = 0.f;
-    if (fill_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); *fill_ms = ms; }
-    if (trace_ms) { TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); *trace_ms = ms; }
-    p->ran = true;
     return TSTA_OK;
 }
 
