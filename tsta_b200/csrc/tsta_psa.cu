@@ -296,8 +296,8 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
     if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
     if (int rc = check_params(prm)) return rc;
     if (n < 0 || m < 0 || (n > 0 && !s0) || (m > 0 && !s1)) return set_error(TSTA_EINVAL, "bad sequence arguments");
-    if (n < m) return set_error(TSTA_EINVAL, "s0 must be the longer read (n=%lld < m=%lld); swap like psa.c:194-199",
-                                (long long)n, (long long)m);
+    if (n_total < m) return set_error(TSTA_EINVAL, "s0 must be the longer read (n=%lld < m=%lld); swap like psa.c:194-199",
+                                      (long long)n_total, (long long)m);
     // int32 headroom: doubled scores, worst step 2*127 per row/column
     if ((n_total + m) > (int64_t)4000000) return set_error(TSTA_EINVAL, "n+m=%lld exceeds the supported 4e6", (long long)(n_total + m));
     TSTA_CUDA_TRY(cudaSetDevice(p->device));

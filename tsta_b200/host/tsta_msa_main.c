@@ -46,7 +46,7 @@ int main(int argc, char* argv[])
     }
     int rc = msa_main(argc, argv, &be);
     if (getenv("TSTA_MSA_TIMING"))
-        fprintf(stderr, "kernels: fill %.1f ms walk %.1f ms, %.3g node-cells, %.1f GCUPS (fill kernel)\n",
+        fprintf(stderr, "kernels: fill %.1f ms walk %.1f ms, %.0f node-cells, %.1f GCUPS (fill kernel)\n",
                 x.fill_ms, x.walk_ms, x.cells, x.fill_ms > 0 ? x.cells / x.fill_ms / 1e6 : 0.0);
     if (x.poa) tsta_poa_destroy(x.poa);
     return rc;
