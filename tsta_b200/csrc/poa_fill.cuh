@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 #pragma unroll
     for (int c = 0; c < C; c++) rc[c] = (j0 + c < len) ? a.read[j0 + c] : 0;
     const bool owns_last = (len - 1 >= j0) && (len - 1 < j0 + C);
+    bool hasN = false;                   // quirk Q3 applies to this lane's strip at all?
+#pragma unroll
+    for (int c = 0; c < C; c++) hasN |= rc[c] == 'N';
     const unsigned long long* bnd_in = a.bnd + (long long)(band - 1) * R;
     unsigned long long* bnd_out = a.bnd + (long long)band * R;
     const bool store_right = (band + 1 < a.nbands) && lane == 31;
@@ -163,7 +166,11 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 const bool head = flags & kPoaHead;
                 const bool late = head && L > 0 && r >= L;
 
-                int bd[C], bdj[C], be[C], bej[C], beH[C];
+                // Reduction over the predecessors with KEYS: the history holds H*64 and
+                // Eout*128 + "opened", so  max(H*64 + (63-j))  and  max(Eout*128 + 2*(63-j) + opened)
+                // give the maximum, the LOWEST predecessor index that attains it (the reference's
+                // tie-break) and the opened flag of exactly that predecessor in one VIADDMNMX each.
+                int kd[C], ke[C];
                 if (head) {
 #pragma unroll
                     for (int c = 0; c < C; c++) {
@@ -171,11 +178,12 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                         int Hd, Hp;
                         if (late && col <= L - 1) { Hd = col * E; Hp = (col + 1) * E; }       // quirk Q1
                         else { Hd = col == 0 ? 0 : O + col * E; Hp = O + (col + 1) * E; }
-                        bd[c] = Hd; bdj[c] = 0; be[c] = Hp + OE; bej[c] = 0; beH[c] = Hp;
+                        kd[c] = Hd * 64 + 63;                       // predecessor index 0
+                        ke[c] = (Hp + OE) * 128 + 2 * 63 + 1;       // Eout_v = Hv + O + E: opened
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < C; c++) { bd[c] = kPoaNegInf; bdj[c] = 0; be[c] = kPoaNegInf; bej[c] = 0; beH[c] = 0; }
+                    for (int c = 0; c < C; c++) { kd[c] = INT_MIN / 2; ke[c] = INT_MIN / 2; }
                     const int e0 = (flags & kPoaSlow) ? __ldg(a.row_ptr + r) : 0;
                     unsigned dw = dsc.y;
                     for (int j = 0; j < npre; j++) {
@@ -185,75 +193,91 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                             p = r - (int)(dw & 0xffffu);
                             dw = (j & 1) ? (j == 1 ? dsc.z : dsc.w) : (dw >> 16);
                         }
-                        int2 v[C];
+                        int4 v01, v23;
                         int Hd0;
                         if (r - p <= kPoaNear) {
                             const int slot = p & (kPoaHist - 1);
-#pragma unroll
-                            for (int c = 0; c < C; c++) v[c] = sm.hist[slot][lane][c];
-                            if (lane > 0) Hd0 = sm.hist[slot][lane - 1][C - 1].x;
-                            else Hd0 = sm.bring[p & (kPoaBndRing - 1)].x;              // (band 0: H(p,-1))
+                            v01 = *reinterpret_cast<const int4*>(&sm.hist[slot][lane][0]);
+                            v23 = *reinterpret_cast<const int4*>(&sm.hist[slot][lane][2]);
+                            const int hl = sm.hist[slot][lane > 0 ? lane - 1 : 0][C - 1].x;
+                            const int hb = sm.bring[p & (kPoaBndRing - 1)].x * 64;          // (band 0: H(p,-1))
+                            Hd0 = lane > 0 ? hl : hb;
                         } else {
                             const int2* src = a.HE + (long long)p * a.stride + j0;
-#pragma unroll
-                            for (int c = 0; c < C; c++) v[c] = __ldcg(src + c);
+                            v01 = __ldcg(reinterpret_cast<const int4*>(src));
+                            v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
-                            else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p);
-                            else Hd0 = __ldg(a.hneg1 + p);
+                            else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p) * 64;
+                            else Hd0 = __ldg(a.hneg1 + p) * 64;
                         }
-#pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            const int Hd = c == 0 ? Hd0 : v[c - 1].x;
-                            if (Hd > bd[c]) { bd[c] = Hd; bdj[c] = j; }
-                            if (v[c].y > be[c]) { be[c] = v[c].y; bej[c] = j; beH[c] = v[c].x; }
-                        }
+                        const int wd = 63 - j, we = 2 * (63 - j);
+                        kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
+                        kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
+                        kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
+                        kd[3] = __viaddmax_s32(v23.x, wd, kd[3]);
+                        ke[0] = __viaddmax_s32(v01.y, we, ke[0]);
+                        ke[1] = __viaddmax_s32(v01.w, we, ke[1]);
+                        ke[2] = __viaddmax_s32(v23.y, we, ke[2]);
+                        ke[3] = __viaddmax_s32(v23.w, we, ke[3]);
                     }
                 }
 
                 // ---- the row itself: serial along the strip --------------------------------------
                 int2 outv[C];
                 uint16_t tw[C];
+                int Hlast = 0;
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     const int col = j0 + c;
                     if (late && col == L) F += O;                              // quirk Q1: carried F re-based
-                    const int sub = ((int)rc[c] == b) ? M : X;
-                    const int h = bd[c] + sub;
-                    int H = max(h, max(be[c], F));
-                    if (rc[c] == 'N') H = Hleft;
-                    int src = 126;
-                    if (be[c] == H) src = bej[c];
-                    if (h == H) src = (sub == M ? 42 : 84) + bdj[c];
-                    const int eopen = (be[c] - beH[c] == OE);
-                    const int eneg = (be[c] + E == H + OE);
+                    const int bd = kd[c] >> 6, bdj = 63 - (kd[c] & 63);
+                    const int be = ke[c] >> 7, bej = 63 - ((ke[c] >> 1) & 63), eopen = ke[c] & 1;
+                    const bool match = (int)rc[c] == b;
+                    const int h = bd + (match ? M : X);
+                    // candidates tagged with the tie-break priority of c-t-simd.c:484-506:
+                    // diagonal (3) beats vertical E (2) beats horizontal F (1)
+                    const int Hk = __vimax3_s32(h * 4 + 3, be * 4 + 2, F * 4 + 1);
+                    int H = Hk >> 2;
+                    const int s3 = (match ? 42 : 84) + bdj;
+                    int src;
+                    if (hasN && rc[c] == 'N') {                                // quirk Q3: 'N' columns copy H from the left
+                        H = Hleft;
+                        src = 126;
+                        if (be == H) src = bej;
+                        if (h == H) src = s3;
+                    } else {
+                        const int tag = Hk & 3;
+                        src = tag == 3 ? s3 : (tag == 2 ? bej : 126);
+                    }
+                    const int t = H + OE, ae = be + E;
+                    const int eneg = (ae == t);
                     const int fabs2 = (F - Hleft == OE);                       // |fsource| == 2
-                    const int fneg = (F + E == H + OE);
+                    const int fneg = (F + E == t);
                     const int cH = (!fabs2) || fneg_left;                      // (767-769), column >= 2 checked by the walker
-                    tw[c] = (uint16_t)(src | (cH << 7) | (bej[c] << 8) | (eopen << 14) | (eneg << 15));
-                    outv[c] = make_int2(H, max(H + OE, be[c] + E));
-                    F = max(F + E, H + OE);
+                    tw[c] = (uint16_t)(src | (cH << 7) | (bej << 8) | (eopen << 14) | (eneg << 15));
+                    // Eout = max(H+O+E, be+E) with "opened" (ties count as opened) in bit 0 of the doubled max
+                    const int z = max(2 * ae, 2 * t + 1);
+                    outv[c] = make_int2(H * 64, (z & ~1) * 64 + (z & 1));      // (H*64, Eout*128 + opened)
+                    F = max(F + E, t);
                     Hleft = H;
                     fneg_left = fneg;
+                    if (j0 + c == len - 1) Hlast = H;
                 }
                 Hout = Hleft; Fout = F; Nout = fneg_left;
-                // history ring, global (H, Eout) matrix, trace ring
+                // history ring, HBM spill for far successors, trace ring
                 {
                     const int slot = r & (kPoaHist - 1);
-                    int2* g = a.HE + (long long)r * a.stride + j0;
-#pragma unroll
-                    for (int c = 0; c < C; c++) sm.hist[slot][lane][c] = outv[c];
+                    *reinterpret_cast<int4*>(&sm.hist[slot][lane][0]) = make_int4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
+                    *reinterpret_cast<int4*>(&sm.hist[slot][lane][2]) = make_int4(outv[2].x, outv[2].y, outv[3].x, outv[3].y);
                     if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
+                        int2* g = a.HE + (long long)r * a.stride + j0;
                         *reinterpret_cast<int4*>(g) = make_int4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
                         *reinterpret_cast<int4*>(g + 2) = make_int4(outv[2].x, outv[2].y, outv[3].x, outv[3].y);
                     }
                     *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) =
                         make_uint2((uint32_t)tw[0] | ((uint32_t)tw[1] << 16), (uint32_t)tw[2] | ((uint32_t)tw[3] << 16));
                 }
-                if (owns_last) {
-#pragma unroll
-                    for (int c = 0; c < C; c++)
-                        if (j0 + c == len - 1) a.lastsorce[r] = outv[c].x;
-                }
+                if (owns_last) a.lastsorce[r] = Hlast;
                 st_relaxed_u64_if(bnd_out + r, poa_bnd_pack(Hout, Fout, Nout, a.epoch), store_right);
             }
         }

@@ -73,6 +73,11 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     if (int rc = check_params(prm)) return rc;
     if (nrows <= 0 || len <= 0 || !row_ptr || !pred_row || !base || !hneg1 || !read || !lastsorce)
         return set_error(TSTA_EINVAL, "bad POA arguments");
+    {   // the kernel carries scores times 128 (key packing, poa_fill.cuh)
+        const long long amax = std::max(std::max(std::abs(prm->M), std::abs(prm->X)), std::abs(prm->E) + std::abs(prm->O));
+        if (((long long)nrows + len + 2) * amax >= (1LL << 23))
+            return set_error(TSTA_EINVAL, "POA job too large for the int32 key packing: (rows + read length) * max|score| must stay below 2^23");
+    }
     const int nedges = row_ptr[nrows];
     for (int r = 0; r < nrows; r++)
         if (row_ptr[r + 1] - row_ptr[r] < 1 || row_ptr[r + 1] - row_ptr[r] > 41)
