@@ -466,9 +466,9 @@ def main():
         if mine is not None:
             plan.upload_slice(s0, s1, mine[0], mine[1], **PARAMS)
         if world > 1:
-            handles = [None] * world
+            from tsta_b200 import shard
             h = plan.inbox_handle() if (mine is not None and mine[0] > 0) else b""
-            dist.all_gather_object(handles, h)
+            handles = shard.exchange_inbox_handles(dist, h, world)
             if mine is not None and rank + 1 < len(slices):
                 plan.connect_right(handles[rank + 1])
 
