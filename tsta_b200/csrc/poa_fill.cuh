@@ -33,19 +33,28 @@ namespace tsta {
 constexpr int kPoaC = 4;            // columns per lane
 constexpr int kPoaHist = 32;        // history ring depth in rows (power of two)
 constexpr int kPoaNear = kPoaHist - 2;   // predecessors at most this many rows back are read from the ring
+constexpr int kPoaSlotNone = 32;    // extra history slots: "no predecessor" (keys of -infinity),
+constexpr int kPoaSlotHead = 33;    // the virtual row above a head node,
+constexpr int kPoaSlotLate = 34;    // and its late-head variant (quirk Q1)
+constexpr int kPoaSlots = 35;
+constexpr int kPoaFast = 3;         // predecessors the unrolled fast path handles
 constexpr int kPoaChunk = 16;       // rows per staging chunk
 constexpr int kPoaBndRing = 64;     // boundary ring (rows)
 constexpr int kPoaTrRing = 64;      // trace ring (rows)
-constexpr int kPoaNegInf = -1000000000;
+constexpr int kPoaDescRing = 64;
+constexpr int kPoaKeyMin = INT_MIN / 2;
+constexpr int kPoaSlotBytes = 33 * kPoaC * 8 + 16;   // 1072
 
 // Row descriptor, built on the host from the CSR graph and staged through shared memory a chunk
 // ahead of the wavefront, so that the inner loop never waits for a dependent global load:
-//   x: base | in-degree << 8 | flags << 16      y, z, w: six predecessor distances (r - p), 16 bit each
-constexpr unsigned kPoaHead = 1u;        // in == 0: the single "predecessor" is the virtual row
-constexpr unsigned kPoaKeep = 2u;        // some successor is further away than the history ring: also store (H, Eout) in HBM
-constexpr unsigned kPoaSlow = 4u;        // more than six predecessors or a distance >= 65536: read the CSR lists instead
-constexpr int kPoaInline = 6;
-constexpr int kPoaDescRing = 64;
+//   x: base | in-degree << 8 | flags << 16
+//   y: history slot of predecessor 0, 1, 2 (one byte each; kPoaSlotNone when absent, the
+//      virtual-row slots for heads) -- the fast path needs nothing else
+//   z: first CSR edge of the row (slow path)
+constexpr unsigned kPoaHead = 1u;        // in == 0
+constexpr unsigned kPoaKeep = 2u;        // some successor is further away than the history ring: also store the keys in HBM
+constexpr unsigned kPoaSlow = 4u;        // more than three predecessors, or one further back than the ring: generic loop
+constexpr unsigned kPoaLate = 8u;        // head with row index >= L (quirk Q1)
 
 struct PoaFillArgs {
     const uint4* desc;        // [nrows] row descriptors
@@ -56,7 +65,7 @@ struct PoaFillArgs {
     const uint8_t* read;      // [len]
     int len, nrows, nbands, L;
     int M, X, E, O;
-    int2* HE;                 // [nrows][stride] (H, Eout) of every cell
+    int2* HE;                 // [nrows][stride] keys (H*64, Eout*256 + flag) of rows with far successors
     long long stride;         // padded read length (multiple of 32*C)
     uint16_t* trace;          // [nrows][stride]
     unsigned long long* bnd;  // [nbands][nrows] tagged right-boundary elements
@@ -66,7 +75,12 @@ struct PoaFillArgs {
 };
 
 struct PoaSmem {
-    int2 hist[kPoaHist][32][kPoaC];          // (H, Eout) of the last kPoaHist rows, per lane
+    // keys of the last kPoaHist rows (+ the three constant slots): entry [slot][lane + 1] holds the
+    // lane's C columns as (H*64, Eout*256 + flag); entry [slot][0] is the band's left edge, so that
+    // "the previous lane's last column" is one uniform load for every lane
+    // (slot stride 1072 B = 67 x 16: lanes sit one row apart, i.e. lane k reads slot t-k, and an odd
+    // multiple of 16 bytes spreads the eight 16-byte loads of a quarter warp over all banks)
+    unsigned char hist[kPoaSlots * kPoaSlotBytes];
     uint16_t tr[kPoaTrRing][32 * kPoaC];     // trace ring
     int2 bring[kPoaBndRing];                 // left boundary (H(r, j0-1), Fg(r, j0)) by row
     uint4 desc[kPoaDescRing];                // row descriptors
@@ -79,10 +93,32 @@ __device__ __forceinline__ unsigned long long poa_bnd_pack(int H, int F, int fne
     const unsigned hi = ((unsigned)(F - H) & 0xffffu) | ((unsigned)fneg << 16) | (epoch << 17);
     return ((unsigned long long)hi << 32) | (unsigned)H;
 }
+__device__ __forceinline__ int4 lds_s4(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_s4(uint32_t addr, int x, int y, int z, int w)
+{
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w));
+}
 
+// Keys.  The predecessor reduction needs, per column, the maximum, the LOWEST predecessor index
+// that attains it (the reference's tie-break) and, for Eout, whether it was opened at that
+// predecessor.  With the history holding  H*64  and  Eout*256 + flag  (flag 2 = opened, 1 = extended),
+//      max_j (H_j*64 + (63-j))        and        max_j (Eout_j*256 + 4*(63-j) + flag_j)
+// deliver all of it in ONE VIADDMNMX per predecessor and column.
 __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ PoaFillArgs a)
 {
     constexpr int C = kPoaC;
+    constexpr int kSlotBytes = kPoaSlotBytes;
     extern __shared__ __align__(16) unsigned char poa_smem_raw[];
     PoaSmem& sm = *reinterpret_cast<PoaSmem*>(poa_smem_raw);
     const int lane = threadIdx.x;
@@ -92,17 +128,56 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 
     const int E = a.E, O = a.O, OE = a.O + a.E, M = a.M, X = a.X;
     const int R = a.nrows, len = a.len, L = a.L;
+    const int E4 = 4 * E, OE4p1 = 4 * OE + 1;
     const int j0 = (band * 32 + lane) * C;
     uint8_t rc[C];                       // read bytes of this lane's columns (0 = pad: matches nothing)
-#pragma unroll
-    for (int c = 0; c < C; c++) rc[c] = (j0 + c < len) ? a.read[j0 + c] : 0;
-    const bool owns_last = (len - 1 >= j0) && (len - 1 < j0 + C);
+    bool isL[C];                         // column == L (the late-head quirk re-bases F there)
     bool hasN = false;                   // quirk Q3 applies to this lane's strip at all?
 #pragma unroll
-    for (int c = 0; c < C; c++) hasN |= rc[c] == 'N';
+    for (int c = 0; c < C; c++) {
+        rc[c] = (j0 + c < len) ? a.read[j0 + c] : 0;
+        isL[c] = (j0 + c == L);
+        hasN |= rc[c] == 'N';
+    }
+    const bool owns_last = (len - 1 >= j0) && (len - 1 < j0 + C);
     const unsigned long long* bnd_in = a.bnd + (long long)(band - 1) * R;
     unsigned long long* bnd_out = a.bnd + (long long)band * R;
     const bool store_right = (band + 1 < a.nbands) && lane == 31;
+    const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(&sm.hist[0]);
+    const uint32_t my_hist = hist_addr + lane * (C * 8);        // this lane's view: +24 previous lane's last H key, +32.. own columns
+
+    // ---- constant history slots -------------------------------------------------------------------
+    {
+        // "no predecessor": keys of -infinity everywhere (also the left edge)
+        sts_s4(hist_addr + kPoaSlotNone * kSlotBytes + (lane + 1) * 32, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
+        sts_s4(hist_addr + kPoaSlotNone * kSlotBytes + (lane + 1) * 32 + 16, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
+        if (lane == 0) {
+            sts_s4(hist_addr + kPoaSlotNone * kSlotBytes, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
+            sts_s4(hist_addr + kPoaSlotNone * kSlotBytes + 16, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
+        }
+        // virtual rows above a head (c-t-simd.c:176-188): the H key of column c is only ever read
+        // as the DIAGONAL input of column c+1, the E key is Eout_v(c) = Hv(c) + O + E (opened)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const bool late = v == 1;
+            int k[2 * C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int col = j0 + c;
+                const int Hd_next = (late && col + 1 <= L - 1) ? (col + 1) * E : O + (col + 1) * E;   // diagonal input of column col+1
+                const int Hp = (late && col <= L - 1) ? (col + 1) * E : O + (col + 1) * E;            // Hv(col)
+                k[2 * c] = Hd_next * 64;
+                k[2 * c + 1] = (Hp + OE) * 256 + 2;
+            }
+            const uint32_t slot = hist_addr + (kPoaSlotHead + v) * kSlotBytes;
+            sts_s4(slot + (lane + 1) * 32, k[0], k[1], k[2], k[3]);
+            sts_s4(slot + (lane + 1) * 32 + 16, k[4], k[5], k[6], k[7]);
+            if (lane == 0) {   // left edge: diagonal input of column j0
+                const int Hd0 = (late && j0 <= L - 1) ? j0 * E : (j0 == 0 ? 0 : O + j0 * E);
+                sts_s4(slot + 16, 0, 0, Hd0 * 64, 0);
+            }
+        }
+    }
 
     int Hout = 0, Fout = 0, Nout = 0;    // right edge of the previous step: H, Fg(next col), fsource<0
     const int nchunks = (R + 31 + kPoaChunk - 1) / kPoaChunk;
@@ -161,47 +236,42 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 }
                 const uint4 dsc = sm.desc[r & (kPoaDescRing - 1)];
                 const int b = (int)(dsc.x & 0xffu);
-                const int npre = (int)((dsc.x >> 8) & 0xffu);
                 const unsigned flags = dsc.x >> 16;
-                const bool head = flags & kPoaHead;
-                const bool late = head && L > 0 && r >= L;
 
-                // Reduction over the predecessors with KEYS: the history holds H*64 and
-                // Eout*128 + "opened", so  max(H*64 + (63-j))  and  max(Eout*128 + 2*(63-j) + opened)
-                // give the maximum, the LOWEST predecessor index that attains it (the reference's
-                // tie-break) and the opened flag of exactly that predecessor in one VIADDMNMX each.
                 int kd[C], ke[C];
-                if (head) {
 #pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const int col = j0 + c;
-                        int Hd, Hp;
-                        if (late && col <= L - 1) { Hd = col * E; Hp = (col + 1) * E; }       // quirk Q1
-                        else { Hd = col == 0 ? 0 : O + col * E; Hp = O + (col + 1) * E; }
-                        kd[c] = Hd * 64 + 63;                       // predecessor index 0
-                        ke[c] = (Hp + OE) * 128 + 2 * 63 + 1;       // Eout_v = Hv + O + E: opened
+                for (int c = 0; c < C; c++) { kd[c] = kPoaKeyMin; ke[c] = kPoaKeyMin; }
+                if (!(flags & kPoaSlow)) {
+                    // ---- fast path: up to three predecessors, all inside the history ring ----------
+#pragma unroll
+                    for (int j = 0; j < kPoaFast; j++) {
+                        const uint32_t A = my_hist + ((dsc.y >> (8 * j)) & 0xffu) * kSlotBytes;
+                        const int Hd0 = lds_s32(A + 24);
+                        const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
+                        const int wd = 63 - j, we = 4 * (63 - j);
+                        kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
+                        kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
+                        kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
+                        kd[3] = __viaddmax_s32(v23.x, wd, kd[3]);
+                        ke[0] = __viaddmax_s32(v01.y, we, ke[0]);
+                        ke[1] = __viaddmax_s32(v01.w, we, ke[1]);
+                        ke[2] = __viaddmax_s32(v23.y, we, ke[2]);
+                        ke[3] = __viaddmax_s32(v23.w, we, ke[3]);
                     }
                 } else {
-#pragma unroll
-                    for (int c = 0; c < C; c++) { kd[c] = INT_MIN / 2; ke[c] = INT_MIN / 2; }
-                    const int e0 = (flags & kPoaSlow) ? __ldg(a.row_ptr + r) : 0;
-                    unsigned dw = dsc.y;
+                    // ---- slow path: any in-degree, predecessors further back than the ring ----------
+                    const int npre = (int)((dsc.x >> 8) & 0xffu);
+                    const int e0 = (int)dsc.z;
                     for (int j = 0; j < npre; j++) {
-                        int p;
-                        if (flags & kPoaSlow) p = __ldg(a.pred_row + e0 + j);
-                        else {
-                            p = r - (int)(dw & 0xffffu);
-                            dw = (j & 1) ? (j == 1 ? dsc.z : dsc.w) : (dw >> 16);
-                        }
+                        const int p = __ldg(a.pred_row + e0 + j);
                         int4 v01, v23;
                         int Hd0;
-                        if (r - p <= kPoaNear) {
-                            const int slot = p & (kPoaHist - 1);
-                            v01 = *reinterpret_cast<const int4*>(&sm.hist[slot][lane][0]);
-                            v23 = *reinterpret_cast<const int4*>(&sm.hist[slot][lane][2]);
-                            const int hl = sm.hist[slot][lane > 0 ? lane - 1 : 0][C - 1].x;
-                            const int hb = sm.bring[p & (kPoaBndRing - 1)].x * 64;          // (band 0: H(p,-1))
-                            Hd0 = lane > 0 ? hl : hb;
+                        if (p < 0 || r - p <= kPoaNear) {
+                            const int slot = p < 0 ? ((flags & kPoaLate) ? kPoaSlotLate : kPoaSlotHead) : (p & (kPoaHist - 1));
+                            const uint32_t A = my_hist + slot * kSlotBytes;
+                            Hd0 = lds_s32(A + 24);
+                            v01 = lds_s4(A + 32);
+                            v23 = lds_s4(A + 48);
                         } else {
                             const int2* src = a.HE + (long long)p * a.stride + j0;
                             v01 = __ldcg(reinterpret_cast<const int4*>(src));
@@ -210,7 +280,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                             else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p) * 64;
                             else Hd0 = __ldg(a.hneg1 + p) * 64;
                         }
-                        const int wd = 63 - j, we = 2 * (63 - j);
+                        const int wd = 63 - j, we = 4 * (63 - j);
                         kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
                         kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
                         kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
@@ -222,57 +292,67 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     }
                 }
 
-                // ---- the row itself: serial along the strip --------------------------------------
-                int2 outv[C];
+                // ---- the row itself: serial along the strip, scores times four ----------------------
+                // candidates of H tagged with the tie-break priority of c-t-simd.c:484-506: diagonal (3)
+                // beats vertical E (2) beats horizontal F (1); F is carried as 4*Fg + 1
+                const int Fadj = (flags & kPoaLate) ? 4 * O : 0;
+                int F4 = 4 * F + 1;
+                int t4prev = 4 * Hleft + OE4p1;                               // "opened from the left neighbour"
+                const int Hleft_in = Hleft;
+                int ko[2 * C];
                 uint16_t tw[C];
                 int Hlast = 0;
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    const int col = j0 + c;
-                    if (late && col == L) F += O;                              // quirk Q1: carried F re-based
-                    const int bd = kd[c] >> 6, bdj = 63 - (kd[c] & 63);
-                    const int be = ke[c] >> 7, bej = 63 - ((ke[c] >> 1) & 63), eopen = ke[c] & 1;
+                    if (isL[c]) F4 += Fadj;                                    // quirk Q1: carried F re-based at column L
                     const bool match = (int)rc[c] == b;
-                    const int h = bd + (match ? M : X);
-                    // candidates tagged with the tie-break priority of c-t-simd.c:484-506:
-                    // diagonal (3) beats vertical E (2) beats horizontal F (1)
-                    const int Hk = __vimax3_s32(h * 4 + 3, be * 4 + 2, F * 4 + 1);
-                    int H = Hk >> 2;
+                    const int h4 = (kd[c] >> 6) * 4 + (match ? 4 * M + 3 : 4 * X + 3);
+                    const int be4 = ((ke[c] >> 6) & ~3) | 2;                   // 4*be + 2
+                    const int bdj = 63 - (kd[c] & 63), bej = 63 - ((ke[c] >> 2) & 63);
+                    const int eopen = (ke[c] >> 1) & 1;
                     const int s3 = (match ? 42 : 84) + bdj;
+                    int Hk = __vimax3_s32(h4, be4, F4);
                     int src;
                     if (hasN && rc[c] == 'N') {                                // quirk Q3: 'N' columns copy H from the left
-                        H = Hleft;
+                        const int H = Hleft;
                         src = 126;
-                        if (be == H) src = bej;
-                        if (h == H) src = s3;
+                        if ((be4 >> 2) == H) src = bej;
+                        if ((h4 >> 2) == H) src = s3;
+                        Hk = 4 * H;
                     } else {
                         const int tag = Hk & 3;
                         src = tag == 3 ? s3 : (tag == 2 ? bej : 126);
                     }
-                    const int t = H + OE, ae = be + E;
-                    const int eneg = (ae == t);
-                    const int fabs2 = (F - Hleft == OE);                       // |fsource| == 2
-                    const int fneg = (F + E == t);
+                    const int H4 = Hk & ~3;
+                    const int t4 = H4 + OE4p1;                                 // 4(H+O+E)+1: Fg / Eout opened from here
+                    const int a4 = F4 + E4;                                    // 4(Fg+E)+1
+                    const int ae4 = be4 + (E4 - 1);                            // 4(be+E)+1
+                    const int eneg = (ae4 == t4);
+                    const int fabs2 = (F4 == t4prev);                          // |fsource| == 2
+                    const int fneg = (a4 == t4);
                     const int cH = (!fabs2) || fneg_left;                      // (767-769), column >= 2 checked by the walker
                     tw[c] = (uint16_t)(src | (cH << 7) | (bej << 8) | (eopen << 14) | (eneg << 15));
-                    // Eout = max(H+O+E, be+E) with "opened" (ties count as opened) in bit 0 of the doubled max
-                    const int z = max(2 * ae, 2 * t + 1);
-                    outv[c] = make_int2(H * 64, (z & ~1) * 64 + (z & 1));      // (H*64, Eout*128 + opened)
-                    F = max(F + E, t);
-                    Hleft = H;
+                    // Eout = max(H+O+E, be+E); ties count as opened: max(4ae+1, 4t+2)
+                    const int zz = max(ae4, t4 + 1);
+                    ko[2 * c] = H4 * 16;                                       // H*64
+                    ko[2 * c + 1] = (zz & ~3) * 64 + (zz & 3);                 // Eout*256 + flag
+                    F4 = max(a4, t4);
+                    t4prev = t4;
+                    Hleft = H4 >> 2;
                     fneg_left = fneg;
-                    if (j0 + c == len - 1) Hlast = H;
+                    if (j0 + c == len - 1) Hlast = Hleft;
                 }
-                Hout = Hleft; Fout = F; Nout = fneg_left;
-                // history ring, HBM spill for far successors, trace ring
+                Hout = Hleft; Fout = (F4 - 1) >> 2; Nout = fneg_left;
+                // history ring (own columns + the band's left edge), HBM spill for far successors, trace ring
                 {
-                    const int slot = r & (kPoaHist - 1);
-                    *reinterpret_cast<int4*>(&sm.hist[slot][lane][0]) = make_int4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
-                    *reinterpret_cast<int4*>(&sm.hist[slot][lane][2]) = make_int4(outv[2].x, outv[2].y, outv[3].x, outv[3].y);
+                    const uint32_t own = my_hist + (r & (kPoaHist - 1)) * kSlotBytes;
+                    sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
+                    sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
+                    if (lane == 0) sts_u32(own + 24, (uint32_t)(Hleft_in * 64));
                     if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
                         int2* g = a.HE + (long long)r * a.stride + j0;
-                        *reinterpret_cast<int4*>(g) = make_int4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
-                        *reinterpret_cast<int4*>(g + 2) = make_int4(outv[2].x, outv[2].y, outv[3].x, outv[3].y);
+                        *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
+                        *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
                     }
                     *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) =
                         make_uint2((uint32_t)tw[0] | ((uint32_t)tw[1] << 16), (uint32_t)tw[2] | ((uint32_t)tw[3] << 16));

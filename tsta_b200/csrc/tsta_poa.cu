@@ -75,8 +75,8 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         return set_error(TSTA_EINVAL, "bad POA arguments");
     {   // the kernel carries scores times 128 (key packing, poa_fill.cuh)
         const long long amax = std::max(std::max(std::abs(prm->M), std::abs(prm->X)), std::abs(prm->E) + std::abs(prm->O));
-        if (((long long)nrows + len + 2) * amax >= (1LL << 23))
-            return set_error(TSTA_EINVAL, "POA job too large for the int32 key packing: (rows + read length) * max|score| must stay below 2^23");
+        if (((long long)nrows + len + 2) * amax >= (1LL << 22))
+            return set_error(TSTA_EINVAL, "POA job too large for the int32 key packing: (rows + read length) * max|score| must stay below 2^22");
     }
     const int nedges = row_ptr[nrows];
     for (int r = 0; r < nrows; r++)
@@ -84,26 +84,34 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
             return set_error(TSTA_EINVAL, "row %d: in-degree must be 1..41 (reference limit: predecessor index < 42)", r);
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     p->filled = false;
-    // row descriptors (see poa_fill.cuh): base, in-degree, flags, up to six predecessor distances
+    // row descriptors (see poa_fill.cuh): base, in-degree, flags, history slots of up to three predecessors
     p->h_desc.assign((size_t)nrows, make_uint4(0, 0, 0, 0));
     for (int r = 0; r < nrows; r++) {
         const int e0 = row_ptr[r], np = row_ptr[r + 1] - e0;
-        unsigned flags = 0, d[kPoaInline] = {0, 0, 0, 0, 0, 0};
-        if (pred_row[e0] < 0) flags |= kPoaHead;
-        else {
-            if (np > kPoaInline) flags |= kPoaSlow;
+        unsigned flags = 0, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone};
+        if (pred_row[e0] < 0) {
+            flags |= kPoaHead;
+            if (L > 0 && r >= L) flags |= kPoaLate;                 // quirk Q1
+            slot[0] = (flags & kPoaLate) ? kPoaSlotLate : kPoaSlotHead;
+            if (np != 1) return set_error(TSTA_EINVAL, "row %d: a head must have the single entry -1", r);
+        } else {
+            if (np > kPoaFast) flags |= kPoaSlow;
             for (int j = 0; j < np; j++) {
                 const int pr = pred_row[e0 + j];
                 if (pr < 0 || pr >= r) return set_error(TSTA_EINVAL, "row %d: predecessor %d is not an earlier row", r, pr);
                 const int dist = r - pr;
-                if (dist > kPoaNear) p->h_desc[(size_t)pr].x |= kPoaKeep << 16;
-                if (dist >= 65536) flags |= kPoaSlow;
-                else if (j < kPoaInline) d[j] = (unsigned)dist;
+                if (dist > kPoaNear) {
+                    p->h_desc[(size_t)pr].x |= kPoaKeep << 16;      // it must also spill its keys to HBM
+                    flags |= kPoaSlow;
+                }
+                if (j < kPoaFast) slot[j] = (unsigned)(pr & (kPoaHist - 1));
             }
         }
         uint4& q = p->h_desc[(size_t)r];
         q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16);
-        q.y = d[0] | (d[1] << 16); q.z = d[2] | (d[3] << 16); q.w = d[4] | (d[5] << 16);
+        q.y = slot[0] | (slot[1] << 8) | (slot[2] << 16);
+        q.z = (unsigned)e0;
+        q.w = 0;
     }
     const int band_cols = 32 * kPoaC;
     p->nbands = (len + band_cols - 1) / band_cols;
