@@ -528,9 +528,17 @@ def main():
     # --------------------------------------------------------------------------------------
     elif kind == "batch":
         npairs, ln = shape
-        s0, o0, l0, s1, o1, l1 = make_batch(npairs, ln, rank)
+        # inputs and outputs live in page-locked host memory (tsta_host_alloc), as a caller that
+        # streams batches would keep them
+        pins = [api.pinned_copy(x) for x in make_batch(npairs, ln, rank)]
+        s0, o0, l0, s1, o1, l1 = [p.array for p in pins]
+        outs = [api.PinnedArray(npairs, np.int32), api.PinnedArray(npairs, np.int32)]
+        if trace:
+            ops_off = np.arange(npairs, dtype=np.int64) * (2 * ln)
+            outs += [api.PinnedArray(npairs * 2 * ln, np.uint8), api.pinned_copy(ops_off), api.PinnedArray(npairs, np.int32)]
+        out = tuple(p.array for p in outs)
         for _ in range(warmup):
-            r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, **PARAMS)
+            r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, out=out, **PARAMS)
         barrier()
         sampler.start()
         kms, walls = [], []
@@ -538,7 +546,7 @@ def main():
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, **PARAMS)
+            r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, out=out, **PARAMS)
             walls.append(time.perf_counter() - t0)
             kms.append(r.kernel_ms)
         barrier()

@@ -165,6 +165,11 @@ int  tsta_poa_walk(tsta_poa* ctx, int start_row, tsta_poa_step* path, int* nstep
 /* Parity helper: the packed trace of the last fill, nrows x len uint16 (see csrc/poa_fill.cuh). */
 int  tsta_poa_debug_trace(tsta_poa* ctx, uint16_t* out_rows_by_len);
 
+/* Page-locked host memory for large inputs/outputs (batches): copies from/to such buffers run
+ * at full PCIe rate and asynchronously; ordinary malloc'd buffers work too, only slower. */
+void* tsta_host_alloc(size_t bytes);   /* NULL on failure */
+void  tsta_host_free(void* p);
+
 /* ------------------------------------------------------------------------------------ */
 /* Measurement helpers                                                                   */
 /* ------------------------------------------------------------------------------------ */

@@ -97,3 +97,43 @@ def test_psa_driver_swaps_and_default_output(bins, tmp_path, gpu):
     o = ob.psa(x, y)
     assert r.stdout == b"maxsorce=%d\n" % o.maxsorce
     assert (tmp_path / "output.txt").read_bytes() == o.output_bytes()
+
+
+def test_batch_driver_argument_errors(bins, tmp_path):
+    r = run(bins / "TSTA_psa_batch")
+    assert r.returncode == 0 and r.stdout.startswith(b"input file is not specified\n")
+    ob.write_fasta(tmp_path / "a.fa", [b"ACGT", b"ACG"])
+    ob.write_fasta(tmp_path / "b.fa", [b"ACGT"])
+    r = run(bins / "TSTA_psa_batch", "-1", tmp_path / "a.fa", "-2", tmp_path / "b.fa")
+    assert r.returncode == 1 and b"2 records" in r.stderr and b"1 in" in r.stderr
+
+
+@pytest.mark.gpu
+def test_batch_driver_equals_one_process_per_pair(bins, tmp_path, gpu):
+    """TSTA_psa_batch on two multi-record files == TSTA_psa run once per pair."""
+    import random
+    rnd = random.Random(4)
+    xs, ys = [], []
+    for k in range(40):
+        la, lb = rnd.choice([1, 30, 250, 257, 700]), rnd.choice([1, 30, 250, 257, 700])
+        x, y = synth.read_pair(la, lb, 300 + k, rnd.choice([None, 0.05]))
+        xs.append(x)
+        ys.append(y or b"C")
+    ob.write_fasta(tmp_path / "a.fa", xs, width=60)
+    with gzip.open(tmp_path / "b.fa.gz", "wb") as f:
+        for k, y in enumerate(ys):
+            f.write(b">r%d\n" % k + y + b"\n")
+    out = tmp_path / "batch.txt"
+    r = run(bins / "TSTA_psa_batch", "-1", tmp_path / "a.fa", "-2", tmp_path / "b.fa.gz", "-o", out)
+    assert r.returncode == 0, r.stderr
+    want_stdout, want_file = b"", b""
+    for x, y in zip(xs, ys):
+        o = ob.psa(x, y)
+        want_stdout += b"maxsorce=%d\n" % o.maxsorce
+        want_file += o.output_bytes() + b"\n"
+    assert r.stdout == want_stdout
+    assert out.read_bytes() == want_file
+    # score-only, linear gaps, and the multi-GPU flag (clamped to the GPUs present)
+    r = run(bins / "TSTA_psa_batch", "-n", "-O", "0", "-G", "8", "-1", tmp_path / "a.fa", "-2", tmp_path / "b.fa.gz")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == b"".join(b"maxsorce=%d\n" % ob.psa(x, y, O=0, trace=False).maxsorce for x, y in zip(xs, ys))

@@ -226,6 +226,37 @@ def slice_columns(n: int, parts: int, granule: int = 1536):
     return out
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory (tsta_host_alloc); keep the object alive while in use."""
+
+    def __init__(self, shape, dtype):
+        L = load()
+        L.tsta_host_alloc.restype = C.c_void_p
+        L.tsta_host_alloc.argtypes = [C.c_size_t]
+        L.tsta_host_free.argtypes = [C.c_void_p]
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        self._p = L.tsta_host_alloc(max(n * dt.itemsize, 1))
+        if not self._p:
+            raise TstaError(-3, L.tsta_last_error().decode())
+        buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._p:
+                load().tsta_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+def pinned_copy(a: np.ndarray) -> PinnedArray:
+    p = PinnedArray(a.shape, a.dtype)
+    p.array[...] = a
+    return p
+
+
 def measure_dpx_peak():
     """(int32 DPX lane-ops per second, kernel ms) from the on-device microbenchmark."""
     v, ms = C.c_double(), C.c_float()
@@ -281,15 +312,18 @@ def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False) -> BatchResult:
 
 
 def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4, trace=False,
-                     pairs=None, swapped=None) -> BatchResult:
-    """Array form of tsta_psa_batch (what bench.py uses; no per-pair Python objects)."""
+                     pairs=None, swapped=None, out=None) -> BatchResult:
+    """Array form of tsta_psa_batch (what bench.py uses; no per-pair Python objects).
+    `out` = (maxsorce, corner[, ops, ops_off, alen]) preallocated arrays (e.g. pinned) to write into."""
     npairs = len(len0)
-    ms = np.zeros(npairs, dtype=np.int32)
-    corner = np.zeros(npairs, dtype=np.int32)
+    ms = out[0] if out else np.zeros(npairs, dtype=np.int32)
+    corner = out[1] if out else np.zeros(npairs, dtype=np.int32)
     p = Params(M, X, E, O)
     kms = C.c_float()
     ops = ops_off = alen = None
-    if trace:
+    if trace and out and len(out) >= 5:
+        ops, ops_off, alen = out[2], out[3], out[4]
+    elif trace:
         cap = len0.astype(np.int64) + len1.astype(np.int64)
         ops_off = np.zeros(npairs, dtype=np.int64)
         if npairs:

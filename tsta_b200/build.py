@@ -67,6 +67,7 @@ def build_host(force: bool = False) -> list:
         "TSTA_psa": (["tsta_psa_main.c"], ["-DTRACE"]),
         "TSTA_psa_notrace": (["tsta_psa_main.c"], []),
         "TSTA_msa": (["tsta_msa_main.c"], []),
+        "TSTA_psa_batch": (["tsta_psa_batch_main.c"], []),
         "tsta_fasta_dump": (["tsta_fasta_dump_main.c"], []),
     }
     for name, (mains, defs) in targets.items():

@@ -186,6 +186,19 @@ static int choose_strip(int64_t n, int sms, bool trace)
 extern "C" {
 
 const char* tsta_last_error(void) { return g_last_error.c_str(); }
+
+void* tsta_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (ensure_device() != TSTA_OK) return nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        set_error(TSTA_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void tsta_host_free(void* p) { if (p) cudaFreeHost(p); }
 const char* tsta_version(void) { return "tsta_b200 0.2 (sm_100a)"; }
 
 int tsta_device_count(void)
