@@ -28,27 +28,38 @@ static void launch_batch(bool prmt, int blocks, cudaStream_t st, const PsaBatchA
 using namespace tsta;
 
 namespace {
-struct Guard {  // frees everything on every exit path
-    std::vector<void*> dev;
+// Device buffers, stream and events of the calling thread, kept across calls: a caller that
+// streams batches pays for the allocations once (cudaMalloc/cudaFree of hundreds of MB cost
+// more than the kernels of a 1M x 250 bp batch).
+struct BatchCtx {
+    int device = -1;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    ~Guard()
+    DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs;
+    int* h_present = nullptr;   // pinned, 8 words
+    void release()
     {
-        for (void* p : dev) cudaFree(p);
+        DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs};
+        for (DevBuf* b : all) b->release();
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         if (st) cudaStreamDestroy(st);
+        if (h_present) cudaFreeHost(h_present);
+        st = nullptr; e0 = e1 = nullptr; h_present = nullptr; device = -1;
     }
-    template <class T> int alloc(T** out, size_t count)
+    ~BatchCtx() { /* process exit: the CUDA context may already be gone; leave the buffers to it */ }
+};
+thread_local BatchCtx g_ctx;
+
+struct Guard {   // shim over the persistent context: same call sites as a scoped allocator
+    BatchCtx& c;
+    cudaStream_t& st;
+    cudaEvent_t &e0, &e1;
+    explicit Guard(BatchCtx& ctx) : c(ctx), st(ctx.st), e0(ctx.e0), e1(ctx.e1) {}
+    template <class T> int alloc(T** out, size_t count, DevBuf& buf)
     {
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return set_error(TSTA_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-        }
-        dev.push_back(p);
-        *out = static_cast<T*>(p);
+        if (int rc = buf.reserve(std::max<size_t>(count, 1) * sizeof(T))) return rc;
+        *out = buf.as<T>();
         return TSTA_OK;
     }
 };
@@ -86,23 +97,28 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     int dev = 0, sms = 0;
     TSTA_CUDA_TRY(cudaGetDevice(&dev));
     TSTA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    Guard g;
-    TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
-    TSTA_CUDA_TRY(cudaEventCreate(&g.e0));
-    TSTA_CUDA_TRY(cudaEventCreate(&g.e1));
+    if (g_ctx.device != dev) {
+        if (g_ctx.device >= 0) { cudaSetDevice(g_ctx.device); g_ctx.release(); cudaSetDevice(dev); }
+        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.st, cudaStreamNonBlocking));
+        TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e0));
+        TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e1));
+        TSTA_CUDA_TRY(cudaMallocHost((void**)&g_ctx.h_present, 8 * sizeof(int)));
+        g_ctx.device = dev;
+    }
+    Guard g(g_ctx);
 
     uint8_t *d_s0, *d_s1;
     long long *d_off0, *d_off1;
     int *d_len0, *d_len1, *d_ms, *d_corner, *d_ctl;
-    if (int rc = g.alloc(&d_s0, (size_t)tot0)) return rc;
-    if (int rc = g.alloc(&d_s1, (size_t)tot1)) return rc;
-    if (int rc = g.alloc(&d_off0, (size_t)npairs)) return rc;
-    if (int rc = g.alloc(&d_off1, (size_t)npairs)) return rc;
-    if (int rc = g.alloc(&d_len0, (size_t)npairs)) return rc;
-    if (int rc = g.alloc(&d_len1, (size_t)npairs)) return rc;
-    if (int rc = g.alloc(&d_ms, (size_t)npairs)) return rc;
-    if (int rc = g.alloc(&d_corner, (size_t)npairs)) return rc;
-    if (int rc = g.alloc(&d_ctl, 16)) return rc;
+    if (int rc = g.alloc(&d_s0, (size_t)tot0, g_ctx.s0)) return rc;
+    if (int rc = g.alloc(&d_s1, (size_t)tot1, g_ctx.s1)) return rc;
+    if (int rc = g.alloc(&d_off0, (size_t)npairs, g_ctx.off0)) return rc;
+    if (int rc = g.alloc(&d_off1, (size_t)npairs, g_ctx.off1)) return rc;
+    if (int rc = g.alloc(&d_len0, (size_t)npairs, g_ctx.len0)) return rc;
+    if (int rc = g.alloc(&d_len1, (size_t)npairs, g_ctx.len1)) return rc;
+    if (int rc = g.alloc(&d_ms, (size_t)npairs, g_ctx.ms)) return rc;
+    if (int rc = g.alloc(&d_corner, (size_t)npairs, g_ctx.corner)) return rc;
+    if (int rc = g.alloc(&d_ctl, 16, g_ctx.ctl)) return rc;
     static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
     TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0, seqs0, (size_t)tot0, cudaMemcpyHostToDevice, g.st));
     TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1, seqs1, (size_t)tot1, cudaMemcpyHostToDevice, g.st));
@@ -115,8 +131,8 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 16 * sizeof(int), g.st));
     TSTA_CUDA_TRY(launch_byte_presence(d_s0, tot0, reinterpret_cast<unsigned*>(d_ctl + 8), sms * 4, g.st));
     TSTA_CUDA_TRY(launch_byte_presence(d_s1, tot1, reinterpret_cast<unsigned*>(d_ctl + 8), sms * 4, g.st));
-    unsigned present[8];
-    TSTA_CUDA_TRY(cudaMemcpyAsync(present, d_ctl + 8, sizeof present, cudaMemcpyDeviceToHost, g.st));
+    unsigned* present = reinterpret_cast<unsigned*>(g_ctx.h_present);
+    TSTA_CUDA_TRY(cudaMemcpyAsync(present, d_ctl + 8, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, g.st));
     TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
 
     PsaBatchArgs a{};
@@ -139,8 +155,8 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     const long long nwarps = (long long)blocks * kBatchWarps;
     unsigned long long* d_scratch;
     int* d_lastrow;
-    if (int rc = g.alloc(&d_scratch, (size_t)nwarps * (size_t)std::max<int64_t>(max1, 1))) return rc;
-    if (int rc = g.alloc(&d_lastrow, (size_t)nwarps * band_cols)) return rc;
+    if (int rc = g.alloc(&d_scratch, (size_t)nwarps * (size_t)std::max<int64_t>(max1, 1), g_ctx.scratch)) return rc;
+    if (int rc = g.alloc(&d_lastrow, (size_t)nwarps * band_cols, g_ctx.lastrow)) return rc;
 
     a.seqs0 = d_s0; a.seqs1 = d_s1;
     a.off0 = d_off0; a.off1 = d_off1; a.len0 = d_len0; a.len1 = d_len1;
@@ -160,10 +176,10 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     if (want_trace) {
         size_t free_b = 0, total_b = 0;
         TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        if (int rc = g.alloc(&d_ops, (size_t)ops_total)) return rc;
-        if (int rc = g.alloc(&d_ops_off, (size_t)npairs)) return rc;
-        if (int rc = g.alloc(&d_alen, (size_t)npairs)) return rc;
-        if (int rc = g.alloc(&d_dirs_off, (size_t)npairs)) return rc;
+        if (int rc = g.alloc(&d_ops, (size_t)ops_total, g_ctx.ops)) return rc;
+        if (int rc = g.alloc(&d_ops_off, (size_t)npairs, g_ctx.ops_off)) return rc;
+        if (int rc = g.alloc(&d_alen, (size_t)npairs, g_ctx.alen)) return rc;
+        if (int rc = g.alloc(&d_dirs_off, (size_t)npairs, g_ctx.dirs_off)) return rc;
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_ops_off, ops_off, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
         dirs_off.resize((size_t)npairs);
         TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -188,13 +204,8 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                 slice_bytes += b;
                 k1++;
             }
-            uint8_t* slice = nullptr;
-            cudaError_t e = cudaMalloc((void**)&slice, std::max<size_t>(slice_bytes, 256));
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                return set_error(TSTA_ENOMEM, "direction matrices: cudaMalloc(%zu) failed", slice_bytes);
-            }
-            d_dirs = slice;
+            if (int rc = g_ctx.dirs.reserve(std::max<size_t>(slice_bytes, 256))) return rc;
+            d_dirs = g_ctx.dirs.as<uint8_t>();
             TSTA_CUDA_TRY(cudaMemcpyAsync(d_dirs_off + k0, dirs_off.data() + k0, (size_t)(k1 - k0) * 8,
                                           cudaMemcpyHostToDevice, g.st));
         }
@@ -228,7 +239,6 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         cudaError_t le = cudaGetLastError();
         TSTA_CUDA_TRY(cudaEventRecord(g.e1, g.st));
         cudaError_t se = cudaStreamSynchronize(g.st);
-        if (want_trace && d_dirs) { cudaFree(d_dirs); d_dirs = nullptr; }
         TSTA_CUDA_TRY(le);
         TSTA_CUDA_TRY(se);
         float ms = 0.f;
