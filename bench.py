@@ -636,6 +636,13 @@ def main():
                     "kernel_ms": fill_only, "traffic": None,
                     "note": "achieved = cells/s x 7 algorithmic int32 lane-ops (SURVEY.md 8d); the packed kernels issue "
                             "3.25 DPX-class instructions per cell (two cells per instruction)"}
+            try:   # DRAM traffic of the dominant kernel, from the committed ncu capture of this workload
+                tr = json.load(open(ROOT / "profiles" / "r01_traffic.json")).get(a.workload)
+                if tr and world == 1:
+                    roof["traffic"] = tr["bytes"]
+                    roof["traffic_source"] = tr["source"]
+            except Exception:
+                pass
             if trace:
                 hbm = pk.get("hbm_gbs", 6650.0)
                 roof["hbm_write"] = {"achieved": 0.5 * fill_rate / 1e9, "peak": hbm, "unit": "GB/s",

@@ -489,11 +489,8 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
         ta.out = ctl + 2;
         ta.enc = p->packed ? 1 : 0;
         if (getenv("TSTA_TRACE_DEBUG")) { if (!tsta::g_trace_dbg) cudaMalloc(&tsta::g_trace_dbg, 64); ta.dbg = tsta::g_trace_dbg; }
-        static bool trace_attr = false;
-        if (!trace_attr) {
-            TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
-            trace_attr = true;
-        }
+        // (function attributes are per device: set it on every launch, it costs nothing)
+        TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
         psa_trace_kernel<<<1, kTraceThreads, kTraceSmemBytes, p->stream>>>(ta);
         TSTA_CUDA_TRY(cudaGetLastError());
         p->launches++;
