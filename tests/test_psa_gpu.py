@@ -158,3 +158,23 @@ def test_full_size_properties_100k(gpu):
     # (3) linear gaps
     r = gpu.psa(x, y, O=0, trace=True)
     assert rescore(r.a, r.b, 2, -5, -2, 0) == r.corner
+
+
+def test_full_size_properties_200k_traced(gpu):
+    """BASELINE config 3 (4e10 cells, 20 GB of packed directions): the emitted alignment spells
+    both reads, rescoring it gives the corner score the fill reported, the score-only fill agrees,
+    and the walk of a related pair stays exact over 200k rows."""
+    n = 200_000
+    x = synth.random_read(n, 21)
+    y = synth.mutate(x, 0.08, 5)[:n]
+    s0, s1 = ob.order_pair(x, y)
+    r = gpu.psa(x, y, trace=True)
+    assert r.a.replace(b"-", b"") == s0 and r.b.replace(b"-", b"") == s1
+    assert rescore(r.a, r.b, 2, -5, -2, -4) == r.corner
+    r0 = gpu.psa(x, y, trace=False)
+    assert (r0.maxsorce, r0.corner) == (r.maxsorce, r.corner)
+    # unrelated pair of the benchmark shape: alignment is valid and optimal w.r.t. the reported corner
+    u, v = synth.random_read(n, 1), synth.random_read(n, 2)
+    r = gpu.psa(u, v, trace=True)
+    assert r.a.replace(b"-", b"") == u and r.b.replace(b"-", b"") == v
+    assert rescore(r.a, r.b, 2, -5, -2, -4) == r.corner
