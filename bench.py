@@ -12,6 +12,7 @@ Workloads (--workload):
   pair100k          configs[1]: one 100 kbp pair per GPU, score-only            (default)
   pair100k_bands    configs[1], multi-GPU form: ONE pair as column slices over the N GPUs,
                     boundary column by peer stores over NVLink (strong scaling)
+  pair400k_bands    the same for a 400 kbp x 100 kbp pair (too many bands for one GPU's sub-partitions)
   pair100k_trace    one 100 kbp pair per GPU with 4-bit directions in HBM + traceback
   pair200k_trace    configs[2]: 200 kbp pair, 20 GB of packed directions + traceback
   batch250          configs[3]: 1,000,000 pairs of 250 bp per GPU, score-only (tsta_psa_batch)
@@ -57,6 +58,8 @@ WORKLOADS = {
                  "TSTA_psa_notrace: one synthetic 100 kbp x 100 kbp pair per GPU, affine (M2 X-5 E-2 O-4), score-only"),
     "pair100k_bands": ("bands", (100_000, 100_000), False,
                        "TSTA_psa_notrace: ONE synthetic 100 kbp x 100 kbp pair as column slices over all GPUs (NVLink boundary hand-off)"),
+    "pair400k_bands": ("bands", (400_000, 100_000), False,
+                       "TSTA_psa_notrace: ONE synthetic 400 kbp x 100 kbp pair as column slices over all GPUs (more bands than one GPU has sub-partitions)"),
     "pair100k_trace": ("pair", (100_000, 100_000), True,
                        "TSTA_psa: one synthetic 100 kbp x 100 kbp pair per GPU, affine, 4-bit directions in HBM + traceback"),
     "pair200k_trace": ("pair", (200_000, 200_000), True,
