@@ -110,6 +110,57 @@ __device__ __forceinline__ void sts_s4(uint32_t addr, int x, int y, int z, int w
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w));
 }
 
+// One row of one lane's strip (C columns, serial in F).  In: the predecessor keys kd/ke, F4 = 4*Fg+1 and
+// H of the left neighbour; out: the strip's keys (ko), trace words (tw), the right edge (F4, Hleft, fneg_left).
+// Candidates of H are tagged with the tie-break priority of c-t-simd.c:484-506: diagonal (3) beats
+// vertical E (2) beats horizontal F (1).
+template <int C, bool QUIRKS>
+__device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], const uint8_t (&rc)[C], const bool (&isL)[C],
+                                        const int b, const int M, const int X, const int E4, const int OE4p1, const int Fadj,
+                                        int& F4, int& Hleft, int& fneg_left, int (&ko)[2 * C], uint16_t (&tw)[C])
+{
+    int t4prev = 4 * Hleft + OE4p1;                                   // "opened from the left neighbour"
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (QUIRKS && isL[c]) F4 += Fadj;                             // quirk Q1: carried F re-based at column L
+        const bool match = (int)rc[c] == b;
+        const int h4 = (kd[c] >> 6) * 4 + (match ? 4 * M + 3 : 4 * X + 3);
+        const int be4 = ((ke[c] >> 6) & ~3) | 2;                      // 4*be + 2
+        const int bdj = 63 - (kd[c] & 63), bej = 63 - ((ke[c] >> 2) & 63);
+        const int eopen = (ke[c] >> 1) & 1;
+        const int s3 = (match ? 42 : 84) + bdj;
+        int Hk = __vimax3_s32(h4, be4, F4);
+        int src;
+        if (QUIRKS && rc[c] == 'N') {                                 // quirk Q3: 'N' columns copy H from the left
+            const int H = Hleft;
+            src = 126;
+            if ((be4 >> 2) == H) src = bej;
+            if ((h4 >> 2) == H) src = s3;
+            Hk = 4 * H;
+        } else {
+            const int tag = Hk & 3;
+            src = tag == 3 ? s3 : (tag == 2 ? bej : 126);
+        }
+        const int H4 = Hk & ~3;
+        const int t4 = H4 + OE4p1;                                    // 4(H+O+E)+1: Fg / Eout opened from here
+        const int a4 = F4 + E4;                                       // 4(Fg+E)+1
+        const int ae4 = be4 + (E4 - 1);                               // 4(be+E)+1
+        const int eneg = (ae4 == t4);
+        const int fabs2 = (F4 == t4prev);                             // |fsource| == 2
+        const int fneg = (a4 == t4);
+        const int cH = (!fabs2) || fneg_left;                         // (767-769), column >= 2 checked by the walker
+        tw[c] = (uint16_t)(src | (cH << 7) | (bej << 8) | (eopen << 14) | (eneg << 15));
+        // Eout = max(H+O+E, be+E); ties count as opened: max(4ae+1, 4t+2)
+        const int zz = max(ae4, t4 + 1);
+        ko[2 * c] = H4 * 16;                                          // H*64
+        ko[2 * c + 1] = (zz & ~3) * 64 + (zz & 3);                    // Eout*256 + flag
+        F4 = max(a4, t4);
+        t4prev = t4;
+        Hleft = H4 >> 2;
+        fneg_left = fneg;
+    }
+}
+
 // Keys.  The predecessor reduction needs, per column, the maximum, the LOWEST predecessor index
 // that attains it (the reference's tie-break) and, for Eout, whether it was opened at that
 // predecessor.  With the history holding  H*64  and  Eout*256 + flag  (flag 2 = opened, 1 = extended),
@@ -140,6 +191,10 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
         hasN |= rc[c] == 'N';
     }
     const bool owns_last = (len - 1 >= j0) && (len - 1 < j0 + C);
+    const int clast = owns_last ? len - 1 - j0 : 0;
+    bool hasL = false;
+#pragma unroll
+    for (int c = 0; c < C; c++) hasL |= isL[c];
     const unsigned long long* bnd_in = a.bnd + (long long)(band - 1) * R;
     unsigned long long* bnd_out = a.bnd + (long long)band * R;
     const bool store_right = (band + 1 < a.nbands) && lane == 31;
@@ -293,55 +348,16 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 }
 
                 // ---- the row itself: serial along the strip, scores times four ----------------------
-                // candidates of H tagged with the tie-break priority of c-t-simd.c:484-506: diagonal (3)
-                // beats vertical E (2) beats horizontal F (1); F is carried as 4*Fg + 1
-                const int Fadj = (flags & kPoaLate) ? 4 * O : 0;
                 int F4 = 4 * F + 1;
-                int t4prev = 4 * Hleft + OE4p1;                               // "opened from the left neighbour"
                 const int Hleft_in = Hleft;
                 int ko[2 * C];
                 uint16_t tw[C];
-                int Hlast = 0;
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    if (isL[c]) F4 += Fadj;                                    // quirk Q1: carried F re-based at column L
-                    const bool match = (int)rc[c] == b;
-                    const int h4 = (kd[c] >> 6) * 4 + (match ? 4 * M + 3 : 4 * X + 3);
-                    const int be4 = ((ke[c] >> 6) & ~3) | 2;                   // 4*be + 2
-                    const int bdj = 63 - (kd[c] & 63), bej = 63 - ((ke[c] >> 2) & 63);
-                    const int eopen = (ke[c] >> 1) & 1;
-                    const int s3 = (match ? 42 : 84) + bdj;
-                    int Hk = __vimax3_s32(h4, be4, F4);
-                    int src;
-                    if (hasN && rc[c] == 'N') {                                // quirk Q3: 'N' columns copy H from the left
-                        const int H = Hleft;
-                        src = 126;
-                        if ((be4 >> 2) == H) src = bej;
-                        if ((h4 >> 2) == H) src = s3;
-                        Hk = 4 * H;
-                    } else {
-                        const int tag = Hk & 3;
-                        src = tag == 3 ? s3 : (tag == 2 ? bej : 126);
-                    }
-                    const int H4 = Hk & ~3;
-                    const int t4 = H4 + OE4p1;                                 // 4(H+O+E)+1: Fg / Eout opened from here
-                    const int a4 = F4 + E4;                                    // 4(Fg+E)+1
-                    const int ae4 = be4 + (E4 - 1);                            // 4(be+E)+1
-                    const int eneg = (ae4 == t4);
-                    const int fabs2 = (F4 == t4prev);                          // |fsource| == 2
-                    const int fneg = (a4 == t4);
-                    const int cH = (!fabs2) || fneg_left;                      // (767-769), column >= 2 checked by the walker
-                    tw[c] = (uint16_t)(src | (cH << 7) | (bej << 8) | (eopen << 14) | (eneg << 15));
-                    // Eout = max(H+O+E, be+E); ties count as opened: max(4ae+1, 4t+2)
-                    const int zz = max(ae4, t4 + 1);
-                    ko[2 * c] = H4 * 16;                                       // H*64
-                    ko[2 * c + 1] = (zz & ~3) * 64 + (zz & 3);                 // Eout*256 + flag
-                    F4 = max(a4, t4);
-                    t4prev = t4;
-                    Hleft = H4 >> 2;
-                    fneg_left = fneg;
-                    if (j0 + c == len - 1) Hlast = Hleft;
-                }
+                // the two quirks (late heads re-base F at column L, 'N' columns copy H) touch a handful of
+                // cells of a whole job: they get their own copy of the row code, the common one is free of them
+                if (hasN || (hasL && (flags & kPoaLate)))
+                    poa_row<C, true>(kd, ke, rc, isL, b, M, X, E4, OE4p1, (flags & kPoaLate) ? 4 * O : 0, F4, Hleft, fneg_left, ko, tw);
+                else
+                    poa_row<C, false>(kd, ke, rc, isL, b, M, X, E4, OE4p1, 0, F4, Hleft, fneg_left, ko, tw);
                 Hout = Hleft; Fout = (F4 - 1) >> 2; Nout = fneg_left;
                 // history ring (own columns + the band's left edge), HBM spill for far successors, trace ring
                 {
@@ -357,7 +373,12 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) =
                         make_uint2((uint32_t)tw[0] | ((uint32_t)tw[1] << 16), (uint32_t)tw[2] | ((uint32_t)tw[3] << 16));
                 }
-                if (owns_last) a.lastsorce[r] = Hlast;
+                if (owns_last) {
+                    int hk = ko[0];
+#pragma unroll
+                    for (int c = 1; c < C; c++) hk = clast == c ? ko[2 * c] : hk;
+                    a.lastsorce[r] = hk >> 6;
+                }
                 st_relaxed_u64_if(bnd_out + r, poa_bnd_pack(Hout, Fout, Nout, a.epoch), store_right);
             }
         }
