@@ -617,7 +617,7 @@ def main():
                              "(process start-up / CUDA context creation excluded; whole-process wall in wall_s)")
         h2d = int(sum(len(r) for r in reads[1:]) + 30 * cells_rank / ln)     # reads + CSR graph + descriptors per round
         d2h = int(12 * cells_rank / ln)                                      # lastsorce + path steps per round
-        extra = {"kernel_ms": step_ms, "wall_s": wall_s}
+        extra = {"kernel_ms": step_ms, "wall_s": wall_s, "driver_loop_s_per_run": ls, "process_wall_s_per_run": ws}
         fill_rate = cells_rank / (fill_only * 1e-3)
 
     value = cells_total / (step_ms * 1e-3) / 1e9
