@@ -95,6 +95,7 @@ struct __align__(16) PsaWarpSmem16 {
     // compile-time s (no wrap inside a chunk)
     uint2 rowring[kRing16 + kMaxChunkRows];
     uint32_t in[kMaxChunkRows];  // left boundary of the current chunk: lo16 = H, hi16 = Ft, relative to base
+    uint2 in2[kMaxChunkRows];    // dual-pair mode: (H of pair A | pair B, F state of pair A | pair B)
 };
 
 // Per-lane register state.
@@ -143,22 +144,28 @@ constexpr uint32_t kM1 = 0x00010001u, kM2 = 0x00020002u, kM3 = 0x00030003u;
 //   ring_next ring entry of this lane's NEXT row at s = 0
 //   bnd_row   boundary element of the row virtual lane 63 works on at s = 0
 //   dir_addr  TRACE: this lane's direction word of step s = 0 in the step ring
-template <int C, bool TRACE, bool CHECK>
+//   DUAL      the two halves are two independent PAIRS (short reads): no low -> high hand-off in lane 0,
+//             both halves work on row t-k, the boundary of both comes from sm.in2, m_hi = rows of pair B
+template <int C, bool TRACE, bool CHECK, bool DUAL = false>
 __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const int s, const int m, const int lane,
                                            const PsaConst16& k, const uint32_t selH, const uint32_t selF,
                                            const int src_lane, const uint32_t in_addr, const uint32_t ring_next,
                                            unsigned long long* bnd_row, const bool store_right,
-                                           const uint32_t outHF, const unsigned epoch, const uint32_t dir_addr)
+                                           const uint32_t outHF, const unsigned epoch, const uint32_t dir_addr,
+                                           const int m_hi = 0)
 {
     const uint32_t rH = __shfl_sync(kFullMask, L.Hout, src_lane);
     const uint32_t rF = __shfl_sync(kFullMask, L.Fout, src_lane);
-    const uint32_t in = lds_u32(in_addr + s * 4);                 // broadcast: the band's left boundary
+    uint32_t in, inF;                                             // broadcast: the band's left boundary
+    if (DUAL) { const uint2 v = lds_u2(in_addr + s * 8); in = v.x; inF = v.y; }
+    else { in = lds_u32(in_addr + s * 4); inF = in; }
     const uint2 T = L.Tnext;
     L.Tnext = lds_u2(ring_next + s * 8);
 
     uint32_t mask = 0xffffffffu;
     if (CHECK) {
-        const bool lo = (unsigned)(t - lane) < (unsigned)m, hi = (unsigned)(t - lane - 32) < (unsigned)m;
+        const bool lo = (unsigned)(t - lane) < (unsigned)m;
+        const bool hi = DUAL ? (unsigned)(t - lane) < (unsigned)m_hi : (unsigned)(t - lane - 32) < (unsigned)m;
         mask = (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
     }
     uint32_t Hn[C];
@@ -174,7 +181,7 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
             hE[c] = vaddmax2(L.Et[c], k.OE2, X);                  // max(Eg, h)
         }
         Hin = prmtu(rH, in, selH);
-        F = prmtu(rF, in, selF);
+        F = prmtu(rF, inF, selF);
         // ---- serial chain + epilogue --------------------------------------------------------
 #pragma unroll
         for (int c = 0; c < C; c++) {
@@ -249,7 +256,7 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
         L.Fout = F;
     }
     // right edge of the band = high halves of lane 31, row t-63: (H | Fg << 16) absolute modulo 2^16
-    {
+    if (!DUAL) {
         const uint32_t e = vadd2(prmtu(L.Hout, L.Fout, 0x7632u), outHF);
         const bool doit = store_right && (!CHECK || (unsigned)(t - 63) < (unsigned)m);
         st_relaxed_pair_if(bnd_row + s, e, epoch, doit);
@@ -463,6 +470,123 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     return ms32;
 }
 
+// ---------------------------------------------------------------------------------------
+// DUAL-PAIR sweep (score-only): two independent short pairs per warp, pair A in the low halves
+// and pair B in the high halves, 32 virtual lanes x C columns each (reads of up to 32*C bases
+// fit one band).  Compared with the 64-virtual-lane sweep a 250 bp pair needs 250+31 steps
+// shared by two pairs instead of 250+63 for one, and far fewer of them are ramp steps.
+// Each half has its own base.  B may be absent (nB == 0 or mB == 0).
+// ---------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int nA, const uint8_t* s1A, const int mA,
+                                                 const uint8_t* s0B, const int nB, const uint8_t* s1B, const int mB,
+                                                 const PsaScoring& sc, const uint32_t* tab4, PsaWarpSmem16<C, false>& sm,
+                                                 const int lane, int& msA, int& msB, int& cornerA, int& cornerB)
+{
+    constexpr int CH = 32;
+    const int Es = sc.E, OEs = sc.O + sc.E;
+    PsaConst16 k;
+    k.E2 = dup16(Es); k.OE2 = dup16(OEs); k.Kf2 = 0; k.E1 = 0;
+    const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, 1);
+    const int j0 = lane * C;
+    int baseA = sc.O + sc.E, baseB = baseA;                      // H(-1, 0)
+    PsaLane16<C> L;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int j = j0 + c;
+        const uint32_t cl = j < nA ? sc.lut[s0A[j]] : 8u;
+        const uint32_t chh = j < nB ? 4u + sc.lut[s0B[j]] : 12u;
+        const uint32_t nl = cl < 8u ? (cl | ((8u | cl) << 4)) : 0x88u;
+        const uint32_t nh = chh < 12u ? (chh | ((8u | chh) << 4)) : 0xccu;
+        L.sel[c] = nl | (nh << 8);
+        const int h = sc.O + (j + 1) * sc.E;                      // H(-1, j); Eg(0,j) = H(-1,j)+O+E, carried minus (O+E)
+        L.Et[c] = pack16(h - baseA, h - baseB);
+        L.Hup[c] = pack16(h - baseA - (j + 1 >= nA ? padlow : 0), h - baseB - (j + 1 >= nB ? padlow : 0));
+        L.cEb[c] = 0;
+    }
+    {
+        const int d = j0 == 0 ? 0 : sc.O + j0 * sc.E;             // H(-1, j0-1)
+        L.diag = pack16(d - baseA - (j0 >= nA ? padlow : 0), d - baseB - (j0 >= nB ? padlow : 0));
+    }
+    L.ms = kMin16x2;
+    L.Hout = 0;
+    L.Fout = 0;
+    int ms32A = INT_MIN, ms32B = INT_MIN;
+
+    const int m = max(mA, mB), mmin = min(mA, mB);
+    const int nsteps = m + 31;
+    const int nchunks = (nsteps + CH - 1) / CH;
+    const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in2);
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
+    const uint32_t selHF = lane == 0 ? 0x7654u : 0x3210u;        // lane 0: both halves from the boundary, others from lane k-1
+    const int src_lane = (lane + 31) & 31;
+
+    __syncwarp();
+    if (lane < m) ring16_put(sm, lane, make_uint2(lane < mA ? tab4[s1A[lane]] : 0u, lane < mB ? tab4[s1B[lane]] : 0u));
+    uint32_t rawA = (CH + lane < mA) ? s1A[CH + lane] : 0u, rawB = (CH + lane < mB) ? s1B[CH + lane] : 0u;
+    __syncwarp();
+    L.Tnext = sm.rowring[0];
+
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int t0 = ch * CH;
+        {   // re-centre each half on its own lane-0 column
+            const uint32_t e0 = __shfl_sync(kFullMask, L.Et[0], 0);
+            const int dA = lo16(e0), dB = mB > 0 ? hi16(e0) : 0;
+            ms32A = max(ms32A, lo16(L.ms) + baseA);
+            ms32B = max(ms32B, hi16(L.ms) + baseB);
+            const uint32_t nd = pack16(-dA, -dB);
+#pragma unroll
+            for (int c = 0; c < C; c++) { L.Hup[c] = vadd2(L.Hup[c], nd); L.Et[c] = vadd2(L.Et[c], nd); }
+            L.diag = vadd2(L.diag, nd);
+            L.Hout = vadd2(L.Hout, nd);
+            L.Fout = vadd2(L.Fout, nd);
+            L.ms = kMin16x2;
+            baseA += dA;
+            baseB += dB;
+        }
+        {   // next chunk's row tables, this chunk's left boundary (column -1 of both pairs: closed form)
+            const int rown = t0 + CH + lane;
+            if (rown < m) ring16_put(sm, rown, make_uint2(rown < mA ? tab4[rawA & 0xffu] : 0u, rown < mB ? tab4[rawB & 0xffu] : 0u));
+            const int rownn = rown + CH;
+            rawA = rownn < mA ? s1A[rownn] : 0u;
+            rawB = rownn < mB ? s1B[rownn] : 0u;
+            const int row = t0 + lane;
+            if (row < m) {
+                const int hb = sc.O + (row + 1) * sc.E;           // H(i,-1); Fg(i,0) = H(i,-1)+O+E, so Ft = H(i,-1)
+                const uint32_t v = pack16(hb - baseA, hb - baseB);
+                sm.in2[lane] = make_uint2(v, v);
+            }
+        }
+        __syncwarp();
+        const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
+        if (t0 >= 31 && t0 + CH - 1 < mmin) {
+#pragma unroll
+            for (int s = 0; s < CH; s++)
+                psa_step16<C, false, false, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                  nullptr, false, 0u, 0u, 0u, mB);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < CH; s++)
+                psa_step16<C, false, true, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                 nullptr, false, 0u, 0u, 0u, mB);
+        }
+        __syncwarp();
+    }
+    ms32A = max(ms32A, lo16(L.ms) + baseA);
+    ms32B = max(ms32B, hi16(L.ms) + baseB);
+    msA = warp_max(ms32A);
+    msB = warp_max(ms32B);
+    // corners: H(m-1, n-1) sits in lane (n-1)/C, column (n-1)%C
+    uint32_t hA = L.Hup[0], hB = L.Hup[0];
+#pragma unroll
+    for (int c = 1; c < C; c++) {
+        hA = ((nA - 1) % C) == c ? L.Hup[c] : hA;
+        hB = ((nB - 1) % C) == c ? L.Hup[c] : hB;
+    }
+    cornerA = nA > 0 ? lo16(__shfl_sync(kFullMask, hA, max(nA - 1, 0) / C)) + baseA : 0;
+    cornerB = nB > 0 ? hi16(__shfl_sync(kFullMask, hB, max(nB - 1, 0) / C)) + baseB : 0;
+}
+
 // 256-entry byte -> 4 x int8 substitution table (codes 0..3) for the packed PRMT.
 __device__ __forceinline__ void psa_build_tab4(uint32_t* tab4, const PsaScoring& sc, int S, int tid, int nthreads)
 {
@@ -555,6 +679,41 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch16_kernel(const __grid_co
             const bool real = n > 0 && m > 0;
             a.maxsorce[k] = real ? max(-100, ms / S) : -100;   // seed: psa.c:110,590
             a.corner[k] = real ? __ldcg(lastrow + (n - 1) - b.lastrow_col0) / S : 0;
+        }
+        __syncwarp();
+    }
+}
+
+// Short reads (every s0 <= 32*C): persistent warps take TWO pairs per ticket and sweep them together.
+template <int C, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) psa_batch16_dual_kernel(const __grid_constant__ PsaBatchArgs a)
+{
+    __shared__ PsaWarpSmem16<C, false> sm[WARPS];
+    __shared__ uint32_t tab4[256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    psa_build_tab4(tab4, a.sc, 1, threadIdx.x, 32 * WARPS);
+    __syncthreads();
+    while (true) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(a.ticket, 2ull);
+        k = __shfl_sync(kFullMask, k, 0);
+        if (k >= (unsigned long long)a.npairs) break;
+        const bool hasB = k + 1 < (unsigned long long)a.npairs;
+        const int nA = a.len0[k], mA = a.len1[k];
+        const int nB = hasB ? a.len0[k + 1] : 0, mB = hasB ? a.len1[k + 1] : 0;
+        int msA = INT_MIN, msB = INT_MIN, cA = 0, cB = 0;
+        if (max(mA, mB) > 0)
+            psa_sweep_dual16<C>(a.seqs0 + a.off0[k], nA, a.seqs1 + a.off1[k], mA,
+                                a.seqs0 + (hasB ? a.off0[k + 1] : 0), nB, a.seqs1 + (hasB ? a.off1[k + 1] : 0), mB,
+                                a.sc, tab4, sm[w], lane, msA, msB, cA, cB);
+        if (lane == 0) {
+            const bool realA = nA > 0 && mA > 0, realB = nB > 0 && mB > 0;
+            a.maxsorce[k] = realA ? max(-100, msA) : -100;      // seed: psa.c:110,590
+            a.corner[k] = realA ? cA : 0;
+            if (hasB) {
+                a.maxsorce[k + 1] = realB ? max(-100, msB) : -100;
+                a.corner[k + 1] = realB ? cB : 0;
+            }
         }
         __syncwarp();
     }

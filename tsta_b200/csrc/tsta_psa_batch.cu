@@ -146,6 +146,9 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     const char* off16 = getenv("TSTA_PSA_PACKED");
     const bool packed = !(off16 && atoi(off16) == 0) &&
                         psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, C16, K);
+    const char* offd = getenv("TSTA_PSA_DUAL");
+    const bool dual = packed && !want_trace && max0 <= 256 && !(offd && atoi(offd) == 0) &&
+                      psa16_fits(prm->M, prm->X, prm->E, prm->O, 1, 8, K);
     const int C = packed ? C16 : ((max0 <= 128) ? 4 : 8);
     const int band_cols = (packed ? 64 : 32) * C;
 
@@ -228,6 +231,10 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
             t.cols_per_band = band_cols;
             t.ops = d_ops; t.ops_off = d_ops_off + k0; t.alen = d_alen + k0;
             psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
+        } else if (packed && dual) {
+            // short reads: two pairs per warp (psa_sweep_dual16), 32*Cd columns each
+            if (max0 <= 128) psa_batch16_dual_kernel<4, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            else psa_batch16_dual_kernel<8, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
         } else if (packed) {
             if (C == 2) psa_batch16_kernel<2, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
             else if (C == 4) psa_batch16_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
