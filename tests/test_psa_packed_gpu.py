@@ -118,3 +118,27 @@ def test_packed_batch_vs_oracle(gpu, env):
             for k, (x, y) in enumerate(pairs):
                 o = ob.psa(x, y, *prm, trace=False)
                 assert (r.maxsorce[k], r.corner[k]) == (o.maxsorce, o.corner), (k, len(x), len(y), prm)
+
+
+@pytest.mark.parametrize("lens", [[1, 2, 30, 64, 100, 127, 128], [129, 200, 250, 255, 256]])
+def test_dual_pair_mode_with_traceback(gpu, env, lens):
+    """Short reads: two pairs per warp (one per int16 half).  Odd pair count, unequal lengths in
+    the two halves, traceback, against the oracle and against the one-pair-per-warp path."""
+    rnd = random.Random(len(lens))
+    pairs = []
+    for k in range(101):
+        la, lb = rnd.choice(lens), rnd.choice(lens)
+        x, y = synth.read_pair(la, lb, 64000 + k, rnd.choice([None, 0.05, 0.15]))
+        pairs.append((x, y or b"A"))
+    for prm in [(2, -5, -2, -4), (2, -5, -2, 0), (1, -1, -1, 0)]:
+        env.pop("TSTA_PSA_DUAL", None)
+        r = gpu.psa_batch(pairs, *prm, trace=True)
+        env["TSTA_PSA_DUAL"] = "0"
+        r1 = gpu.psa_batch(pairs, *prm, trace=True)
+        np.testing.assert_array_equal(r.maxsorce, r1.maxsorce)
+        np.testing.assert_array_equal(r.corner, r1.corner)
+        for k, (x, y) in enumerate(pairs):
+            o = ob.psa(x, y, *prm)
+            assert (r.maxsorce[k], r.corner[k]) == (o.maxsorce, o.corner), (k, len(x), len(y), prm)
+            assert r.output_bytes(k) == o.output_bytes(), (k, len(x), len(y), prm)
+            assert r1.output_bytes(k) == o.output_bytes()

@@ -204,7 +204,7 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
         }
         const uint32_t Hraw = prmtu(rH, in, selH);                // bit 0 / 16: cF of this lane's first column
         Hin = Hraw & ~kM3;
-        F = prmtu(rF, in, selF);                                  // flagged Fg state
+        F = prmtu(rF, inF, selF);                                 // flagged Fg state
         uint32_t f1 = Hraw & kM1;
         // ---- serial chain + epilogue --------------------------------------------------------
         uint32_t acc[(C + 3) / 4];
@@ -305,6 +305,38 @@ __device__ __forceinline__ void psa_flush_dirs16(const uint32_t* dirw, const Psa
         }
         uint4* dst = reinterpret_cast<uint4*>(b.dirs + (long long)r * b.dirs_stride + (long long)b.band * kRowBytes + part * 16);
         __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+}
+
+// Dual-pair mode: the finished direction rows [lo, hi) of ONE of the two pairs (half = 0: pair A in
+// the low halves, 1: pair B in the high halves); row r of virtual lane k was produced at step r + k.
+// A row is 32*C columns = 16*C bytes.
+template <int C>
+__device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint8_t* dirs, int half, int lo, int hi, int lane)
+{
+    constexpr int kRowBytes = 16 * C;
+    constexpr int kUnits = kRowBytes / 16;              // C == 4: 4 units, C == 8: 8 units
+    constexpr int kW = C == 8 ? 2 : 1;
+    const int units = (hi - lo) * kUnits;
+    for (int u = lane; u < units; u += 32) {
+        const int r = lo + u / kUnits, part = u % kUnits;
+        uint32_t w[4];
+        if (C == 8) {           // 4 bytes per lane: 4 lanes per unit
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int v = part * 4 + q;
+                w[q] = dirw[(((r + v) & (kDirSteps - 1)) * 32 + v) * kW + half];
+            }
+        } else {                // C == 4: 2 bytes per lane: 8 lanes per unit
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int v0 = part * 8 + 2 * q, v1 = v0 + 1;
+                const uint32_t a = dirw[((r + v0) & (kDirSteps - 1)) * 32 + v0];
+                const uint32_t c = dirw[((r + v1) & (kDirSteps - 1)) * 32 + v1];
+                w[q] = (half ? (a >> 16) : (a & 0xffffu)) | ((half ? (c >> 16) : (c & 0xffffu)) << 16);
+            }
+        }
+        __stcs(reinterpret_cast<uint4*>(dirs + (long long)r * kRowBytes + part * 16), make_uint4(w[0], w[1], w[2], w[3]));
     }
 }
 
@@ -477,19 +509,23 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
 // shared by two pairs instead of 250+63 for one, and far fewer of them are ramp steps.
 // Each half has its own base.  B may be absent (nB == 0 or mB == 0).
 // ---------------------------------------------------------------------------------------
-template <int C>
+template <int C, bool TRACE>
 __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int nA, const uint8_t* s1A, const int mA,
                                                  const uint8_t* s0B, const int nB, const uint8_t* s1B, const int mB,
-                                                 const PsaScoring& sc, const uint32_t* tab4, PsaWarpSmem16<C, false>& sm,
+                                                 uint8_t* dirsA, uint8_t* dirsB,
+                                                 const PsaScoring& sc, const uint32_t* tab4, PsaWarpSmem16<C, TRACE>& sm,
                                                  const int lane, int& msA, int& msB, int& cornerA, int& cornerB)
 {
     constexpr int CH = 32;
-    const int Es = sc.E, OEs = sc.O + sc.E;
+    constexpr int S = TRACE ? 4 : 1;
+    static_assert(!TRACE || C == 4 || C == 8, "traced dual strips");
+    const int Es = S * sc.E, OEs = S * (sc.O + sc.E) + (TRACE ? 2 : 0);
     PsaConst16 k;
-    k.E2 = dup16(Es); k.OE2 = dup16(OEs); k.Kf2 = 0; k.E1 = 0;
-    const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, 1);
+    k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.Kf2 = dup16(max(Es, OEs) - 2); k.E1 = dup16(Es + 1);
+    const int shiftOE = TRACE ? 0 : OEs;                         // score-only: gap states are carried minus (O+E)
+    const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, S);
     const int j0 = lane * C;
-    int baseA = sc.O + sc.E, baseB = baseA;                      // H(-1, 0)
+    int baseA = S * (sc.O + sc.E), baseB = baseA;                // H(-1, 0)
     PsaLane16<C> L;
 #pragma unroll
     for (int c = 0; c < C; c++) {
@@ -499,13 +535,14 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
         const uint32_t nl = cl < 8u ? (cl | ((8u | cl) << 4)) : 0x88u;
         const uint32_t nh = chh < 12u ? (chh | ((8u | chh) << 4)) : 0xccu;
         L.sel[c] = nl | (nh << 8);
-        const int h = sc.O + (j + 1) * sc.E;                      // H(-1, j); Eg(0,j) = H(-1,j)+O+E, carried minus (O+E)
-        L.Et[c] = pack16(h - baseA, h - baseB);
+        const int h = S * (sc.O + (j + 1) * sc.E);                // H(-1, j); Eg(0,j) = H(-1,j)+O+E, opened
+        const int eo = OEs - shiftOE;
+        L.Et[c] = pack16(h + eo - baseA, h + eo - baseB);
         L.Hup[c] = pack16(h - baseA - (j + 1 >= nA ? padlow : 0), h - baseB - (j + 1 >= nB ? padlow : 0));
         L.cEb[c] = 0;
     }
     {
-        const int d = j0 == 0 ? 0 : sc.O + j0 * sc.E;             // H(-1, j0-1)
+        const int d = S * (j0 == 0 ? 0 : sc.O + j0 * sc.E);       // H(-1, j0-1)
         L.diag = pack16(d - baseA - (j0 >= nA ? padlow : 0), d - baseB - (j0 >= nB ? padlow : 0));
     }
     L.ms = kMin16x2;
@@ -518,6 +555,7 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
     const int nchunks = (nsteps + CH - 1) / CH;
     const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in2);
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
+    const uint32_t dirw_addr = (uint32_t)__cvta_generic_to_shared(sm.dirw) + lane * (C == 8 ? 8 : 4);
     const uint32_t selHF = lane == 0 ? 0x7654u : 0x3210u;        // lane 0: both halves from the boundary, others from lane k-1
     const int src_lane = (lane + 31) & 31;
 
@@ -531,7 +569,8 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
         const int t0 = ch * CH;
         {   // re-centre each half on its own lane-0 column
             const uint32_t e0 = __shfl_sync(kFullMask, L.Et[0], 0);
-            const int dA = lo16(e0), dB = mB > 0 ? hi16(e0) : 0;
+            int dA = lo16(e0), dB = mB > 0 ? hi16(e0) : 0;
+            if (TRACE) { dA &= ~3; dB &= ~3; }
             ms32A = max(ms32A, lo16(L.ms) + baseA);
             ms32B = max(ms32B, hi16(L.ms) + baseB);
             const uint32_t nd = pack16(-dA, -dB);
@@ -552,25 +591,39 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
             rawB = rownn < mB ? s1B[rownn] : 0u;
             const int row = t0 + lane;
             if (row < m) {
-                const int hb = sc.O + (row + 1) * sc.E;           // H(i,-1); Fg(i,0) = H(i,-1)+O+E, so Ft = H(i,-1)
-                const uint32_t v = pack16(hb - baseA, hb - baseB);
-                sm.in2[lane] = make_uint2(v, v);
+                const int hb = S * (sc.O + (row + 1) * sc.E);     // H(i,-1); Fg(i,0) = H(i,-1)+O+E, opened
+                const int fb = hb + OEs - shiftOE;
+                sm.in2[lane] = make_uint2(pack16(hb - baseA, hb - baseB), pack16(fb - baseA, fb - baseB));
             }
         }
         __syncwarp();
         const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
+        const uint32_t dir_addr = dirw_addr + (t0 & (kDirSteps - 1)) * (C == 8 ? 256 : 128);
         if (t0 >= 31 && t0 + CH - 1 < mmin) {
+            if constexpr (!TRACE) {
 #pragma unroll
-            for (int s = 0; s < CH; s++)
-                psa_step16<C, false, false, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
-                                                  nullptr, false, 0u, 0u, 0u, mB);
+                for (int s = 0; s < CH; s++)
+                    psa_step16<C, TRACE, false, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                      nullptr, false, 0u, 0u, dir_addr, mB);
+            } else {
+#pragma unroll 2
+                for (int s = 0; s < CH; s++)
+                    psa_step16<C, TRACE, false, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                      nullptr, false, 0u, 0u, dir_addr, mB);
+            }
         } else {
 #pragma unroll 1
             for (int s = 0; s < CH; s++)
-                psa_step16<C, false, true, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
-                                                 nullptr, false, 0u, 0u, 0u, mB);
+                psa_step16<C, TRACE, true, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                 nullptr, false, 0u, 0u, dir_addr, mB);
         }
         __syncwarp();
+        if (TRACE) {
+            // rows every lane has finished: [t0 - 31, t0 + CH - 31)
+            psa_flush_dirs16_dual<C>(sm.dirw, dirsA, 0, min(mA, max(0, t0 - 31)), min(mA, max(0, t0 + CH - 31)), lane);
+            if (mB > 0) psa_flush_dirs16_dual<C>(sm.dirw, dirsB, 1, min(mB, max(0, t0 - 31)), min(mB, max(0, t0 + CH - 31)), lane);
+            __syncwarp();
+        }
     }
     ms32A = max(ms32A, lo16(L.ms) + baseA);
     ms32B = max(ms32B, hi16(L.ms) + baseB);
@@ -685,13 +738,14 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch16_kernel(const __grid_co
 }
 
 // Short reads (every s0 <= 32*C): persistent warps take TWO pairs per ticket and sweep them together.
-template <int C, int WARPS>
+template <int C, bool TRACE, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) psa_batch16_dual_kernel(const __grid_constant__ PsaBatchArgs a)
 {
-    __shared__ PsaWarpSmem16<C, false> sm[WARPS];
+    constexpr int S = TRACE ? 4 : 1;
+    __shared__ PsaWarpSmem16<C, TRACE> sm[WARPS];
     __shared__ uint32_t tab4[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    psa_build_tab4(tab4, a.sc, 1, threadIdx.x, 32 * WARPS);
+    psa_build_tab4(tab4, a.sc, S, threadIdx.x, 32 * WARPS);
     __syncthreads();
     while (true) {
         unsigned long long k = 0;
@@ -703,16 +757,17 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch16_dual_kernel(const __gr
         const int nB = hasB ? a.len0[k + 1] : 0, mB = hasB ? a.len1[k + 1] : 0;
         int msA = INT_MIN, msB = INT_MIN, cA = 0, cB = 0;
         if (max(mA, mB) > 0)
-            psa_sweep_dual16<C>(a.seqs0 + a.off0[k], nA, a.seqs1 + a.off1[k], mA,
-                                a.seqs0 + (hasB ? a.off0[k + 1] : 0), nB, a.seqs1 + (hasB ? a.off1[k + 1] : 0), mB,
-                                a.sc, tab4, sm[w], lane, msA, msB, cA, cB);
+            psa_sweep_dual16<C, TRACE>(a.seqs0 + a.off0[k], nA, a.seqs1 + a.off1[k], mA,
+                                       a.seqs0 + (hasB ? a.off0[k + 1] : 0), nB, a.seqs1 + (hasB ? a.off1[k + 1] : 0), mB,
+                                       TRACE ? a.dirs + a.dirs_off[k] : nullptr, (TRACE && hasB) ? a.dirs + a.dirs_off[k + 1] : nullptr,
+                                       a.sc, tab4, sm[w], lane, msA, msB, cA, cB);
         if (lane == 0) {
             const bool realA = nA > 0 && mA > 0, realB = nB > 0 && mB > 0;
-            a.maxsorce[k] = realA ? max(-100, msA) : -100;      // seed: psa.c:110,590
-            a.corner[k] = realA ? cA : 0;
+            a.maxsorce[k] = realA ? max(-100, msA / S) : -100;      // seed: psa.c:110,590
+            a.corner[k] = realA ? cA / S : 0;
             if (hasB) {
-                a.maxsorce[k + 1] = realB ? max(-100, msB) : -100;
-                a.corner[k + 1] = realB ? cB : 0;
+                a.maxsorce[k + 1] = realB ? max(-100, msB / S) : -100;
+                a.corner[k + 1] = realB ? cB / S : 0;
             }
         }
         __syncwarp();

@@ -147,10 +147,11 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     const bool packed = !(off16 && atoi(off16) == 0) &&
                         psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, C16, K);
     const char* offd = getenv("TSTA_PSA_DUAL");
-    const bool dual = packed && !want_trace && max0 <= 256 && !(offd && atoi(offd) == 0) &&
-                      psa16_fits(prm->M, prm->X, prm->E, prm->O, 1, 8, K);
-    const int C = packed ? C16 : ((max0 <= 128) ? 4 : 8);
-    const int band_cols = (packed ? 64 : 32) * C;
+    const bool dual = packed && max0 <= 256 && !(offd && atoi(offd) == 0) &&
+                      psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, 8, K);
+    const int Cd = max0 <= 128 ? 4 : 8;                          // dual-pair mode: 32*Cd columns, one band
+    const int C = dual ? Cd : (packed ? C16 : ((max0 <= 128) ? 4 : 8));
+    const int band_cols = dual ? 32 * Cd : (packed ? 64 : 32) * C;
 
     // persistent grid: ~24 warps per SM (register-limited), never more warps than pairs
     int blocks = sms * 6;
@@ -219,7 +220,10 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 8, g.st));
         TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
         if (want_trace) {
-            if (packed) {   // two warps per CTA: the step ring of direction words is 16 KB per warp
+            if (packed && dual) {   // short reads: two pairs per warp; the step ring is 16 KB (Cd = 4) or 32 KB (Cd = 8) per warp
+                if (Cd == 4) psa_batch16_dual_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
+                else psa_batch16_dual_kernel<8, true, 1><<<blocks * 4, 32, 0, g.st>>>(a);
+            } else if (packed) {   // two warps per CTA: the step ring of direction words is 16 KB per warp
                 if (C == 2) psa_batch16_kernel<2, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
                 else psa_batch16_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
             } else if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
@@ -233,8 +237,8 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
             psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
         } else if (packed && dual) {
             // short reads: two pairs per warp (psa_sweep_dual16), 32*Cd columns each
-            if (max0 <= 128) psa_batch16_dual_kernel<4, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
-            else psa_batch16_dual_kernel<8, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            if (Cd == 4) psa_batch16_dual_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            else psa_batch16_dual_kernel<8, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
         } else if (packed) {
             if (C == 2) psa_batch16_kernel<2, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
             else if (C == 4) psa_batch16_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
