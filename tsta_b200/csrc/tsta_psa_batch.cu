@@ -187,13 +187,22 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_ops_off, ops_off, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
         dirs_off.resize((size_t)npairs);
         TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        dirs_budget = std::min<size_t>(free_b / 2, (size_t)48 << 30);
+        // slices of direction matrices: as large as HBM allows -- a slice with fewer pairs than
+        // resident warps (3552) leaves sub-partitions idle
+        dirs_budget = (size_t)((double)(free_b + g_ctx.dirs.cap) * 0.8);
     }
     auto dirs_bytes = [&](int64_t k) -> size_t {
         const size_t nb = (size_t)((len0[k] + band_cols - 1) / band_cols);
         return (size_t)len1[k] * nb * (size_t)(band_cols / 2);
     };
 
+    size_t slice_target = dirs_budget;   // equal slices: a short last slice would leave most warps idle
+    if (want_trace) {
+        size_t total = 0;
+        for (int64_t k = 0; k < npairs; k++) total += (dirs_bytes(k) + 255) & ~(size_t)255;
+        const size_t nslices = std::max<size_t>(1, (total + dirs_budget - 1) / std::max<size_t>(dirs_budget, 1));
+        slice_target = std::min(dirs_budget, (total + nslices - 1) / nslices + ((size_t)64 << 20));
+    }
     float total_ms = 0.f;
     int64_t k0 = 0;
     while (k0 < npairs) {
@@ -203,7 +212,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
             k1 = k0;
             while (k1 < npairs) {
                 const size_t b = (dirs_bytes(k1) + 255) & ~(size_t)255;
-                if (k1 > k0 && slice_bytes + b > dirs_budget) break;
+                if (k1 > k0 && slice_bytes + b > slice_target) break;
                 dirs_off[(size_t)k1] = (long long)slice_bytes;
                 slice_bytes += b;
                 k1++;
