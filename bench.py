@@ -90,8 +90,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, interval_ms: int = 100):
         self.device = device
+        self.interval_ms = interval_ms
         self.proc = None
         self.path = None
 
@@ -101,7 +102,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", str(self.interval_ms)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -415,7 +416,8 @@ def main():
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     dpx_peak, _ = api.measure_dpx_peak()
-    sampler = ClockSampler(local_rank)
+    # (nvidia-smi polling takes driver locks; the MSA driver makes many small CUDA calls per read, so it is sampled at 1 Hz)
+    sampler = ClockSampler(local_rank, 1000 if kind == "msa" else 100)
     extra = {}
     scaling = "weak"
     kernel_name = "psa_pair16_kernel"
