@@ -51,6 +51,7 @@ constexpr int kPoaSlotBytes = 33 * kPoaC * 8 + 16;   // 1072
 //   y: history slot of predecessor 0, 1, 2 (one byte each; kPoaSlotNone when absent, the
 //      virtual-row slots for heads) -- the fast path needs nothing else
 //   z: first CSR edge of the row (slow path)
+//   w: for rows flagged kPoaKeep: their row in the HBM spill
 constexpr unsigned kPoaHead = 1u;        // in == 0
 constexpr unsigned kPoaKeep = 2u;        // some successor is further away than the history ring: also store the keys in HBM
 constexpr unsigned kPoaSlow = 4u;        // more than three predecessors, or one further back than the ring: generic loop
@@ -65,7 +66,7 @@ struct PoaFillArgs {
     const uint8_t* read;      // [len]
     int len, nrows, nbands, L;
     int M, X, E, O;
-    int2* HE;                 // [nrows][stride] keys (H*64, Eout*256 + flag) of rows with far successors
+    int2* HE;                 // [nkeep][stride] keys (H*64, Eout*256 + flag) of the rows with far successors (desc.w = their slot)
     long long stride;         // padded read length (multiple of 32*C)
     uint16_t* trace;          // [nrows][stride]
     unsigned long long* bnd;  // [nbands][nrows] tagged right-boundary elements
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                             v01 = lds_s4(A + 32);
                             v23 = lds_s4(A + 48);
                         } else {
-                            const int2* src = a.HE + (long long)p * a.stride + j0;
+                            const int2* src = a.HE + (long long)__ldg(&a.desc[p].w) * a.stride + j0;
                             v01 = __ldcg(reinterpret_cast<const int4*>(src));
                             v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
                     if (lane == 0) sts_u32(own + 24, (uint32_t)(Hleft_in * 64));
                     if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
-                        int2* g = a.HE + (long long)r * a.stride + j0;
+                        int2* g = a.HE + (long long)dsc.w * a.stride + j0;
                         *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
                         *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
                     }

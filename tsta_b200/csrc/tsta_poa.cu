@@ -111,7 +111,12 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16);
         q.y = slot[0] | (slot[1] << 8) | (slot[2] << 16);
         q.z = (unsigned)e0;
-        q.w = 0;
+    }
+    // rows with a successor further away than the history ring get a row of the HBM spill
+    size_t nkeep = 0;
+    for (int r = 0; r < nrows; r++) {
+        uint4& q = p->h_desc[(size_t)r];
+        q.w = ((q.x >> 16) & kPoaKeep) ? (unsigned)nkeep++ : 0u;
     }
     const int band_cols = 32 * kPoaC;
     p->nbands = (len + band_cols - 1) / band_cols;
@@ -130,7 +135,8 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     if (int rc = p->d_path.reserve((size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
     {   // grow generously: the graph gains rows every round
         const size_t cells = (size_t)nrows * (size_t)p->stride;
-        if (cells * sizeof(int2) > p->d_HE.cap) if (int rc = p->d_HE.reserve(cells * sizeof(int2) * 5 / 4)) return rc;
+        const size_t spill = std::max<size_t>(nkeep, 1) * (size_t)(((len + 32 * kPoaC - 1) / (32 * kPoaC)) * 32 * kPoaC) * sizeof(int2);
+        if (spill > p->d_HE.cap) if (int rc = p->d_HE.reserve(spill * 5 / 4)) return rc;
         if (cells * 2 > p->d_trace.cap) if (int rc = p->d_trace.reserve(cells * 2 * 5 / 4)) return rc;
         const size_t need = (size_t)p->nbands * (size_t)nrows * 8;
         if (need > p->d_bnd.cap) {
