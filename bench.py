@@ -634,13 +634,18 @@ def main():
                     "traffic": None, "note": "no algorithmic op count is defined for the graph DP (2*in+5 int ops per cell, "
                                              "SURVEY.md 8d); see profiles/ for the ncu summary"}
         else:
-            roof = {"bound": "int32 DPX/ALU issue (not hbm, not tensor: SURVEY.md 8d)", "achieved": achieved,
-                    "peak": dpx_peak / 1e12, "unit": "Tlaneop/s", "frac": achieved / (dpx_peak / 1e12),
-                    "peak_source": "measured live: dependency-free VIADDMNMX loop (tsta_measure_dpx_peak)",
+            # The packed kernels advance two cells per lane-op (int16 x 2), so their issue roofline is
+            # twice the measured int32 VIADDMNMX rate; int32 kernels (fallback) are held against the rate itself.
+            packf = 2 if config.get("packed_int16x2", True) else 1
+            peak = packf * dpx_peak / 1e12
+            roof = {"bound": "integer-ALU / DPX issue (not hbm, not tensor: SURVEY.md 8d)", "achieved": achieved,
+                    "peak": peak, "unit": "Tlaneop/s", "frac": achieved / peak,
+                    "peak_source": "measured live: dependency-free VIADDMNMX loop (tsta_measure_dpx_peak) = %.2f Tlaneop/s, x%d "
+                                   "cells per lane-op for the %s kernels" % (dpx_peak / 1e12, packf, "int16x2" if packf == 2 else "int32"),
                     "algorithmic_ops_per_cell": LANE_OPS_PER_CELL, "kernel": kernel_name,
                     "kernel_ms": fill_only, "traffic": None,
-                    "note": "achieved = cells/s x 7 algorithmic int32 lane-ops (SURVEY.md 8d); the packed kernels issue "
-                            "3.25 DPX-class instructions per cell (two cells per instruction)"}
+                    "note": "achieved = cells/s x 7 algorithmic lane-ops (SURVEY.md 8d). ncu (profiles/): ALU pipe 38 % active for the "
+                            "single 100 kbp pair (latency/ramp bound, DESIGN.md 5), 90-92 % for the batched kernels"}
             try:   # DRAM traffic of the dominant kernel, from the committed ncu capture of this workload
                 tr = json.load(open(ROOT / "profiles" / "r01_traffic.json")).get(a.workload)
                 if tr and world == 1:
