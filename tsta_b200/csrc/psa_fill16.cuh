@@ -98,6 +98,16 @@ struct __align__(16) PsaWarpSmem16 {
     uint2 in2[kMaxChunkRows];    // dual-pair mode: (H of pair A | pair B, F state of pair A | pair B)
 };
 
+// Dual-pair mode (short reads): the skew is 31 steps instead of 63, so with 16-row chunks a ring of
+// 64 steps is enough -- half the shared memory, twice the warps per SM for the traced kernels.
+constexpr int kDirStepsDual = 64;
+template <int C, bool TRACE>
+struct __align__(16) PsaWarpSmem16D {
+    uint32_t dirw[TRACE ? kDirStepsDual * 32 * (C == 8 ? 2 : 1) : 4];
+    uint2 rowring[kRing16 + kMaxChunkRows];
+    uint2 in2[kMaxChunkRows];
+};
+
 // Per-lane register state.
 template <int C>
 struct PsaLane16 {
@@ -311,7 +321,7 @@ __device__ __forceinline__ void psa_flush_dirs16(const uint32_t* dirw, const Psa
 // Dual-pair mode: the finished direction rows [lo, hi) of ONE of the two pairs (half = 0: pair A in
 // the low halves, 1: pair B in the high halves); row r of virtual lane k was produced at step r + k.
 // A row is 32*C columns = 16*C bytes.
-template <int C>
+template <int C, int STEPS>
 __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint8_t* dirs, int half, int lo, int hi, int lane)
 {
     constexpr int kRowBytes = 16 * C;
@@ -325,14 +335,14 @@ __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int v = part * 4 + q;
-                w[q] = dirw[(((r + v) & (kDirSteps - 1)) * 32 + v) * kW + half];
+                w[q] = dirw[(((r + v) & (STEPS - 1)) * 32 + v) * kW + half];
             }
         } else {                // C == 4: 2 bytes per lane: 8 lanes per unit
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int v0 = part * 8 + 2 * q, v1 = v0 + 1;
-                const uint32_t a = dirw[((r + v0) & (kDirSteps - 1)) * 32 + v0];
-                const uint32_t c = dirw[((r + v1) & (kDirSteps - 1)) * 32 + v1];
+                const uint32_t a = dirw[((r + v0) & (STEPS - 1)) * 32 + v0];
+                const uint32_t c = dirw[((r + v1) & (STEPS - 1)) * 32 + v1];
                 w[q] = (half ? (a >> 16) : (a & 0xffffu)) | ((half ? (c >> 16) : (c & 0xffffu)) << 16);
             }
         }
@@ -513,10 +523,11 @@ template <int C, bool TRACE>
 __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int nA, const uint8_t* s1A, const int mA,
                                                  const uint8_t* s0B, const int nB, const uint8_t* s1B, const int mB,
                                                  uint8_t* dirsA, uint8_t* dirsB,
-                                                 const PsaScoring& sc, const uint32_t* tab4, PsaWarpSmem16<C, TRACE>& sm,
+                                                 const PsaScoring& sc, const uint32_t* tab4, PsaWarpSmem16D<C, TRACE>& sm,
                                                  const int lane, int& msA, int& msB, int& cornerA, int& cornerB)
 {
-    constexpr int CH = 32;
+    constexpr int CH = TRACE ? 16 : 32;                          // traced: 16-row chunks keep the step ring at 64 entries
+    constexpr int kSteps = kDirStepsDual;
     constexpr int S = TRACE ? 4 : 1;
     static_assert(!TRACE || C == 4 || C == 8, "traced dual strips");
     const int Es = S * sc.E, OEs = S * (sc.O + sc.E) + (TRACE ? 2 : 0);
@@ -560,8 +571,9 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
     const int src_lane = (lane + 31) & 31;
 
     __syncwarp();
-    if (lane < m) ring16_put(sm, lane, make_uint2(lane < mA ? tab4[s1A[lane]] : 0u, lane < mB ? tab4[s1B[lane]] : 0u));
-    uint32_t rawA = (CH + lane < mA) ? s1A[CH + lane] : 0u, rawB = (CH + lane < mB) ? s1B[CH + lane] : 0u;
+    const bool stager = lane < CH;
+    if (stager && lane < m) ring16_put(sm, lane, make_uint2(lane < mA ? tab4[s1A[lane]] : 0u, lane < mB ? tab4[s1B[lane]] : 0u));
+    uint32_t rawA = (stager && CH + lane < mA) ? s1A[CH + lane] : 0u, rawB = (stager && CH + lane < mB) ? s1B[CH + lane] : 0u;
     __syncwarp();
     L.Tnext = sm.rowring[0];
 
@@ -585,12 +597,12 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
         }
         {   // next chunk's row tables, this chunk's left boundary (column -1 of both pairs: closed form)
             const int rown = t0 + CH + lane;
-            if (rown < m) ring16_put(sm, rown, make_uint2(rown < mA ? tab4[rawA & 0xffu] : 0u, rown < mB ? tab4[rawB & 0xffu] : 0u));
+            if (stager && rown < m) ring16_put(sm, rown, make_uint2(rown < mA ? tab4[rawA & 0xffu] : 0u, rown < mB ? tab4[rawB & 0xffu] : 0u));
             const int rownn = rown + CH;
-            rawA = rownn < mA ? s1A[rownn] : 0u;
-            rawB = rownn < mB ? s1B[rownn] : 0u;
+            rawA = (stager && rownn < mA) ? s1A[rownn] : 0u;
+            rawB = (stager && rownn < mB) ? s1B[rownn] : 0u;
             const int row = t0 + lane;
-            if (row < m) {
+            if (stager && row < m) {
                 const int hb = S * (sc.O + (row + 1) * sc.E);     // H(i,-1); Fg(i,0) = H(i,-1)+O+E, opened
                 const int fb = hb + OEs - shiftOE;
                 sm.in2[lane] = make_uint2(pack16(hb - baseA, hb - baseB), pack16(fb - baseA, fb - baseB));
@@ -598,7 +610,7 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
         }
         __syncwarp();
         const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
-        const uint32_t dir_addr = dirw_addr + (t0 & (kDirSteps - 1)) * (C == 8 ? 256 : 128);
+        const uint32_t dir_addr = dirw_addr + (t0 & (kSteps - 1)) * (C == 8 ? 256 : 128);
         if (t0 >= 31 && t0 + CH - 1 < mmin) {
             if constexpr (!TRACE) {
 #pragma unroll
@@ -620,8 +632,8 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
         __syncwarp();
         if (TRACE) {
             // rows every lane has finished: [t0 - 31, t0 + CH - 31)
-            psa_flush_dirs16_dual<C>(sm.dirw, dirsA, 0, min(mA, max(0, t0 - 31)), min(mA, max(0, t0 + CH - 31)), lane);
-            if (mB > 0) psa_flush_dirs16_dual<C>(sm.dirw, dirsB, 1, min(mB, max(0, t0 - 31)), min(mB, max(0, t0 + CH - 31)), lane);
+            psa_flush_dirs16_dual<C, kSteps>(sm.dirw, dirsA, 0, min(mA, max(0, t0 - 31)), min(mA, max(0, t0 + CH - 31)), lane);
+            if (mB > 0) psa_flush_dirs16_dual<C, kSteps>(sm.dirw, dirsB, 1, min(mB, max(0, t0 - 31)), min(mB, max(0, t0 + CH - 31)), lane);
             __syncwarp();
         }
     }
@@ -742,7 +754,7 @@ template <int C, bool TRACE, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) psa_batch16_dual_kernel(const __grid_constant__ PsaBatchArgs a)
 {
     constexpr int S = TRACE ? 4 : 1;
-    __shared__ PsaWarpSmem16<C, TRACE> sm[WARPS];
+    __shared__ PsaWarpSmem16D<C, TRACE> sm[WARPS];
     __shared__ uint32_t tab4[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     psa_build_tab4(tab4, a.sc, S, threadIdx.x, 32 * WARPS);

@@ -230,8 +230,8 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
         if (want_trace) {
             if (packed && dual) {   // short reads: two pairs per warp; the step ring is 16 KB (Cd = 4) or 32 KB (Cd = 8) per warp
-                if (Cd == 4) psa_batch16_dual_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
-                else psa_batch16_dual_kernel<8, true, 1><<<blocks * 4, 32, 0, g.st>>>(a);
+                if (Cd == 4) psa_batch16_dual_kernel<4, true, 4><<<blocks, 128, 0, g.st>>>(a);
+                else psa_batch16_dual_kernel<8, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
             } else if (packed) {   // two warps per CTA: the step ring of direction words is 16 KB per warp
                 if (C == 2) psa_batch16_kernel<2, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
                 else psa_batch16_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
