@@ -629,7 +629,7 @@ def main():
         pk = peaks()
         achieved = fill_rate * LANE_OPS_PER_CELL / 1e12
         if kind == "msa":
-            roof = {"bound": "int32 ALU issue (POA fill; int32, in-degree dependent)", "achieved": fill_rate / 1e9,
+            roof = {"bound": "int_alu", "bound_note": "int32 ALU issue, latency bound (POA fill; in-degree dependent)", "achieved": fill_rate / 1e9,
                     "peak": None, "unit": "GCUPS", "frac": None, "kernel": kernel_name, "kernel_ms": fill_only,
                     "traffic": None, "note": "no algorithmic op count is defined for the graph DP (2*in+5 int ops per cell, "
                                              "SURVEY.md 8d); see profiles/ for the ncu summary"}
@@ -638,7 +638,7 @@ def main():
             # twice the measured int32 VIADDMNMX rate; int32 kernels (fallback) are held against the rate itself.
             packf = 2 if config.get("packed_int16x2", True) else 1
             peak = packf * dpx_peak / 1e12
-            roof = {"bound": "integer-ALU / DPX issue (not hbm, not tensor: SURVEY.md 8d)", "achieved": achieved,
+            roof = {"bound": "int_alu", "bound_note": "integer-ALU / DPX issue (neither hbm nor tensor: SURVEY.md 8d)", "achieved": achieved,
                     "peak": peak, "unit": "Tlaneop/s", "frac": achieved / peak,
                     "peak_source": "measured live: dependency-free VIADDMNMX loop (tsta_measure_dpx_peak) = %.2f Tlaneop/s, x%d "
                                    "cells per lane-op for the %s kernels" % (dpx_peak / 1e12, packf, "int16x2" if packf == 2 else "int32"),
