@@ -114,6 +114,16 @@ int  tsta_psa_plan_upload_slice(tsta_psa_plan* plan, const tsta_params* p, const
 int  tsta_psa_plan_inbox_handle(tsta_psa_plan* plan, unsigned char handle[64]);
 int  tsta_psa_plan_connect_right(tsta_psa_plan* plan, const unsigned char handle[64]);
 int  tsta_psa_plan_connect_right_local(tsta_psa_plan* plan, tsta_psa_plan* right);
+/* Traceback of a sliced pair (plans created with want_trace = 1): after all slices have run, walk
+ * them right to left.  trace_from walks THIS slice's direction matrix from (start_i, its last column)
+ * in state start_forced (0 free, 2 forced left, 1 forced up) until it leaves through the left edge
+ * (end_i >= 0: continue in the left neighbour with end_i / end_forced) or the top (end_i < 0: done).
+ * The last slice starts at (m-1, free).  ops() copies the nops moves of the last trace_from in walk
+ * order (1 = both bases, 0 = base of s0 against a gap, 2 = gap against a base of s1); the caller
+ * concatenates them right to left and adds the leftovers of psa/psa.c:497-510. */
+int  tsta_psa_plan_trace_from(tsta_psa_plan* plan, int64_t start_i, int start_forced,
+                              int64_t* end_i, int* end_forced, int64_t* nops, float* ms);
+int  tsta_psa_plan_ops(tsta_psa_plan* plan, uint8_t* out, int64_t nops);
 
 /* Many independent pairs.  seqs0/seqs1 are concatenations; off*[k], len*[k] locate pair k
  * (len0[k] >= len1[k], caller swaps).  Outputs are arrays of npairs entries.  When

@@ -68,6 +68,9 @@ def load() -> C.CDLL:
     L.tsta_psa_plan_inbox_handle.argtypes = [C.c_void_p, C.c_char_p]
     L.tsta_psa_plan_connect_right.argtypes = [C.c_void_p, C.c_char_p]
     L.tsta_psa_plan_connect_right_local.argtypes = [C.c_void_p, C.c_void_p]
+    L.tsta_psa_plan_trace_from.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+    L.tsta_psa_plan_ops.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.tsta_set_device.argtypes = [C.c_int]
     L.tsta_measure_dpx_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if hasattr(L, "tsta_psa_batch"):
@@ -164,6 +167,14 @@ class PsaPlan:
     def connect_right_local(self, right: "PsaPlan") -> None:
         _check(load().tsta_psa_plan_connect_right_local(self._h, right._h))
 
+    def trace_from(self, start_i: int, start_forced: int = 0):
+        """Walk this (slice's) direction matrix; returns (moves uint8[nops], end_i, end_forced, ms)."""
+        ei, ef, n, ms = C.c_int64(), C.c_int(), C.c_int64(), C.c_float()
+        _check(load().tsta_psa_plan_trace_from(self._h, start_i, start_forced, C.byref(ei), C.byref(ef), C.byref(n), C.byref(ms)))
+        ops = np.zeros(max(n.value, 1), dtype=np.uint8)
+        _check(load().tsta_psa_plan_ops(self._h, ops.ctypes.data, n.value))
+        return ops[:n.value], ei.value, ef.value, ms.value
+
     def launch(self) -> None:
         _check(load().tsta_psa_plan_launch(self._h))
 
@@ -209,6 +220,20 @@ class PsaPlan:
             self.close()
         except Exception:
             pass
+
+
+def assemble_alignment(s0: bytes, s1: bytes, moves: np.ndarray):
+    """(a, b) strings of TSTA_psa's -o file from the moves in walk order (end of the alignment first),
+    including the leftovers of psa/psa.c:497-510 (rest of s0 against gaps, then rest of s1)."""
+    n0 = int(np.count_nonzero(moves != 2))      # bases of s0 consumed
+    n1 = int(np.count_nonzero(moves != 0))
+    tail = np.concatenate([moves, np.zeros(len(s0) - n0, dtype=np.uint8), np.full(len(s1) - n1, 2, dtype=np.uint8)])
+    ops = tail[::-1]
+    A = np.full(len(ops), ord("-"), dtype=np.uint8)
+    B = np.full(len(ops), ord("-"), dtype=np.uint8)
+    A[ops != 2] = np.frombuffer(s0, dtype=np.uint8)
+    B[ops != 0] = np.frombuffer(s1, dtype=np.uint8)
+    return A.tobytes(), B.tobytes()
 
 
 def slice_columns(n: int, parts: int, granule: int = 1536):

@@ -29,7 +29,9 @@ struct PsaTraceArgs {
     long long dirs_stride;   // bytes per row
     int n, m;
     uint8_t* ops;            // [n + m] moves in walk order
-    int* out;                // out[0] = number of moves written, out[1] = final i, out[2] = final j
+    int* out;                // out[0] = number of moves written, out[1] = final i, out[2] = final j, out[3] = final forced state
+    int start_i, start_j;    // where the walk starts ((m-1, n-1) for a whole pair; a slice continues its right neighbour's walk)
+    int start_forced;        // 0 free, 2 forced left, 1 forced up (tag form)
     int enc;                 // back code: 0 = (1 diagonal, 0 left, 2 up), 1 = (3 diagonal, 2 left, 1 up)
     long long* dbg;          // optional: walker cycles, total cycles, windows, prefetch hits
 };
@@ -100,9 +102,9 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const P
     const int tid = threadIdx.x;
 
     if (tid == 0) {
-        s_i = a.m - 1;
-        s_j = a.n - 1;
-        s_forced = 0;
+        s_i = a.start_i;
+        s_j = a.start_j;
+        s_forced = a.start_forced;
         s_nops = 0;
     }
     __syncthreads();
@@ -189,6 +191,7 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const P
         a.out[0] = s_nops;
         a.out[1] = s_i;
         a.out[2] = s_j;
+        a.out[3] = s_forced;
         if (a.dbg) {
             a.dbg[0] = dbg_walk; a.dbg[1] = clock64() - dbg_total0; a.dbg[2] = dbg_windows; a.dbg[3] = dbg_hits;
         }

@@ -255,7 +255,6 @@ int tsta_psa_plan_upload_slice(tsta_psa_plan* p, const tsta_params* prm, const c
                                int64_t col0, int64_t n_total, const char* s1, int64_t m, int has_left, int has_right)
 {
     if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
-    if (p->want_trace) return set_error(TSTA_EINVAL, "column slices are score-only (the traceback of a sliced pair is not built yet)");
     if (n_slice <= 0 || m <= 0 || col0 < 0 || col0 + n_slice > n_total || (has_left != 0) != (col0 > 0) ||
         (has_right != 0) != (col0 + n_slice < n_total))
         return set_error(TSTA_EINVAL, "bad slice: columns [%lld, %lld) of %lld", (long long)col0, (long long)(col0 + n_slice), (long long)n_total);
@@ -480,7 +479,7 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
     TSTA_CUDA_TRY(cudaGetLastError());
     p->launches++;
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
-    if (p->want_trace) {
+    if (p->want_trace && !(p->has_left || p->has_right)) {   // (slices are walked later, right to left: tsta_psa_plan_trace_from)
         PsaTraceArgs ta{};
         ta.dirs = fa.dirs;
         ta.dirs_stride = fa.dirs_stride;
@@ -488,6 +487,7 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
         ta.ops = p->d_ops.as<uint8_t>();
         ta.out = ctl + 2;
         ta.enc = p->packed ? 1 : 0;
+        ta.start_i = fa.m - 1; ta.start_j = fa.n - 1; ta.start_forced = 0;
         if (getenv("TSTA_TRACE_DEBUG")) { if (!tsta::g_trace_dbg) cudaMalloc(&tsta::g_trace_dbg, 64); ta.dbg = tsta::g_trace_dbg; }
         // (function attributes are per device: set it on every launch, it costs nothing)
         TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
@@ -518,7 +518,7 @@ int tsta_psa_plan_fetch(tsta_psa_plan* p, tsta_psa_result* out)
         TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
         out->maxsorce = std::max(-100, p->h_small[1] / S);
         out->corner = p->h_small[7] / S;
-        if (p->want_trace) {
+        if (p->want_trace && !(p->has_left || p->has_right)) {
             nops = p->h_small[2];
             fi = p->h_small[3];
             fj = p->h_small[4];
@@ -527,7 +527,7 @@ int tsta_psa_plan_fetch(tsta_psa_plan* p, tsta_psa_result* out)
                 TSTA_CUDA_TRY(cudaMemcpy(ops.data(), p->d_ops.p, (size_t)nops, cudaMemcpyDeviceToHost));
         }
     }
-    if (p->want_trace) {
+    if (p->want_trace && !(p->has_left || p->has_right)) {   // (slices: tsta_psa_plan_trace_from / _ops)
         ops.resize((size_t)(n + m));
         // leftovers: rest of s0 against gaps, then rest of s1 (psa.c:497-510)
         while (fj >= 0) { ops[(size_t)nops++] = 0; fj--; }
@@ -587,6 +587,45 @@ int tsta_psa_plan_info(tsta_psa_plan* p, int* launches, int* cols_per_lane, int*
 }
 
 int tsta_psa_plan_packed(tsta_psa_plan* p) { return p && p->packed ? 1 : 0; }
+
+int tsta_psa_plan_trace_from(tsta_psa_plan* p, int64_t start_i, int start_forced,
+                             int64_t* end_i, int* end_forced, int64_t* nops, float* ms)
+{
+    if (!p || !p->ran || !p->want_trace) return set_error(TSTA_EINVAL, "plan not run with traceback");
+    if (!end_i || !end_forced || !nops) return set_error(TSTA_EINVAL, "NULL argument");
+    if (start_i < 0 || start_i >= p->m || start_forced < 0 || start_forced > 2)
+        return set_error(TSTA_EINVAL, "bad start of the walk (row %lld, state %d)", (long long)start_i, start_forced);
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    int* ctl = p->d_ctl.as<int>();
+    PsaTraceArgs ta{};
+    ta.dirs = p->d_dirs.as<uint8_t>();
+    ta.dirs_stride = p->n_pad / 2;
+    ta.n = (int)p->n; ta.m = (int)p->m;
+    ta.ops = p->d_ops.as<uint8_t>();
+    ta.out = ctl + 2;
+    ta.enc = p->packed ? 1 : 0;
+    ta.start_i = (int)start_i; ta.start_j = (int)p->n - 1; ta.start_forced = start_forced;
+    TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+    psa_trace_kernel<<<1, kTraceThreads, kTraceSmemBytes, p->stream>>>(ta);
+    TSTA_CUDA_TRY(cudaGetLastError());
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small, ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    *nops = p->h_small[2];
+    *end_i = p->h_small[3];
+    *end_forced = p->h_small[5];
+    if (ms) TSTA_CUDA_TRY(cudaEventElapsedTime(ms, p->ev[1], p->ev[2]));
+    return TSTA_OK;
+}
+
+int tsta_psa_plan_ops(tsta_psa_plan* p, uint8_t* out, int64_t nops)
+{
+    if (!p || !out || !p->want_trace || nops < 0 || nops > p->n + p->m) return set_error(TSTA_EINVAL, "bad arguments");
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    if (nops > 0) TSTA_CUDA_TRY(cudaMemcpy(out, p->d_ops.p, (size_t)nops, cudaMemcpyDeviceToHost));
+    return TSTA_OK;
+}
 
 void tsta_psa_result_free(tsta_psa_result* r)
 {
