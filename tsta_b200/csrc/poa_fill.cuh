@@ -18,12 +18,22 @@
 // Recurrences, tie-breaks and the two quirks (late heads Q1, 'N' columns) are the ones
 // restated in oracle/poa_oracle.c; predecessor order decides ties (lowest index wins).
 //
+// Keys.  Every score the kernel carries is  score*256 + low byte, and the low byte is
+//   [type:2][63 - predecessor index:6]   type 3 = diagonal, 2 = vertical (Eout), 1 = horizontal (Fg)
+// so ONE 3-way maximum picks the cell's H, the move that produced it with the tie-break priority of
+// c-t-simd.c:484-506 (diagonal > vertical > horizontal) and, inside a type, the LOWEST predecessor
+// index that attains the maximum (the reference's tie-break).  The history holds H*256 and
+// Eout*256 + 64; a successor adds 192 + (63-j) resp. 64 + (63-j) for its predecessor j.
+//
 // Trace: 2 bytes per cell, row-major, written with 128-bit stores from a shared ring:
-//   byte 0  bits 0-6 `source` (42*type + predecessor index; 126 = horizontal), bit 7 = cH:
-//           "a horizontal move from this cell forces the next cell horizontal"  (767-769)
-//   byte 1  bits 0-5 j* (index of the predecessor whose Eout is largest), bit 6 = that Eout
-//           was opened at the predecessor, bit 7 = its extension ties with opening here
-//           (the sign of the reference's esource, 509-538)
+//   byte 0  low byte of the winning key: type and 63 - j of the move (match / mismatch of a
+//           diagonal is re-derived by the walker from the read and the node's base)
+//   byte 1  bits 0-5: 63 - j*, j* = predecessor whose Eout is largest (the reference's esource index)
+//           bit 6 = 0 iff  be + E >= H + O + E  at THIS cell: a vertical move arriving here keeps going
+//                   up (the reference's rule 776-782 reads "not opened there, or opened and tied":
+//                   both are this one comparison at the cell being entered)
+//           bit 7 = 1 iff  Fg + E >= H + O + E  at THIS cell: a horizontal move arriving here from the
+//                   right keeps going left (767-769, same argument)
 #pragma once
 #include "common.cuh"
 #include "psa_fill.cuh"   // ld_relaxed_u64 / st_relaxed_u64_if, lds/sts helpers
@@ -66,7 +76,7 @@ struct PoaFillArgs {
     const uint8_t* read;      // [len]
     int len, nrows, nbands, L;
     int M, X, E, O;
-    int2* HE;                 // [nkeep][stride] keys (H*64, Eout*256 + flag) of the rows with far successors (desc.w = their slot)
+    int2* HE;                 // [nkeep][stride] keys (H*256, Eout*256 + 64) of the rows with far successors (desc.w = their slot)
     long long stride;         // padded read length (multiple of 32*C)
     uint16_t* trace;          // [nrows][stride]
     unsigned long long* bnd;  // [nbands][nrows] tagged right-boundary elements
@@ -77,21 +87,20 @@ struct PoaFillArgs {
 
 struct PoaSmem {
     // keys of the last kPoaHist rows (+ the three constant slots): entry [slot][lane + 1] holds the
-    // lane's C columns as (H*64, Eout*256 + flag); entry [slot][0] is the band's left edge, so that
+    // lane's C columns as (H*256, Eout*256 + 64); entry [slot][0] is the band's left edge, so that
     // "the previous lane's last column" is one uniform load for every lane
     // (slot stride 1072 B = 67 x 16: lanes sit one row apart, i.e. lane k reads slot t-k, and an odd
     // multiple of 16 bytes spreads the eight 16-byte loads of a quarter warp over all banks)
     unsigned char hist[kPoaSlots * kPoaSlotBytes];
     uint16_t tr[kPoaTrRing][32 * kPoaC];     // trace ring
-    int2 bring[kPoaBndRing];                 // left boundary (H(r, j0-1), Fg(r, j0)) by row
+    int2 bring[kPoaBndRing];                 // left boundary keys (H(r, j0-1)*256, Fg(r, j0)*256 + 64) by row
     uint4 desc[kPoaDescRing];                // row descriptors
-    uint8_t bneg[kPoaBndRing];               // fsource(r, j0-1) < 0
 };
 
-// boundary element: low word H; high word: bits 0-15 Fg-H, bit 16 fsource sign, bits 17-31 epoch
-__device__ __forceinline__ unsigned long long poa_bnd_pack(int H, int F, int fneg, unsigned epoch)
+// boundary element: low word H; high word: bits 0-15 Fg-H, bits 17-31 epoch
+__device__ __forceinline__ unsigned long long poa_bnd_pack(int H, int F, unsigned epoch)
 {
-    const unsigned hi = ((unsigned)(F - H) & 0xffffu) | ((unsigned)fneg << 16) | (epoch << 17);
+    const unsigned hi = ((unsigned)(F - H) & 0xffffu) | (epoch << 17);
     return ((unsigned long long)hi << 32) | (unsigned)H;
 }
 __device__ __forceinline__ int4 lds_s4(uint32_t addr)
@@ -111,62 +120,50 @@ __device__ __forceinline__ void sts_s4(uint32_t addr, int x, int y, int z, int w
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w));
 }
 
-// One row of one lane's strip (C columns, serial in F).  In: the predecessor keys kd/ke, F4 = 4*Fg+1 and
-// H of the left neighbour; out: the strip's keys (ko), trace words (tw), the right edge (F4, Hleft, fneg_left).
-// Candidates of H are tagged with the tie-break priority of c-t-simd.c:484-506: diagonal (3) beats
-// vertical E (2) beats horizontal F (1).
+// One row of one lane's strip (C columns, serial in F).  In: the reduced predecessor keys kd/ke, the
+// Fg key of the strip's first column and (quirks only) the H key of the left neighbour; out: the
+// strip's history keys (ko), trace words (tw) and the right edge (Fk, Hleft).
 template <int C, bool QUIRKS>
 __device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], const uint8_t (&rc)[C], const bool (&isL)[C],
-                                        const int b, const int M, const int X, const int E4, const int OE4p1, const int Fadj,
-                                        int& F4, int& Hleft, int& fneg_left, int (&ko)[2 * C], uint16_t (&tw)[C])
+                                        const bool (&isLm1)[C], const int b, const int MS, const int XS, const int ES,
+                                        const int OES, const int Fadj, int& Fk, int& Hleft, int (&ko)[2 * C], uint32_t (&tw)[C / 2])
 {
-    int t4prev = 4 * Hleft + OE4p1;                                   // "opened from the left neighbour"
+    uint32_t lo8[C], hi8[C];
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        if (QUIRKS && isL[c]) F4 += Fadj;                             // quirk Q1: carried F re-based at column L
-        const bool match = (int)rc[c] == b;
-        const int h4 = (kd[c] >> 6) * 4 + (match ? 4 * M + 3 : 4 * X + 3);
-        const int be4 = ((ke[c] >> 6) & ~3) | 2;                      // 4*be + 2
-        const int bdj = 63 - (kd[c] & 63), bej = 63 - ((ke[c] >> 2) & 63);
-        const int eopen = (ke[c] >> 1) & 1;
-        const int s3 = (match ? 42 : 84) + bdj;
-        int Hk = __vimax3_s32(h4, be4, F4);
-        int src;
+        if (QUIRKS && isL[c]) Fk += Fadj;                             // quirk Q1: carried F re-based at column L
+        const int hk = kd[c] + ((int)rc[c] == b ? MS : XS);
+        int Hk = __vimax3_s32(hk, ke[c], Fk);
         if (QUIRKS && rc[c] == 'N') {                                 // quirk Q3: 'N' columns copy H from the left
-            const int H = Hleft;
-            src = 126;
-            if ((be4 >> 2) == H) src = bej;
-            if ((h4 >> 2) == H) src = s3;
-            Hk = 4 * H;
-        } else {
-            const int tag = Hk & 3;
-            src = tag == 3 ? s3 : (tag == 2 ? bej : 126);
+            const int H = Hleft >> 8;
+            int lb = 64;
+            if ((ke[c] >> 8) == H) lb = ke[c] & 255;
+            if ((hk >> 8) == H) lb = hk & 255;
+            Hk = H * 256 + lb;
         }
-        const int H4 = Hk & ~3;
-        const int t4 = H4 + OE4p1;                                    // 4(H+O+E)+1: Fg / Eout opened from here
-        const int a4 = F4 + E4;                                       // 4(Fg+E)+1
-        const int ae4 = be4 + (E4 - 1);                               // 4(be+E)+1
-        const int eneg = (ae4 == t4);
-        const int fabs2 = (F4 == t4prev);                             // |fsource| == 2
-        const int fneg = (a4 == t4);
-        const int cH = (!fabs2) || fneg_left;                         // (767-769), column >= 2 checked by the walker
-        tw[c] = (uint16_t)(src | (cH << 7) | (bej << 8) | (eopen << 14) | (eneg << 15));
-        // Eout = max(H+O+E, be+E); ties count as opened: max(4ae+1, 4t+2)
-        const int zz = max(ae4, t4 + 1);
-        ko[2 * c] = H4 * 16;                                          // H*64
-        ko[2 * c + 1] = (zz & ~3) * 64 + (zz & 3);                    // Eout*256 + flag
-        F4 = max(a4, t4);
-        t4prev = t4;
-        Hleft = H4 >> 2;
-        fneg_left = fneg;
+        const int H256 = Hk & ~255;
+        const int t = H256 + OES;                                     // (H+O+E)*256 + 64: Fg / Eout opened from here
+        const int kem = ke[c] & ~255;
+        const int WE = __viaddmax_s32(kem, ES + 128, t);              // low byte 128 iff be+E >= H+O+E, else 64
+        int WF = __viaddmax_s32(Fk, ES + 64, t);                      // low byte 128 iff Fg+E >= H+O+E, else 64
+        ko[2 * c] = H256;
+        ko[2 * c + 1] = __viaddmax_s32(kem, ES + 64, t);              // Eout*256 + 64
+        const int Fn = __viaddmax_s32(Fk, ES, t);                     // Fg(c+1)*256 + 64
+        if (QUIRKS && isLm1[c] && Fadj != 0) {
+            // the next column re-bases F: its |fsource| == 2 test sees the re-based value (c-t-simd.c:228-233)
+            const bool fabs2 = (Fn + Fadj == t), fneg = (Fk + ES == t);
+            WF = (!fabs2 || fneg) ? 128 : 64;
+        }
+        lo8[c] = (uint32_t)Hk;
+        hi8[c] = ((uint32_t)ke[c] & ~0xc0u) | ((uint32_t)WF & 0x80u) | ((uint32_t)WE & 0x40u);
+        Fk = Fn;
+        Hleft = H256;
     }
+#pragma unroll
+    for (int c = 0; c + 1 < C; c += 2)
+        tw[c / 2] = __byte_perm(__byte_perm(lo8[c], lo8[c + 1], 0x0040), __byte_perm(hi8[c], hi8[c + 1], 0x0040), 0x5140);
 }
 
-// Keys.  The predecessor reduction needs, per column, the maximum, the LOWEST predecessor index
-// that attains it (the reference's tie-break) and, for Eout, whether it was opened at that
-// predecessor.  With the history holding  H*64  and  Eout*256 + flag  (flag 2 = opened, 1 = extended),
-//      max_j (H_j*64 + (63-j))        and        max_j (Eout_j*256 + 4*(63-j) + flag_j)
-// deliver all of it in ONE VIADDMNMX per predecessor and column.
 __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ PoaFillArgs a)
 {
     constexpr int C = kPoaC;
@@ -180,22 +177,23 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 
     const int E = a.E, O = a.O, OE = a.O + a.E, M = a.M, X = a.X;
     const int R = a.nrows, len = a.len, L = a.L;
-    const int E4 = 4 * E, OE4p1 = 4 * OE + 1;
+    const int MS = 256 * M, XS = 256 * X, ES = 256 * E, OES = 256 * OE + 64;
     const int j0 = (band * 32 + lane) * C;
     uint8_t rc[C];                       // read bytes of this lane's columns (0 = pad: matches nothing)
-    bool isL[C];                         // column == L (the late-head quirk re-bases F there)
+    bool isL[C], isLm1[C];               // column == L / L-1 (the late-head quirk re-bases F at column L)
     bool hasN = false;                   // quirk Q3 applies to this lane's strip at all?
 #pragma unroll
     for (int c = 0; c < C; c++) {
         rc[c] = (j0 + c < len) ? a.read[j0 + c] : 0;
         isL[c] = (j0 + c == L);
+        isLm1[c] = (j0 + c + 1 == L);
         hasN |= rc[c] == 'N';
     }
     const bool owns_last = (len - 1 >= j0) && (len - 1 < j0 + C);
     const int clast = owns_last ? len - 1 - j0 : 0;
     bool hasL = false;
 #pragma unroll
-    for (int c = 0; c < C; c++) hasL |= isL[c];
+    for (int c = 0; c < C; c++) hasL |= isL[c] || isLm1[c];
     const unsigned long long* bnd_in = a.bnd + (long long)(band - 1) * R;
     unsigned long long* bnd_out = a.bnd + (long long)band * R;
     const bool store_right = (band + 1 < a.nbands) && lane == 31;
@@ -222,20 +220,20 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 const int col = j0 + c;
                 const int Hd_next = (late && col + 1 <= L - 1) ? (col + 1) * E : O + (col + 1) * E;   // diagonal input of column col+1
                 const int Hp = (late && col <= L - 1) ? (col + 1) * E : O + (col + 1) * E;            // Hv(col)
-                k[2 * c] = Hd_next * 64;
-                k[2 * c + 1] = (Hp + OE) * 256 + 2;
+                k[2 * c] = Hd_next * 256;
+                k[2 * c + 1] = (Hp + OE) * 256 + 64;
             }
             const uint32_t slot = hist_addr + (kPoaSlotHead + v) * kSlotBytes;
             sts_s4(slot + (lane + 1) * 32, k[0], k[1], k[2], k[3]);
             sts_s4(slot + (lane + 1) * 32 + 16, k[4], k[5], k[6], k[7]);
             if (lane == 0) {   // left edge: diagonal input of column j0
                 const int Hd0 = (late && j0 <= L - 1) ? j0 * E : (j0 == 0 ? 0 : O + j0 * E);
-                sts_s4(slot + 16, 0, 0, Hd0 * 64, 0);
+                sts_s4(slot + 16, 0, 0, Hd0 * 256, 0);
             }
         }
     }
 
-    int Hout = 0, Fout = 0, Nout = 0;    // right edge of the previous step: H, Fg(next col), fsource<0
+    int Hout = 0, Fout = 0;              // right edge of the previous step: keys of H and of Fg(next column)
     const int nchunks = (R + 31 + kPoaChunk - 1) / kPoaChunk;
     unsigned long long pre_b = 0;
     if (band > 0 && lane < kPoaChunk && lane < R) pre_b = ld_relaxed_u64(bnd_in + lane);
@@ -263,15 +261,13 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 if (row < R) {
                     const int H = (int)(unsigned)pre_b;
                     const unsigned hi = (unsigned)(pre_b >> 32);
-                    sm.bring[row & (kPoaBndRing - 1)] = make_int2(H, H + (int)(short)(hi & 0xffffu));
-                    sm.bneg[row & (kPoaBndRing - 1)] = (uint8_t)((hi >> 16) & 1u);
+                    sm.bring[row & (kPoaBndRing - 1)] = make_int2(H * 256, (H + (int)(short)(hi & 0xffffu)) * 256 + 64);
                 }
                 const int rowp = row + kPoaChunk;
                 if (rowp < R) pre_b = ld_relaxed_u64(bnd_in + rowp);
             } else if (row < R) {
                 const int h = a.hneg1[row];
-                sm.bring[row & (kPoaBndRing - 1)] = make_int2(h, h + OE);   // Fg(r,0) = H(r,-1)+O+E
-                sm.bneg[row & (kPoaBndRing - 1)] = 0;
+                sm.bring[row & (kPoaBndRing - 1)] = make_int2(h * 256, (h + OE) * 256 + 64);   // Fg(r,0) = H(r,-1)+O+E
             }
         }
         __syncwarp();
@@ -281,14 +277,12 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
             const int r = t0 + s - lane;
             int Hleft = __shfl_up_sync(kFullMask, Hout, 1);
             int F = __shfl_up_sync(kFullMask, Fout, 1);
-            int fneg_left = __shfl_up_sync(kFullMask, Nout, 1);
             __syncwarp();   // orders last step's history stores before this step's loads
             if ((unsigned)r < (unsigned)R) {
                 if (lane == 0) {
                     const int2 v = sm.bring[r & (kPoaBndRing - 1)];
                     Hleft = v.x;
                     F = v.y;
-                    fneg_left = sm.bneg[r & (kPoaBndRing - 1)];
                 }
                 const uint4 dsc = sm.desc[r & (kPoaDescRing - 1)];
                 const int b = (int)(dsc.x & 0xffu);
@@ -304,7 +298,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                         const uint32_t A = my_hist + ((dsc.y >> (8 * j)) & 0xffu) * kSlotBytes;
                         const int Hd0 = lds_s32(A + 24);
                         const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
-                        const int wd = 63 - j, we = 4 * (63 - j);
+                        const int wd = 192 + 63 - j, we = 64 + 63 - j;
                         kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
                         kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
                         kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
@@ -333,10 +327,10 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                             v01 = __ldcg(reinterpret_cast<const int4*>(src));
                             v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
-                            else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p) * 64;
-                            else Hd0 = __ldg(a.hneg1 + p) * 64;
+                            else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p) * 256;
+                            else Hd0 = __ldg(a.hneg1 + p) * 256;
                         }
-                        const int wd = 63 - j, we = 4 * (63 - j);
+                        const int wd = 192 + 63 - j, we = 64 + 63 - j;
                         kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
                         kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
                         kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
@@ -348,39 +342,38 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     }
                 }
 
-                // ---- the row itself: serial along the strip, scores times four ----------------------
-                int F4 = 4 * F + 1;
+                // ---- the row itself: serial along the strip ---------------------------------------------
+                int Fk = F;
                 const int Hleft_in = Hleft;
                 int ko[2 * C];
-                uint16_t tw[C];
+                uint32_t tw[C / 2];
                 // the two quirks (late heads re-base F at column L, 'N' columns copy H) touch a handful of
                 // cells of a whole job: they get their own copy of the row code, the common one is free of them
                 if (hasN || (hasL && (flags & kPoaLate)))
-                    poa_row<C, true>(kd, ke, rc, isL, b, M, X, E4, OE4p1, (flags & kPoaLate) ? 4 * O : 0, F4, Hleft, fneg_left, ko, tw);
+                    poa_row<C, true>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, OES, (flags & kPoaLate) ? 256 * O : 0, Fk, Hleft, ko, tw);
                 else
-                    poa_row<C, false>(kd, ke, rc, isL, b, M, X, E4, OE4p1, 0, F4, Hleft, fneg_left, ko, tw);
-                Hout = Hleft; Fout = (F4 - 1) >> 2; Nout = fneg_left;
+                    poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, OES, 0, Fk, Hleft, ko, tw);
+                Hout = Hleft; Fout = Fk;
                 // history ring (own columns + the band's left edge), HBM spill for far successors, trace ring
                 {
                     const uint32_t own = my_hist + (r & (kPoaHist - 1)) * kSlotBytes;
                     sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
                     sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
-                    if (lane == 0) sts_u32(own + 24, (uint32_t)(Hleft_in * 64));
+                    if (lane == 0) sts_u32(own + 24, (uint32_t)Hleft_in);
                     if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
                         int2* g = a.HE + (long long)dsc.w * a.stride + j0;
                         *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
                         *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
                     }
-                    *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) =
-                        make_uint2((uint32_t)tw[0] | ((uint32_t)tw[1] << 16), (uint32_t)tw[2] | ((uint32_t)tw[3] << 16));
+                    *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) = make_uint2(tw[0], tw[1]);
                 }
                 if (owns_last) {
                     int hk = ko[0];
 #pragma unroll
                     for (int c = 1; c < C; c++) hk = clast == c ? ko[2 * c] : hk;
-                    a.lastsorce[r] = hk >> 6;
+                    a.lastsorce[r] = hk >> 8;
                 }
-                st_relaxed_u64_if(bnd_out + r, poa_bnd_pack(Hout, Fout, Nout, a.epoch), store_right);
+                st_relaxed_u64_if(bnd_out + r, poa_bnd_pack(Hout >> 8, Fout >> 8, a.epoch), store_right);
             }
         }
 
@@ -421,6 +414,8 @@ struct PoaWalkArgs {
     long long stride;
     const int* row_ptr;
     const int* pred_row;
+    const uint8_t* base;      // [nrows]  a diagonal move is a match iff read[col] == base[row]
+    const uint8_t* read;      // [len]
     int len, nrows, start_row;
     PoaStep* path;
     int* nsteps;
@@ -431,8 +426,9 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
     __shared__ __align__(16) uint16_t win[kPoaWinRows][kPoaWinCols];
     __shared__ int s_ptr[kPoaWinRows + 1];
     __shared__ int s_pred[kPoaWinEdges];
-    __shared__ int s_row, s_col, s_forced, s_n;
-    if (threadIdx.x == 0) { s_row = a.start_row; s_col = a.len - 1; s_forced = -1; s_n = 0; }
+    __shared__ uint8_t s_base[kPoaWinRows], s_read[kPoaWinCols];
+    __shared__ int s_row, s_col, s_pend, s_n;
+    if (threadIdx.x == 0) { s_row = a.start_row; s_col = a.len - 1; s_pend = 0; s_n = 0; }
     __syncthreads();
     while (true) {
         const int r0 = s_row, c0 = s_col;
@@ -450,46 +446,42 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
                     __ldcs(reinterpret_cast<const uint4*>(a.trace + (long long)row * a.stride + col));
         }
         for (int u = threadIdx.x; u <= r0 - rlo + 1; u += kPoaWalkThreads) s_ptr[u] = a.row_ptr[rlo + u];
+        for (int u = threadIdx.x; u < kPoaWinRows; u += kPoaWalkThreads) s_base[u] = r0 - u >= 0 ? a.base[r0 - u] : 0;
+        for (int u = threadIdx.x; u < kPoaWinCols; u += kPoaWalkThreads) s_read[u] = w0 + u < a.len ? a.read[w0 + u] : 0;
         __syncthreads();
         const int ebase = s_ptr[0];
         const int ecount = min(s_ptr[r0 - rlo + 1] - ebase, kPoaWinEdges);
         for (int u = threadIdx.x; u < ecount; u += kPoaWalkThreads) s_pred[u] = a.pred_row[ebase + u];
         __syncthreads();
         if (threadIdx.x == 0) {
-            int r = r0, c = c0, forced = s_forced, n = s_n;
+            // pend: how this cell was entered (1 = horizontal move, 2 = vertical move, 0 = otherwise);
+            // the cell's own bits 14 / 15 then say whether the move is forced to continue
+            int r = r0, c = c0, pend = s_pend, n = s_n;
             while (r >= rlo && r >= 0 && c >= w0) {
-                const uint16_t w = win[r0 - r][c - w0];
-                const int S = forced >= 0 ? forced : (w & 0x7f);
-                const int kind = S / 42, pj = S % 42;
+                const uint32_t w = win[r0 - r][c - w0];
+                int kind, pj = 63 - (int)(w & 63u);
+                if (pend == 1 && c > 0 && (w & 0x8000u)) { kind = 3; }
+                else if (pend == 2 && r > 0 && !(w & 0x4000u)) { kind = 0; pj = 63 - (int)((w >> 8) & 63u); }
+                else {
+                    const uint32_t type = (w >> 6) & 3u;
+                    kind = type == 3u ? (s_read[c - w0] == s_base[r0 - r] ? 1 : 2) : (type == 2u ? 0 : 3);
+                }
                 PoaStep st;
                 st.row = r; st.col = c; st.kind = (uint8_t)kind; st.pred = (uint8_t)(kind == 3 ? 0 : pj); st.pad = 0;
                 a.path[n++] = st;
                 if (kind == 3) {
-                    forced = (c - 1 > 0 && (w & 0x80)) ? 126 : -1;
+                    pend = 1;
                     c--;
                     continue;
                 }
                 const int e = s_ptr[r - rlo] - ebase + pj;
                 const int p = e < kPoaWinEdges ? s_pred[e] : a.pred_row[ebase + e];
-                if (kind == 0) {
-                    // vertical: the predecessor keeps going up when this cell's best E was an
-                    // extension there, or was opened there and ties with extending (776-782)
-                    forced = -1;
-                    if (p > 0) {
-                        const int eopen = (w >> 14) & 1;
-                        const uint16_t wp = (p >= rlo) ? win[r0 - p][c - w0]
-                                                      : a.trace[(long long)p * a.stride + c];
-                        if (!eopen || (wp >> 15)) forced = (wp >> 8) & 0x3f;
-                    }
-                    r = p;
-                } else {
-                    forced = -1;
-                    r = p;
-                    c--;
-                }
+                r = p;
+                if (kind == 0) pend = 2;
+                else { pend = 0; c--; }
                 if (r < 0) break;
             }
-            s_row = r; s_col = c; s_forced = forced; s_n = n;
+            s_row = r; s_col = c; s_pend = pend; s_n = n;
         }
         __syncthreads();
     }

@@ -5,6 +5,7 @@
 // device matrix, the tile loop (1019-1043) one kernel launch, and the trace walk of
 // node_fuse() (751-785) a second kernel that returns the compact path.
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -26,7 +27,13 @@ struct tsta_poa {
     long long stride = 0;
     bool filled = false;
     int launches = 0;
+    double t_desc = 0, t_alloc = 0, t_run = 0;   // host seconds per phase (TSTA_POA_TIMING=1 prints them)
 };
+
+static double poa_now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static void poa_free(tsta_poa* p)
 {
@@ -62,7 +69,13 @@ int tsta_poa_create(tsta_poa** out)
     return TSTA_OK;
 }
 
-void tsta_poa_destroy(tsta_poa* p) { poa_free(p); }
+void tsta_poa_destroy(tsta_poa* p)
+{
+    if (p && getenv("TSTA_POA_TIMING"))
+        fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s\n",
+                p->t_desc, p->t_alloc, p->t_run);
+    poa_free(p);
+}
 
 int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
                   const int32_t* row_ptr, const int32_t* pred_row, const uint8_t* base, const int32_t* hneg1,
@@ -84,6 +97,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
             return set_error(TSTA_EINVAL, "row %d: in-degree must be 1..41 (reference limit: predecessor index < 42)", r);
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     p->filled = false;
+    const double t0 = poa_now();
     // row descriptors (see poa_fill.cuh): base, in-degree, flags, history slots of up to three predecessors
     p->h_desc.assign((size_t)nrows, make_uint4(0, 0, 0, 0));
     for (int r = 0; r < nrows; r++) {
@@ -123,24 +137,34 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     p->stride = (long long)p->nbands * band_cols;
     p->nrows = nrows;
     p->len = len;
+    const double t1 = poa_now();
+    p->t_desc += t1 - t0;
 
-    if (int rc = p->d_desc.reserve((size_t)nrows * sizeof(uint4))) return rc;
-    if (int rc = p->d_rowptr.reserve((size_t)(nrows + 1) * 4)) return rc;
-    if (int rc = p->d_pred.reserve((size_t)nedges * 4)) return rc;
-    if (int rc = p->d_base.reserve((size_t)nrows)) return rc;
-    if (int rc = p->d_hneg1.reserve((size_t)nrows * 4)) return rc;
-    if (int rc = p->d_read.reserve((size_t)len)) return rc;
-    if (int rc = p->d_last.reserve((size_t)nrows * 4)) return rc;
+    // The graph gains rows every round and a cudaFree + cudaMalloc pair costs milliseconds whatever
+    // the size (tools/malloc_time.py), so every buffer grows with 60 % headroom: a 16-read job
+    // reallocates once or twice instead of on every call.
+    auto grow = [](DevBuf& b, size_t bytes) {
+        if (bytes <= b.cap) return (int)TSTA_OK;
+        if (b.reserve(bytes + bytes * 3 / 5 + 4096) == TSTA_OK) return (int)TSTA_OK;
+        return b.reserve(bytes);                                    // no room for headroom: exact size
+    };
+    if (int rc = grow(p->d_desc, (size_t)nrows * sizeof(uint4))) return rc;
+    if (int rc = grow(p->d_rowptr, (size_t)(nrows + 1) * 4)) return rc;
+    if (int rc = grow(p->d_pred, (size_t)nedges * 4)) return rc;
+    if (int rc = grow(p->d_base, (size_t)nrows)) return rc;
+    if (int rc = grow(p->d_hneg1, (size_t)nrows * 4)) return rc;
+    if (int rc = grow(p->d_read, (size_t)len)) return rc;
+    if (int rc = grow(p->d_last, (size_t)nrows * 4)) return rc;
     if (int rc = p->d_ctl.reserve(64)) return rc;
-    if (int rc = p->d_path.reserve((size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
+    if (int rc = grow(p->d_path, (size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
     {   // grow generously: the graph gains rows every round
         const size_t cells = (size_t)nrows * (size_t)p->stride;
         const size_t spill = std::max<size_t>(nkeep, 1) * (size_t)(((len + 32 * kPoaC - 1) / (32 * kPoaC)) * 32 * kPoaC) * sizeof(int2);
-        if (spill > p->d_HE.cap) if (int rc = p->d_HE.reserve(spill * 5 / 4)) return rc;
-        if (cells * 2 > p->d_trace.cap) if (int rc = p->d_trace.reserve(cells * 2 * 5 / 4)) return rc;
+        if (int rc = grow(p->d_HE, spill)) return rc;
+        if (int rc = grow(p->d_trace, cells * 2)) return rc;
         const size_t need = (size_t)p->nbands * (size_t)nrows * 8;
         if (need > p->d_bnd.cap) {
-            if (int rc = p->d_bnd.reserve(need * 5 / 4)) return rc;
+            if (int rc = grow(p->d_bnd, need)) return rc;
             TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
             p->epoch = 0;
         }
@@ -149,6 +173,8 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
         p->epoch = 1;
     }
+    const double t2 = poa_now();
+    p->t_alloc += t2 - t1;
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_desc.p, p->h_desc.data(), (size_t)nrows * sizeof(uint4), cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_rowptr.p, row_ptr, (size_t)(nrows + 1) * 4, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_pred.p, pred_row, (size_t)nedges * 4, cudaMemcpyHostToDevice, p->stream));
@@ -177,6 +203,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     if (kernel_ms) TSTA_CUDA_TRY(cudaEventElapsedTime(kernel_ms, p->ev[0], p->ev[1]));
     p->filled = true;
     p->launches = 1;
+    p->t_run += poa_now() - t2;
     return TSTA_OK;
 }
 
@@ -190,6 +217,7 @@ int tsta_poa_walk(tsta_poa* p, int start_row, tsta_poa_step* path, int* nsteps, 
     PoaWalkArgs w{};
     w.trace = p->d_trace.as<uint16_t>(); w.stride = p->stride;
     w.row_ptr = p->d_rowptr.as<int>(); w.pred_row = p->d_pred.as<int>();
+    w.base = p->d_base.as<uint8_t>(); w.read = p->d_read.as<uint8_t>();
     w.len = p->len; w.nrows = p->nrows; w.start_row = start_row;
     w.path = p->d_path.as<PoaStep>();
     w.nsteps = p->d_ctl.as<int>() + 4;
