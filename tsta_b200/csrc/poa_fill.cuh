@@ -47,7 +47,7 @@ constexpr int kPoaSlotNone = 32;    // extra history slots: "no predecessor" (ke
 constexpr int kPoaSlotHead = 33;    // the virtual row above a head node,
 constexpr int kPoaSlotLate = 34;    // and its late-head variant (quirk Q1)
 constexpr int kPoaSlots = 35;
-constexpr int kPoaFast = 3;         // predecessors the unrolled fast path handles
+constexpr int kPoaFast = 4;         // predecessors the unrolled fast path handles
 constexpr int kPoaChunk = 16;       // rows per staging chunk
 constexpr int kPoaBndRing = 64;     // boundary ring (rows)
 constexpr int kPoaTrRing = 64;      // trace ring (rows)
@@ -58,13 +58,13 @@ constexpr int kPoaSlotBytes = 33 * kPoaC * 8 + 16;   // 1072
 // Row descriptor, built on the host from the CSR graph and staged through shared memory a chunk
 // ahead of the wavefront, so that the inner loop never waits for a dependent global load:
 //   x: base | in-degree << 8 | flags << 16
-//   y: history slot of predecessor 0, 1, 2 (one byte each; kPoaSlotNone when absent, the
+//   y: history slot of predecessor 0..3 (one byte each; kPoaSlotNone when absent, the
 //      virtual-row slots for heads) -- the fast path needs nothing else
 //   z: first CSR edge of the row (slow path)
 //   w: for rows flagged kPoaKeep: their row in the HBM spill
 constexpr unsigned kPoaHead = 1u;        // in == 0
 constexpr unsigned kPoaKeep = 2u;        // some successor is further away than the history ring: also store the keys in HBM
-constexpr unsigned kPoaSlow = 4u;        // more than three predecessors, or one further back than the ring: generic loop
+constexpr unsigned kPoaSlow = 4u;        // more than four predecessors, or one further back than the ring: generic loop
 constexpr unsigned kPoaLate = 8u;        // head with row index >= L (quirk Q1)
 
 struct PoaFillArgs {
@@ -97,11 +97,18 @@ struct PoaSmem {
     uint4 desc[kPoaDescRing];                // row descriptors
 };
 
-// boundary element: low word H; high word: bits 0-15 Fg-H, bits 17-31 epoch
-__device__ __forceinline__ unsigned long long poa_bnd_pack(int H, int F, unsigned epoch)
+// boundary element: low word = key of H (H*256); high word: bits 0-15 Fg-H, bits 17-31 epoch.
+// Fk - Hk = (Fg-H)*256 + 64, so its bytes 1-2 are the 16-bit difference; ep16 = epoch << 1.
+__device__ __forceinline__ unsigned long long poa_bnd_pack(int Hk, int Fk, unsigned ep16)
 {
-    const unsigned hi = ((unsigned)(F - H) & 0xffffu) | (epoch << 17);
-    return ((unsigned long long)hi << 32) | (unsigned)H;
+    const unsigned hi = __byte_perm((unsigned)(Fk - Hk), ep16, 0x5421);
+    return ((unsigned long long)hi << 32) | (unsigned)Hk;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ int4 lds_s4(uint32_t addr)
 {
@@ -234,6 +241,12 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
     }
 
     int Hout = 0, Fout = 0;              // right edge of the previous step: keys of H and of Fg(next column)
+    // explicit shared addresses: the compiler otherwise re-derives the shared window inside the step loop
+    const uint32_t desc_addr = (uint32_t)__cvta_generic_to_shared(&sm.desc[0]);
+    const uint32_t bring_addr = (uint32_t)__cvta_generic_to_shared(&sm.bring[0]);
+    const uint32_t tr_addr = (uint32_t)__cvta_generic_to_shared(&sm.tr[0][0]) + lane * (C * 2);
+    const unsigned ep16 = a.epoch << 1;
+    const bool last_band = band + 1 == a.nbands;
     const int nchunks = (R + 31 + kPoaChunk - 1) / kPoaChunk;
     unsigned long long pre_b = 0;
     if (band > 0 && lane < kPoaChunk && lane < R) pre_b = ld_relaxed_u64(bnd_in + lane);
@@ -259,9 +272,9 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     if (row < R && (unsigned)(pre_b >> 49) != a.epoch) pre_b = ld_relaxed_u64(bnd_in + row);
                 }
                 if (row < R) {
-                    const int H = (int)(unsigned)pre_b;
+                    const int Hk = (int)(unsigned)pre_b;
                     const unsigned hi = (unsigned)(pre_b >> 32);
-                    sm.bring[row & (kPoaBndRing - 1)] = make_int2(H * 256, (H + (int)(short)(hi & 0xffffu)) * 256 + 64);
+                    sm.bring[row & (kPoaBndRing - 1)] = make_int2(Hk, Hk + (int)(short)(hi & 0xffffu) * 256 + 64);
                 }
                 const int rowp = row + kPoaChunk;
                 if (rowp < R) pre_b = ld_relaxed_u64(bnd_in + rowp);
@@ -272,29 +285,95 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
         }
         __syncwarp();
 
+        unsigned long long* bout = bnd_out + (t0 - lane);          // boundary element of this lane's row at s = 0
+        // the descriptor of a lane's row is fetched one step ahead, off the step's dependency chain
+        uint4 dsc_next = lds_u4(desc_addr + ((uint32_t)(t0 - lane) & 63u) * 16);
 #pragma unroll 1
-        for (int s = 0; s < kPoaChunk; s++) {
+        for (int s = 0; s < kPoaChunk; s++, bout++) {
             const int r = t0 + s - lane;
             int Hleft = __shfl_up_sync(kFullMask, Hout, 1);
             int F = __shfl_up_sync(kFullMask, Fout, 1);
             __syncwarp();   // orders last step's history stores before this step's loads
-            if ((unsigned)r < (unsigned)R) {
-                if (lane == 0) {
-                    const int2 v = sm.bring[r & (kPoaBndRing - 1)];
-                    Hleft = v.x;
-                    F = v.y;
+            const bool active = (unsigned)r < (unsigned)R;
+            const uint32_t rm = (uint32_t)r & 63u;
+            const uint4 dsc = dsc_next;
+            dsc_next = lds_u4(desc_addr + ((rm + 1u) & 63u) * 16);
+            // how many predecessors does any lane of the warp have this step?  (78 % of the rows of an
+            // MSA graph have one, 19 % two, 3 % three: the fourth round of the reduction is skipped
+            // warp-wide whenever no lane needs it)
+            const int npre_l = active ? (int)((dsc.x >> 8) & 0xffu) : 0;
+            const bool any3 = __any_sync(kFullMask, npre_l >= 3), any4 = __any_sync(kFullMask, npre_l >= 4);
+            // PLAIN step: every lane active, at most four near predecessors, no spill, no quirk -- the
+            // whole step is one straight-line block (selects and predicated stores instead of branches)
+            const bool plain = active && !((dsc.x >> 16) & (kPoaSlow | kPoaKeep)) && !hasN && !(hasL && ((dsc.x >> 16) & kPoaLate));
+            if (__all_sync(kFullMask, plain)) {
+                const uint2 bv = lds_u2(bring_addr + rm * 8);
+                const int Hleft_in = lane == 0 ? (int)bv.x : Hleft;
+                int Fk = lane == 0 ? (int)bv.y : F;
+                const int b = (int)(dsc.x & 0xffu);
+                int kd[C], ke[C];
+                {
+                    const uint32_t A = my_hist + (dsc.y & 0xffu) * kSlotBytes;
+                    const int Hd0 = lds_s32(A + 24);
+                    const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
+                    kd[0] = Hd0 + 255; kd[1] = v01.x + 255; kd[2] = v01.z + 255; kd[3] = v23.x + 255;
+                    ke[0] = v01.y + 127; ke[1] = v01.w + 127; ke[2] = v23.y + 127; ke[3] = v23.w + 127;
                 }
-                const uint4 dsc = sm.desc[r & (kPoaDescRing - 1)];
+#pragma unroll
+                for (int j = 1; j < kPoaFast; j++) {
+                    if (j == 3 && !any4) continue;
+                    const uint32_t A = my_hist + ((dsc.y >> (8 * j)) & 0xffu) * kSlotBytes;
+                    const int Hd0 = lds_s32(A + 24);
+                    const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
+                    const int wd = 192 + 63 - j, we = 64 + 63 - j;
+                    kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
+                    kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
+                    kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
+                    kd[3] = __viaddmax_s32(v23.x, wd, kd[3]);
+                    ke[0] = __viaddmax_s32(v01.y, we, ke[0]);
+                    ke[1] = __viaddmax_s32(v01.w, we, ke[1]);
+                    ke[2] = __viaddmax_s32(v23.y, we, ke[2]);
+                    ke[3] = __viaddmax_s32(v23.w, we, ke[3]);
+                }
+                int ko[2 * C];
+                uint32_t tw[C / 2];
+                int Hl = Hleft_in;
+                poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, OES, 0, Fk, Hl, ko, tw);
+                Hout = Hl; Fout = Fk;
+                const uint32_t own = my_hist + ((uint32_t)r & (kPoaHist - 1)) * kSlotBytes;
+                sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
+                sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
+                if (lane == 0) sts_u32(own + 24, (uint32_t)Hleft_in);
+                sts_u2(tr_addr + rm * (32 * C * 2), tw[0], tw[1]);
+                if (owns_last) {
+                    int hk = ko[0];
+#pragma unroll
+                    for (int c = 1; c < C; c++) hk = clast == c ? ko[2 * c] : hk;
+                    a.lastsorce[r] = hk >> 8;
+                }
+                st_relaxed_u64_if(bout, poa_bnd_pack(Hout, Fout, ep16), store_right);
+            } else if (active) {
+                if (lane == 0) {
+                    const uint2 v = lds_u2(bring_addr + rm * 8);
+                    Hleft = (int)v.x;
+                    F = (int)v.y;
+                }
                 const int b = (int)(dsc.x & 0xffu);
                 const unsigned flags = dsc.x >> 16;
 
                 int kd[C], ke[C];
-#pragma unroll
-                for (int c = 0; c < C; c++) { kd[c] = kPoaKeyMin; ke[c] = kPoaKeyMin; }
                 if (!(flags & kPoaSlow)) {
-                    // ---- fast path: up to three predecessors, all inside the history ring ----------
+                    // ---- fast path: up to four predecessors, all inside the history ring -----------
+                    {   // predecessor 0: every row has one (heads: the virtual row's slot)
+                        const uint32_t A = my_hist + (dsc.y & 0xffu) * kSlotBytes;
+                        const int Hd0 = lds_s32(A + 24);
+                        const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
+                        kd[0] = Hd0 + 255; kd[1] = v01.x + 255; kd[2] = v01.z + 255; kd[3] = v23.x + 255;
+                        ke[0] = v01.y + 127; ke[1] = v01.w + 127; ke[2] = v23.y + 127; ke[3] = v23.w + 127;
+                    }
 #pragma unroll
-                    for (int j = 0; j < kPoaFast; j++) {
+                    for (int j = 1; j < kPoaFast; j++) {
+                        if ((j == 2 && !any3) || (j == 3 && !any4)) continue;
                         const uint32_t A = my_hist + ((dsc.y >> (8 * j)) & 0xffu) * kSlotBytes;
                         const int Hd0 = lds_s32(A + 24);
                         const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
@@ -310,6 +389,8 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     }
                 } else {
                     // ---- slow path: any in-degree, predecessors further back than the ring ----------
+#pragma unroll
+                    for (int c = 0; c < C; c++) { kd[c] = kPoaKeyMin; ke[c] = kPoaKeyMin; }
                     const int npre = (int)((dsc.x >> 8) & 0xffu);
                     const int e0 = (int)dsc.z;
                     for (int j = 0; j < npre; j++) {
@@ -327,7 +408,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                             v01 = __ldcg(reinterpret_cast<const int4*>(src));
                             v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
-                            else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p) * 256;
+                            else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p);
                             else Hd0 = __ldg(a.hneg1 + p) * 256;
                         }
                         const int wd = 192 + 63 - j, we = 64 + 63 - j;
@@ -356,7 +437,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 Hout = Hleft; Fout = Fk;
                 // history ring (own columns + the band's left edge), HBM spill for far successors, trace ring
                 {
-                    const uint32_t own = my_hist + (r & (kPoaHist - 1)) * kSlotBytes;
+                    const uint32_t own = my_hist + ((uint32_t)r & (kPoaHist - 1)) * kSlotBytes;
                     sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
                     sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
                     if (lane == 0) sts_u32(own + 24, (uint32_t)Hleft_in);
@@ -365,15 +446,17 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                         *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
                         *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
                     }
-                    *reinterpret_cast<uint2*>(&sm.tr[r & (kPoaTrRing - 1)][lane * C]) = make_uint2(tw[0], tw[1]);
+                    sts_u2(tr_addr + rm * (32 * C * 2), tw[0], tw[1]);
                 }
-                if (owns_last) {
-                    int hk = ko[0];
+                if (last_band) {
+                    if (owns_last) {
+                        int hk = ko[0];
 #pragma unroll
-                    for (int c = 1; c < C; c++) hk = clast == c ? ko[2 * c] : hk;
-                    a.lastsorce[r] = hk >> 8;
+                        for (int c = 1; c < C; c++) hk = clast == c ? ko[2 * c] : hk;
+                        a.lastsorce[r] = hk >> 8;
+                    }
                 }
-                st_relaxed_u64_if(bnd_out + r, poa_bnd_pack(Hout >> 8, Fout >> 8, a.epoch), store_right);
+                st_relaxed_u64_if(bout, poa_bnd_pack(Hout, Fout, ep16), store_right);
             }
         }
 
@@ -455,31 +538,27 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
         __syncthreads();
         if (threadIdx.x == 0) {
             // pend: how this cell was entered (1 = horizontal move, 2 = vertical move, 0 = otherwise);
-            // the cell's own bits 14 / 15 then say whether the move is forced to continue
+            // the cell's own bits 14 / 15 then say whether the move is forced to continue.
+            // Written with selects only: one iteration is a chain of two shared-memory loads.
             int r = r0, c = c0, pend = s_pend, n = s_n;
-            while (r >= rlo && r >= 0 && c >= w0) {
+            while (r >= rlo && c >= w0) {
                 const uint32_t w = win[r0 - r][c - w0];
-                int kind, pj = 63 - (int)(w & 63u);
-                if (pend == 1 && c > 0 && (w & 0x8000u)) { kind = 3; }
-                else if (pend == 2 && r > 0 && !(w & 0x4000u)) { kind = 0; pj = 63 - (int)((w >> 8) & 63u); }
-                else {
-                    const uint32_t type = (w >> 6) & 3u;
-                    kind = type == 3u ? (s_read[c - w0] == s_base[r0 - r] ? 1 : 2) : (type == 2u ? 0 : 3);
-                }
+                const int e0 = s_ptr[r - rlo] - ebase;
+                const bool match = s_read[c - w0] == s_base[r0 - r];
+                const bool fF = pend == 1 && c > 0 && (w & 0x8000u);
+                const bool fE = pend == 2 && r > 0 && !(w & 0x4000u);
+                const uint32_t type = fF ? 1u : (fE ? 2u : ((w >> 6) & 3u));        // 3 diagonal, 2 vertical, 1 horizontal
+                const int pj = 63 - (int)((fE ? (w >> 8) : w) & 63u);
+                const int kind = type == 3u ? (match ? 1 : 2) : (type == 2u ? 0 : 3);
                 PoaStep st;
-                st.row = r; st.col = c; st.kind = (uint8_t)kind; st.pred = (uint8_t)(kind == 3 ? 0 : pj); st.pad = 0;
+                st.row = r; st.col = c; st.kind = (uint8_t)kind; st.pred = (uint8_t)(type == 1u ? 0 : pj); st.pad = 0;
                 a.path[n++] = st;
-                if (kind == 3) {
-                    pend = 1;
-                    c--;
-                    continue;
-                }
-                const int e = s_ptr[r - rlo] - ebase + pj;
-                const int p = e < kPoaWinEdges ? s_pred[e] : a.pred_row[ebase + e];
-                r = p;
-                if (kind == 0) pend = 2;
-                else { pend = 0; c--; }
-                if (r < 0) break;
+                const int e = e0 + pj;
+                int p = s_pred[min(e, kPoaWinEdges - 1)];
+                if (type != 1u && e >= kPoaWinEdges) p = a.pred_row[ebase + e];   // (a window with > 2048 edges: never seen)
+                r = type == 1u ? r : p;
+                c = type == 2u ? c : c - 1;
+                pend = type == 1u ? 1 : (type == 2u ? 2 : 0);
             }
             s_row = r; s_col = c; s_pend = pend; s_n = n;
         }

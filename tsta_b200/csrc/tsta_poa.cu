@@ -28,6 +28,7 @@ struct tsta_poa {
     bool filled = false;
     int launches = 0;
     double t_desc = 0, t_alloc = 0, t_run = 0;   // host seconds per phase (TSTA_POA_TIMING=1 prints them)
+    long long n_rows = 0, n_wide = 0, n_far = 0, n_keep = 0, n_deg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static double poa_now()
@@ -74,6 +75,9 @@ void tsta_poa_destroy(tsta_poa* p)
     if (p && getenv("TSTA_POA_TIMING"))
         fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s\n",
                 p->t_desc, p->t_alloc, p->t_run);
+    if (p && getenv("TSTA_POA_TIMING"))
+        fprintf(stderr, "tsta_poa rows %lld: in-degree>3 %lld, with a far predecessor %lld, spilled %lld; in-degree histogram 1:%lld 2:%lld 3:%lld 4:%lld 5:%lld 6:%lld 7+:%lld\n",
+                p->n_rows, p->n_wide, p->n_far, p->n_keep, p->n_deg[1], p->n_deg[2], p->n_deg[3], p->n_deg[4], p->n_deg[5], p->n_deg[6], p->n_deg[7]);
     poa_free(p);
 }
 
@@ -102,14 +106,16 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     p->h_desc.assign((size_t)nrows, make_uint4(0, 0, 0, 0));
     for (int r = 0; r < nrows; r++) {
         const int e0 = row_ptr[r], np = row_ptr[r + 1] - e0;
-        unsigned flags = 0, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone};
+        unsigned flags = 0, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone};
+        static_assert(kPoaFast == 4, "descriptor word y holds four slot bytes");
         if (pred_row[e0] < 0) {
             flags |= kPoaHead;
             if (L > 0 && r >= L) flags |= kPoaLate;                 // quirk Q1
             slot[0] = (flags & kPoaLate) ? kPoaSlotLate : kPoaSlotHead;
             if (np != 1) return set_error(TSTA_EINVAL, "row %d: a head must have the single entry -1", r);
         } else {
-            if (np > kPoaFast) flags |= kPoaSlow;
+            if (np > kPoaFast) { flags |= kPoaSlow; p->n_wide++; }
+            bool far = false;
             for (int j = 0; j < np; j++) {
                 const int pr = pred_row[e0 + j];
                 if (pr < 0 || pr >= r) return set_error(TSTA_EINVAL, "row %d: predecessor %d is not an earlier row", r, pr);
@@ -117,13 +123,17 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
                 if (dist > kPoaNear) {
                     p->h_desc[(size_t)pr].x |= kPoaKeep << 16;      // it must also spill its keys to HBM
                     flags |= kPoaSlow;
+                    far = true;
                 }
                 if (j < kPoaFast) slot[j] = (unsigned)(pr & (kPoaHist - 1));
             }
+            if (far) p->n_far++;
         }
+        p->n_deg[np < 7 ? np : 7]++;
+        p->n_rows++;
         uint4& q = p->h_desc[(size_t)r];
         q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16);
-        q.y = slot[0] | (slot[1] << 8) | (slot[2] << 16);
+        q.y = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
         q.z = (unsigned)e0;
     }
     // rows with a successor further away than the history ring get a row of the HBM spill
@@ -132,6 +142,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         uint4& q = p->h_desc[(size_t)r];
         q.w = ((q.x >> 16) & kPoaKeep) ? (unsigned)nkeep++ : 0u;
     }
+    p->n_keep += (long long)nkeep;
     const int band_cols = 32 * kPoaC;
     p->nbands = (len + band_cols - 1) / band_cols;
     p->stride = (long long)p->nbands * band_cols;
