@@ -246,10 +246,15 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
     const uint32_t bring_addr = (uint32_t)__cvta_generic_to_shared(&sm.bring[0]);
     const uint32_t tr_addr = (uint32_t)__cvta_generic_to_shared(&sm.tr[0][0]) + lane * (C * 2);
     const unsigned ep16 = a.epoch << 1;
+    // flags (descriptor bits 16..) that take a lane out of the PLAIN step: slow / spilled rows always,
+    // late heads only in the lanes that own column L-1 or L; every row when the strip has an 'N'
+    const unsigned unplain = hasN ? 0xffffffffu : (((kPoaSlow | kPoaKeep) | (hasL ? kPoaLate : 0u)) << 16);
     const bool last_band = band + 1 == a.nbands;
     const int nchunks = (R + 31 + kPoaChunk - 1) / kPoaChunk;
     unsigned long long pre_b = 0;
     if (band > 0 && lane < kPoaChunk && lane < R) pre_b = ld_relaxed_u64(bnd_in + lane);
+    int pre_h = 0;                       // band 0: H(r,-1) of the next chunk's rows, fetched a chunk ahead
+    if (band == 0 && lane < kPoaChunk && lane < R) pre_h = __ldg(a.hneg1 + lane);
     // descriptors: lanes 16..31 stage rows [t0+16, t0+32) at the top of chunk t0 (one chunk ahead)
     if (lane < kPoaChunk && lane < R) sm.desc[lane] = __ldg(a.desc + lane);
     uint4 pre_d = make_uint4(0, 0, 0, 0);
@@ -278,9 +283,10 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 }
                 const int rowp = row + kPoaChunk;
                 if (rowp < R) pre_b = ld_relaxed_u64(bnd_in + rowp);
-            } else if (row < R) {
-                const int h = a.hneg1[row];
-                sm.bring[row & (kPoaBndRing - 1)] = make_int2(h * 256, (h + OE) * 256 + 64);   // Fg(r,0) = H(r,-1)+O+E
+            } else {
+                if (row < R) sm.bring[row & (kPoaBndRing - 1)] = make_int2(pre_h * 256, (pre_h + OE) * 256 + 64);   // Fg(r,0) = H(r,-1)+O+E
+                const int rowp = row + kPoaChunk;
+                if (rowp < R) pre_h = __ldg(a.hneg1 + rowp);
             }
         }
         __syncwarp();
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
             const bool any3 = __any_sync(kFullMask, npre_l >= 3), any4 = __any_sync(kFullMask, npre_l >= 4);
             // PLAIN step: every lane active, at most four near predecessors, no spill, no quirk -- the
             // whole step is one straight-line block (selects and predicated stores instead of branches)
-            const bool plain = active && !((dsc.x >> 16) & (kPoaSlow | kPoaKeep)) && !hasN && !(hasL && ((dsc.x >> 16) & kPoaLate));
+            const bool plain = active && !(dsc.x & unplain) && !hasN;
             if (__all_sync(kFullMask, plain)) {
                 const uint2 bv = lds_u2(bring_addr + rm * 8);
                 const int Hleft_in = lane == 0 ? (int)bv.x : Hleft;
@@ -467,6 +473,18 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
             const int lo = min(R, max(0, t0 - 31));
             constexpr int kUnits = 32 * C * 2 / 16;    // 16 units per row
             const int units = (hi - lo) * kUnits;
+            if (hi - lo == kPoaChunk) {
+                // a whole chunk: lane u handles part u%16 of rows lo + u/16 + 2k -- eight independent load/store pairs
+                const int part = lane % kUnits;
+                uint16_t* dst = a.trace + (long long)(lo + lane / kUnits) * a.stride + (long long)band * 32 * C + part * 8;
+                uint4 v[kPoaChunk / 2];
+#pragma unroll
+                for (int k = 0; k < kPoaChunk / 2; k++)
+                    v[k] = *reinterpret_cast<const uint4*>(&sm.tr[(lo + lane / kUnits + 2 * k) & (kPoaTrRing - 1)][part * 8]);
+#pragma unroll
+                for (int k = 0; k < kPoaChunk / 2; k++)
+                    __stcs(reinterpret_cast<uint4*>(dst + (long long)(2 * k) * a.stride), v[k]);
+            } else
             for (int u = lane; u < units; u += 32) {
                 const int row = lo + u / kUnits, part = u % kUnits;
                 const uint4 v = *reinterpret_cast<const uint4*>(&sm.tr[row & (kPoaTrRing - 1)][part * 8]);

@@ -23,23 +23,80 @@ static int node_new(poa_graph* g, unsigned char base)
     return g->nnode++;
 }
 
-static void push_pre(poa_node* n, int id, int weight)
+/* pool of small arrays: power-of-two size classes (in 8-byte units), bump allocation from 1 MiB
+ * blocks, per-class free lists threaded through the freed arrays themselves */
+#define POOL_BLOCK ((size_t)1 << 20)
+static int pool_class(size_t bytes)
+{
+    int k = 0;
+    while (((size_t)8 << k) < bytes) k++;
+    return k;
+}
+static void* pool_get(poa_graph* g, size_t bytes)
+{
+    const int k = pool_class(bytes);
+    const size_t sz = (size_t)8 << k;
+    if (g->pool_free[k]) {
+        void* p = g->pool_free[k];
+        g->pool_free[k] = *(void**)p;
+        return p;
+    }
+    if (sz > POOL_BLOCK / 4) {                       /* huge: its own block, kept on the block list */
+        void** b = (void**)malloc(sz + 16);
+        b[0] = g->pool_blocks; g->pool_blocks = b;
+        return (char*)b + 16;
+    }
+    if (g->pool_left < sz) {
+        void** b = (void**)malloc(POOL_BLOCK);
+        b[0] = g->pool_blocks; g->pool_blocks = b;
+        g->pool_cur = (char*)b + 16;
+        g->pool_left = POOL_BLOCK - 16;
+    }
+    void* p = g->pool_cur;
+    g->pool_cur += sz; g->pool_left -= sz;
+    return p;
+}
+static void pool_put(poa_graph* g, void* p, size_t bytes)
+{
+    if (!p) return;
+    const int k = pool_class(bytes);
+    *(void**)p = g->pool_free[k];
+    g->pool_free[k] = p;
+}
+static int* pool_grow(poa_graph* g, int* old, int used, int old_cap, int new_cap)
+{
+    int* p = (int*)pool_get(g, (size_t)new_cap * sizeof(int));
+    if (used > 0) memcpy(p, old, (size_t)used * sizeof(int));
+    pool_put(g, old, (size_t)old_cap * sizeof(int));
+    return p;
+}
+static uint8_t* passing_new(poa_graph* g)
+{
+    uint8_t* p = (uint8_t*)pool_get(g, (size_t)g->nseq);
+    memset(p, 0, (size_t)g->nseq);
+    return p;
+}
+
+static void push_pre(poa_graph* g, poa_node* n, int id, int weight)
 {
     if (n->in + 1 > n->pre_cap) {
-        n->pre_cap = n->pre_cap ? n->pre_cap * 2 : 2;
-        n->pre = (int*)realloc(n->pre, (size_t)n->pre_cap * sizeof(int));
-        n->ew = (int*)realloc(n->ew, (size_t)n->pre_cap * sizeof(int));
+        const int cap = n->pre_cap ? n->pre_cap * 2 : 2;
+        /* (a head keeps pre[0] = sentinel with in == 0: copy the whole old array) */
+        n->pre = pool_grow(g, n->pre, n->pre_cap, n->pre_cap, cap);
+        n->ew = pool_grow(g, n->ew, n->pre_cap, n->pre_cap, cap);
+        n->pre_cap = cap;
     }
     n->pre[n->in] = id;
     n->ew[n->in] = weight;
     n->in++;
 }
 
-static void push_next(poa_node* n, int id)
+static void push_next(poa_graph* g, poa_node* n, int id)
 {
     if (n->out + 1 > n->next_cap) {
-        n->next_cap = n->next_cap ? n->next_cap * 2 : 2;
-        n->next = (int*)realloc(n->next, (size_t)n->next_cap * sizeof(int));
+        const int cap = n->next_cap ? n->next_cap * 2 : 2;
+        n->next = pool_grow(g, n->next, n->out, n->next_cap, cap);
+        n->next_cap = cap;
     }
     n->next[n->out++] = id;
 }
@@ -47,9 +104,13 @@ static void push_next(poa_node* n, int id)
 static void node_kill(poa_graph* g, int id)
 {
     poa_node* n = &g->node[id];
-    free(n->pre); free(n->ew); free(n->next); free(n->passing_seq);
+    pool_put(g, n->pre, (size_t)n->pre_cap * sizeof(int));
+    pool_put(g, n->ew, (size_t)n->pre_cap * sizeof(int));
+    pool_put(g, n->next, (size_t)n->next_cap * sizeof(int));
+    pool_put(g, n->passing_seq, (size_t)g->nseq);
     n->pre = n->ew = n->next = NULL;
     n->passing_seq = NULL;
+    n->pre_cap = n->next_cap = 0;
     n->alive = 0;
 }
 
@@ -78,16 +139,16 @@ void poa_graph_init(poa_graph* g, const char* a, int nseq)
     for (int i = 0; i < len; i++) {
         const int id = node_new(g, (unsigned char)a[i]);
         poa_node* n = &g->node[id];
-        n->passing_seq = (uint8_t*)calloc((size_t)nseq, 1);
+        n->passing_seq = passing_new(g);
         n->passing_seq[0] = 1;
         if (i == 0) {
-            push_pre(n, POA_SENTINEL, 0);
+            push_pre(g, n, POA_SENTINEL, 0);
             n->in = 0;                 /* a head: pre[0] is the sentinel, weight 0 */
             n->node_base_len = 1;
         } else {
-            push_pre(n, id - 1, 1);
+            push_pre(g, n, id - 1, 1);
         }
-        if (i + 1 < len) push_next(n, id + 1);
+        if (i + 1 < len) push_next(g, n, id + 1);
         n->sub = i;
         g->unsort[i] = g->sort[i] = id;
     }
@@ -97,8 +158,7 @@ void poa_graph_init(poa_graph* g, const char* a, int nseq)
 
 void poa_graph_free(poa_graph* g)
 {
-    for (int i = 0; i < g->nnode; i++)
-        if (g->node[i].alive) node_kill(g, i);
+    for (void* b = g->pool_blocks; b;) { void* nx = *(void**)b; free(b); b = nx; }
     free(g->node); free(g->unsort); free(g->sort);
     memset(g, 0, sizeof *g);
 }
@@ -169,7 +229,7 @@ int poa_graph_pick_start(const poa_graph* g, const int32_t* lastsorce)
 static void realize(poa_graph* g, int id, int num, int* l, int set_sub)
 {
     poa_node* n = &g->node[id];
-    n->passing_seq = (uint8_t*)calloc((size_t)g->nseq, 1);
+    n->passing_seq = passing_new(g);
     n->passing_seq[num] = 1;
     n->ew[0] = 1;
     order_reserve(g, g->len + *l + 1);
@@ -187,9 +247,9 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
     for (int i = 0; i < len_b; i++) seq[i] = node_new(g, (unsigned char)b[i]);
     for (int i = 0; i < len_b; i++) {
         poa_node* n = &g->node[seq[i]];
-        if (i == 0) { push_pre(n, POA_SENTINEL, 0); n->in = 0; n->node_base_len = 1; }
-        else push_pre(n, seq[i - 1], 0);
-        if (i + 1 < len_b) push_next(n, seq[i + 1]);
+        if (i == 0) { push_pre(g, n, POA_SENTINEL, 0); n->in = 0; n->node_base_len = 1; }
+        else push_pre(g, n, seq[i - 1], 0);
+        if (i + 1 < len_b) push_next(g, n, seq[i + 1]);
     }
     order_reserve(g, g->len + len_b);
 
@@ -221,7 +281,7 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
                     node_kill(g, seq[num2]);
                 } else {
                     if (num2 >= 1) {
-                        push_pre(c, seq[num2 - 1], 1);
+                        push_pre(g, c, seq[num2 - 1], 1);
                         poa_node* q = &g->node[seq[num2 - 1]];
                         q->next[q->out - 1] = cur;
                     }
@@ -233,7 +293,7 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
                     node_kill(g, seq[0]);
                     seq[0] = cur;
                 } else {
-                    push_next(c, seq[1]);
+                    push_next(g, c, seq[1]);
                     poa_node* q = &g->node[seq[1]];
                     q->pre[(q->in > 0 ? q->in : 1) - 1] = cur;
                     node_kill(g, seq[0]);          /* the reference leaks it; it is in no list */
@@ -243,13 +303,13 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
                 if (P_sub != -1 && next_is_match) {
                     c->ew[st.pred]++;
                 } else {
-                    push_pre(c, seq[num2 - 1], 1);
+                    push_pre(g, c, seq[num2 - 1], 1);
                     poa_node* q = &g->node[seq[num2 - 1]];
                     q->next[q->out - 1] = cur;
                 }
                 if (!(cont == 1 || cont == 5)) {
                     c = &g->node[cur];
-                    push_next(c, seq[num2 + 1]);
+                    push_next(g, c, seq[num2 + 1]);
                     poa_node* q = &g->node[seq[num2 + 1]];
                     q->pre[(q->in > 0 ? q->in : 1) - 1] = cur;
                 }
@@ -274,7 +334,7 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
                         if (mn->pre[ss] == P) { mn->ew[ss]++; s2 = -1; }
                 }
                 if (s2 != -1) {
-                    push_pre(&g->node[MN], seq[num2 - 1], 1);
+                    push_pre(g, &g->node[MN], seq[num2 - 1], 1);
                     poa_node* q = &g->node[seq[num2 - 1]];
                     q->next[q->out - 1] = MN;
                 }
@@ -293,7 +353,7 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
             if (s4 == 1 && num2 != len_b - 1) {
                 poa_node* q = &g->node[seq[num2 + 1]];
                 q->pre[(q->in > 0 ? q->in : 1) - 1] = MN;
-                push_next(&g->node[MN], seq[num2 + 1]);
+                push_next(g, &g->node[MN], seq[num2 + 1]);
             }
             g->node[MN].passing_seq[num] = 1;
             cont = (s2 == -1) ? 5 : 4;

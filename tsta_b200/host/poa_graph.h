@@ -48,6 +48,12 @@ typedef struct {
     int order_cap;
     int last_node_num;
     int nseq;
+    /* small-array pool: the pre / ew / next / passing_seq arrays of the nodes (a read adds one
+     * provisional node per base every round, so malloc/free of these dominated the fuse step) */
+    void* pool_blocks;        /* singly linked 1 MiB blocks */
+    char* pool_cur;
+    size_t pool_left;
+    void* pool_free[28];      /* free lists by log2(size in 8-byte units) */
 } poa_graph;
 
 /* One traceback step, produced by the DP (GPU) or the oracle: the cell (row, col) and what
