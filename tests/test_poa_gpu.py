@@ -119,6 +119,35 @@ def test_long_graph_far_predecessors_and_wide_in_degree(gpu):
     poa.close()
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_quirk_rows_n_columns_and_late_heads(gpu, seed):
+    """The two quirks the kernel keeps out of its straight-line step: reads with 'N'
+    (Q3, c-t-simd.c:461,481) and head rows at or beyond row L whose carried F is re-based at column L
+    (Q1, 228-233) -- many heads, small L, so that both meet inside one strip."""
+    rnd = random.Random(1000 + seed)
+    poa = gpu.Poa()
+    for k in range(4):
+        M, X, E, O = rnd.choice([(2, -5, -2, -4), (2, -3, -2, -4), (1, -1, -1, 0), (1, -3, -1, -5)])
+        nrows, ln, L = rnd.choice([200, 500, 900]), rnd.choice([130, 300, 700]), rnd.choice([64, 128])
+        read = bytearray(synth.random_read(ln, 77 * seed + k))
+        for i in range(ln):
+            if rnd.random() < 0.06:
+                read[i] = ord("N")
+        read = bytes(read)
+        g = random_dag(nrows, rnd, E, O, heads=0.05, backbone=read.replace(b"N", b"A"))
+        src, es, fs, last = ob.poa_fill(*g, read, M, X, E, O, L)
+        glast, _ = poa.fill(*g, read, M, X, E, O, L)
+        np.testing.assert_array_equal(glast, last)
+        assert_trace(poa, src, es, fs, g)
+        for start in {nrows - 1, rnd.randrange(nrows)}:
+            want = ob.poa_walk(g[0], g[1], src, es, fs, start)
+            got, _ = poa.walk(start)
+            assert len(got) == len(want)
+            for fld in ("row", "col", "kind", "pred"):
+                np.testing.assert_array_equal(got[fld], want[fld])
+    poa.close()
+
+
 def run_msa(reads, prm, W, tmp_path):
     fa, fo = tmp_path / "r.fa", tmp_path / "o.txt"
     ob.write_fasta(fa, reads)
