@@ -33,6 +33,27 @@ def test_short_read_batch_vs_oracle(gpu, prm):
         assert r1.output_bytes(k) == o.output_bytes(), k
 
 
+@pytest.mark.parametrize("chunks", [3, 8])
+def test_chunked_upload_mixed_alphabets(gpu, chunks, monkeypatch):
+    """Large batches are uploaded in chunks that overlap with the kernels of the previous chunk; every
+    chunk scans its own alphabet, so a batch whose chunks differ (ACGT reads, then 20-letter reads)
+    runs packed kernels on one chunk and the generic ones on the other."""
+    monkeypatch.setenv("TSTA_BATCH_CHUNKS", str(chunks))
+    rnd = random.Random(4)
+    alpha = b"ACDEFGHIKLMNPQRSTVWY"
+    pairs = _mixed_pairs(150, 8, [1, 60, 128, 250, 256])
+    pairs += [(bytes(rnd.choice(alpha) for _ in range(rnd.randint(1, 200))),
+               bytes(rnd.choice(alpha) for _ in range(rnd.randint(1, 200)))) for _ in range(90)]
+    pairs += _mixed_pairs(60, 9, [100, 250])
+    r0 = gpu.psa_batch(pairs, trace=False)
+    r1 = gpu.psa_batch(pairs, trace=True)
+    for k, (x, y) in enumerate(pairs):
+        o = ob.psa(x, y)
+        assert (r0.maxsorce[k], r0.corner[k]) == (o.maxsorce, o.corner), k
+        assert (r1.maxsorce[k], r1.corner[k]) == (o.maxsorce, o.corner), k
+        assert r1.output_bytes(k) == o.output_bytes(), k
+
+
 def test_long_pairs_in_a_batch(gpu):
     pairs = _mixed_pairs(12, 5, [3000, 5000, 10000]) + _mixed_pairs(40, 6, [250])
     r1 = gpu.psa_batch(pairs, trace=True)

@@ -31,21 +31,27 @@ namespace {
 // Device buffers, stream and events of the calling thread, kept across calls: a caller that
 // streams batches pays for the allocations once (cudaMalloc/cudaFree of hundreds of MB cost
 // more than the kernels of a 1M x 250 bp batch).
+constexpr int kMaxChunks = 8;
 struct BatchCtx {
     int device = -1;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;             // kernels
+    cudaStream_t cp = nullptr, dh = nullptr;   // host -> device copies of the chunks ahead; device -> host of finished chunks
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t evc[kMaxChunks] = {};      // chunk c uploaded and its alphabet scanned
     DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs;
-    int* h_present = nullptr;   // pinned, 8 words
+    int* h_present = nullptr;   // pinned, 8 words per chunk
     void release()
     {
         DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs};
         for (DevBuf* b : all) b->release();
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+        for (auto& e : evc) { if (e) cudaEventDestroy(e); e = nullptr; }
         if (st) cudaStreamDestroy(st);
+        if (cp) cudaStreamDestroy(cp);
+        if (dh) cudaStreamDestroy(dh);
         if (h_present) cudaFreeHost(h_present);
-        st = nullptr; e0 = e1 = nullptr; h_present = nullptr; device = -1;
+        st = cp = dh = nullptr; e0 = e1 = nullptr; h_present = nullptr; device = -1;
     }
     ~BatchCtx() { /* process exit: the CUDA context may already be gone; leave the buffers to it */ }
 };
@@ -82,6 +88,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     if (int rc = ensure_device()) return rc;
 
     int64_t tot0 = 0, tot1 = 0, max0 = 0, max1 = 0, ops_total = 0;
+    double cells = 0.0;
     for (int64_t k = 0; k < npairs; k++) {
         if (len0[k] < len1[k] || len1[k] < 0 || off0[k] < 0 || off1[k] < 0)
             return set_error(TSTA_EINVAL, "pair %lld: need len0 >= len1 >= 0 (the caller swaps, psa.c:194-199)", (long long)k);
@@ -90,6 +97,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         tot1 = std::max<int64_t>(tot1, off1[k] + len1[k]);
         max0 = std::max<int64_t>(max0, len0[k]);
         max1 = std::max<int64_t>(max1, len1[k]);
+        cells += (double)len0[k] * (double)len1[k];
         if (want_trace) ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
     }
     const int S = want_trace ? 2 : 1;
@@ -100,9 +108,12 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     if (g_ctx.device != dev) {
         if (g_ctx.device >= 0) { cudaSetDevice(g_ctx.device); g_ctx.release(); cudaSetDevice(dev); }
         TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.st, cudaStreamNonBlocking));
+        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.cp, cudaStreamNonBlocking));
+        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.dh, cudaStreamNonBlocking));
         TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e0));
         TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e1));
-        TSTA_CUDA_TRY(cudaMallocHost((void**)&g_ctx.h_present, 8 * sizeof(int)));
+        for (auto& e : g_ctx.evc) TSTA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        TSTA_CUDA_TRY(cudaMallocHost((void**)&g_ctx.h_present, kMaxChunks * 8 * sizeof(int)));
         g_ctx.device = dev;
     }
     Guard g(g_ctx);
@@ -118,40 +129,48 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     if (int rc = g.alloc(&d_len1, (size_t)npairs, g_ctx.len1)) return rc;
     if (int rc = g.alloc(&d_ms, (size_t)npairs, g_ctx.ms)) return rc;
     if (int rc = g.alloc(&d_corner, (size_t)npairs, g_ctx.corner)) return rc;
-    if (int rc = g.alloc(&d_ctl, 16, g_ctx.ctl)) return rc;
+    if (int rc = g.alloc(&d_ctl, 16 + 8 * kMaxChunks, g_ctx.ctl)) return rc;
     static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
-    TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0, seqs0, (size_t)tot0, cudaMemcpyHostToDevice, g.st));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1, seqs1, (size_t)tot1, cudaMemcpyHostToDevice, g.st));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(d_off0, off0, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1, off1, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0, len0, (size_t)npairs * 4, cudaMemcpyHostToDevice, g.st));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(d_len1, len1, (size_t)npairs * 4, cudaMemcpyHostToDevice, g.st));
 
-    // alphabet over the whole batch
-    TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 16 * sizeof(int), g.st));
-    TSTA_CUDA_TRY(launch_byte_presence(d_s0, tot0, reinterpret_cast<unsigned*>(d_ctl + 8), sms * 4, g.st));
-    TSTA_CUDA_TRY(launch_byte_presence(d_s1, tot1, reinterpret_cast<unsigned*>(d_ctl + 8), sms * 4, g.st));
-    unsigned* present = reinterpret_cast<unsigned*>(g_ctx.h_present);
-    TSTA_CUDA_TRY(cudaMemcpyAsync(present, d_ctl + 8, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, g.st));
-    TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
+    // ---- chunks: the reads of chunk c+1 travel to the device while chunk c is computed -----------
+    // (a 1M x 250 bp batch is 0.5 GB of reads against 15 ms of kernel time).  Every chunk gets its
+    // own alphabet scan, so its kernels can start as soon as its bytes have arrived.
+    // Worth it only when the copy is not negligible against the kernels (short reads: ~125 cells per
+    // byte; 10 kbp reads: 5000) and every chunk still has many pairs per resident warp.
+    int nch = (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(1, (tot0 + tot1) / ((int64_t)48 << 20)));
+    nch = (int)std::min<int64_t>(nch, std::max<int64_t>(1, npairs / ((int64_t)sms * 24 * 16)));
+    if (cells > 1000.0 * (double)(tot0 + tot1)) nch = 1;
+    if (const char* e = getenv("TSTA_BATCH_CHUNKS")) nch = std::max(1, std::min(kMaxChunks, atoi(e)));
+    nch = (int)std::min<int64_t>(nch, npairs);
+    int64_t kb[kMaxChunks + 1];
+    for (int c = 0; c <= nch; c++) kb[c] = npairs * c / nch;
+    unsigned* d_present = reinterpret_cast<unsigned*>(d_ctl + 16);
+    TSTA_CUDA_TRY(cudaMemsetAsync(d_present, 0, 8 * kMaxChunks * sizeof(unsigned), g_ctx.cp));
+    for (int c = 0; c < nch; c++) {
+        const int64_t a0 = kb[c], a1 = kb[c + 1];
+        int64_t lo0 = INT64_MAX, hi0 = 0, lo1 = INT64_MAX, hi1 = 0;
+        for (int64_t k = a0; k < a1; k++) {
+            lo0 = std::min<int64_t>(lo0, off0[k]); hi0 = std::max<int64_t>(hi0, off0[k] + len0[k]);
+            lo1 = std::min<int64_t>(lo1, off1[k]); hi1 = std::max<int64_t>(hi1, off1[k] + len1[k]);
+        }
+        cudaStream_t cp = g_ctx.cp;
+        if (hi0 > lo0) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0 + lo0, seqs0 + lo0, (size_t)(hi0 - lo0), cudaMemcpyHostToDevice, cp));
+        if (hi1 > lo1) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1 + lo1, seqs1 + lo1, (size_t)(hi1 - lo1), cudaMemcpyHostToDevice, cp));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(d_off0 + a0, off0 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1 + a0, off1 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0 + a0, len0 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(d_len1 + a0, len1 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));
+        if (hi0 > lo0) TSTA_CUDA_TRY(launch_byte_presence(d_s0 + lo0, hi0 - lo0, d_present + 8 * c, sms * 4, cp));
+        if (hi1 > lo1) TSTA_CUDA_TRY(launch_byte_presence(d_s1 + lo1, hi1 - lo1, d_present + 8 * c, sms * 4, cp));
+        TSTA_CUDA_TRY(cudaMemcpyAsync(g_ctx.h_present + 8 * c, d_present + 8 * c, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, cp));
+        TSTA_CUDA_TRY(cudaEventRecord(g_ctx.evc[c], cp));
+    }
 
     PsaBatchArgs a{};
     a.sc.M = prm->M; a.sc.X = prm->X; a.sc.E = prm->E; a.sc.O = prm->O;
-    const int K = build_lut(present, a.sc.lut);
-    const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
-    // packed int16 kernels (psa_fill16.cuh) when alphabet and score range allow; 64*C columns per band
-    // (traced: at most 4 columns per virtual lane, the direction ring of wider strips would
-    // not leave room for enough warps per SM)
-    const int C16 = (max0 <= 128) ? 2 : ((max0 <= 256 || want_trace) ? 4 : 8);
-    const char* off16 = getenv("TSTA_PSA_PACKED");
-    const bool packed = !(off16 && atoi(off16) == 0) &&
-                        psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, C16, K);
-    const char* offd = getenv("TSTA_PSA_DUAL");
-    const bool dual = packed && max0 <= 256 && !(offd && atoi(offd) == 0) &&
-                      psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, 8, K);
-    const int Cd = max0 <= 128 ? 4 : 8;                          // dual-pair mode: 32*Cd columns, one band
-    const int C = dual ? Cd : (packed ? C16 : ((max0 <= 128) ? 4 : 8));
-    const int band_cols = dual ? 32 * Cd : (packed ? 64 : 32) * C;
+    // strip widths depend on the longest read of the whole batch; the largest band any variant uses
+    // is 512 columns (per-chunk choices below only pick among them)
+    constexpr int kMaxBandCols = 512;
 
     // persistent grid: ~24 warps per SM (register-limited), never more warps than pairs
     int blocks = sms * 6;
@@ -160,10 +179,9 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     unsigned long long* d_scratch;
     int* d_lastrow;
     if (int rc = g.alloc(&d_scratch, (size_t)nwarps * (size_t)std::max<int64_t>(max1, 1), g_ctx.scratch)) return rc;
-    if (int rc = g.alloc(&d_lastrow, (size_t)nwarps * band_cols, g_ctx.lastrow)) return rc;
+    if (int rc = g.alloc(&d_lastrow, (size_t)nwarps * kMaxBandCols, g_ctx.lastrow)) return rc;
 
     a.seqs0 = d_s0; a.seqs1 = d_s1;
-    a.off0 = d_off0; a.off1 = d_off1; a.len0 = d_len0; a.len1 = d_len1;
     a.scratch = d_scratch; a.scratch_stride = std::max<int64_t>(max1, 1);
     a.ticket = reinterpret_cast<unsigned long long*>(d_ctl);
     a.lastrow = d_lastrow;
@@ -179,7 +197,6 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     size_t dirs_budget = 0;
     if (want_trace) {
         size_t free_b = 0, total_b = 0;
-        TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         if (int rc = g.alloc(&d_ops, (size_t)ops_total, g_ctx.ops)) return rc;
         if (int rc = g.alloc(&d_ops_off, (size_t)npairs, g_ctx.ops_off)) return rc;
         if (int rc = g.alloc(&d_alen, (size_t)npairs, g_ctx.alen)) return rc;
@@ -191,88 +208,121 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         // resident warps (3552) leaves sub-partitions idle
         dirs_budget = (size_t)((double)(free_b + g_ctx.dirs.cap) * 0.8);
     }
-    auto dirs_bytes = [&](int64_t k) -> size_t {
-        const size_t nb = (size_t)((len0[k] + band_cols - 1) / band_cols);
-        return (size_t)len1[k] * nb * (size_t)(band_cols / 2);
-    };
 
-    size_t slice_target = dirs_budget;   // equal slices: a short last slice would leave most warps idle
-    if (want_trace) {
-        size_t total = 0;
-        for (int64_t k = 0; k < npairs; k++) total += (dirs_bytes(k) + 255) & ~(size_t)255;
-        const size_t nslices = std::max<size_t>(1, (total + dirs_budget - 1) / std::max<size_t>(dirs_budget, 1));
-        slice_target = std::min(dirs_budget, (total + nslices - 1) / nslices + ((size_t)64 << 20));
-    }
     float total_ms = 0.f;
-    int64_t k0 = 0;
-    while (k0 < npairs) {
-        int64_t k1 = npairs;
-        size_t slice_bytes = 0;
+    for (int c = 0; c < nch; c++) {
+        // ---- this chunk's alphabet decides its kernels -------------------------------------------
+        TSTA_CUDA_TRY(cudaEventSynchronize(g_ctx.evc[c]));
+        TSTA_CUDA_TRY(cudaStreamWaitEvent(g.st, g_ctx.evc[c], 0));
+        const unsigned* present = reinterpret_cast<const unsigned*>(g_ctx.h_present + 8 * c);
+        const int K = build_lut(present, a.sc.lut);
+        const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
+        // packed int16 kernels (psa_fill16.cuh) when alphabet and score range allow; 64*C columns per band
+        // (traced: at most 4 columns per virtual lane, the direction ring of wider strips would
+        // not leave room for enough warps per SM)
+        const int C16 = (max0 <= 128) ? 2 : ((max0 <= 256 || want_trace) ? 4 : 8);
+        const char* off16 = getenv("TSTA_PSA_PACKED");
+        const bool packed = !(off16 && atoi(off16) == 0) &&
+                            psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, C16, K);
+        const char* offd = getenv("TSTA_PSA_DUAL");
+        const bool dual = packed && max0 <= 256 && !(offd && atoi(offd) == 0) &&
+                          psa16_fits(prm->M, prm->X, prm->E, prm->O, want_trace ? 4 : 1, 8, K);
+        const int Cd = max0 <= 128 ? 4 : 8;                          // dual-pair mode: 32*Cd columns, one band
+        const int C = dual ? Cd : (packed ? C16 : ((max0 <= 128) ? 4 : 8));
+        const int band_cols = dual ? 32 * Cd : (packed ? 64 : 32) * C;
+        auto dirs_bytes = [&](int64_t k) -> size_t {
+            const size_t nb = (size_t)((len0[k] + band_cols - 1) / band_cols);
+            return (size_t)len1[k] * nb * (size_t)(band_cols / 2);
+        };
+        const int64_t kend = kb[c + 1];
+        size_t slice_target = dirs_budget;   // equal slices: a short last slice would leave most warps idle
         if (want_trace) {
-            k1 = k0;
-            while (k1 < npairs) {
-                const size_t b = (dirs_bytes(k1) + 255) & ~(size_t)255;
-                if (k1 > k0 && slice_bytes + b > slice_target) break;
-                dirs_off[(size_t)k1] = (long long)slice_bytes;
-                slice_bytes += b;
-                k1++;
+            size_t total = 0;
+            for (int64_t k = kb[c]; k < kend; k++) total += (dirs_bytes(k) + 255) & ~(size_t)255;
+            const size_t nslices = std::max<size_t>(1, (total + dirs_budget - 1) / std::max<size_t>(dirs_budget, 1));
+            slice_target = std::min(dirs_budget, (total + nslices - 1) / nslices + ((size_t)64 << 20));
+        }
+        int64_t k0 = kb[c];
+        while (k0 < kend) {
+            int64_t k1 = kend;
+            size_t slice_bytes = 0;
+            if (want_trace) {
+                k1 = k0;
+                while (k1 < kend) {
+                    const size_t b = (dirs_bytes(k1) + 255) & ~(size_t)255;
+                    if (k1 > k0 && slice_bytes + b > slice_target) break;
+                    dirs_off[(size_t)k1] = (long long)slice_bytes;
+                    slice_bytes += b;
+                    k1++;
+                }
+                if (slice_bytes > g_ctx.dirs.cap) TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));   // (the old buffer may still be read)
+                if (int rc = g_ctx.dirs.reserve(std::max<size_t>(slice_bytes, 256))) return rc;
+                d_dirs = g_ctx.dirs.as<uint8_t>();
+                TSTA_CUDA_TRY(cudaMemcpyAsync(d_dirs_off + k0, dirs_off.data() + k0, (size_t)(k1 - k0) * 8,
+                                              cudaMemcpyHostToDevice, g.st));
             }
-            if (int rc = g_ctx.dirs.reserve(std::max<size_t>(slice_bytes, 256))) return rc;
-            d_dirs = g_ctx.dirs.as<uint8_t>();
-            TSTA_CUDA_TRY(cudaMemcpyAsync(d_dirs_off + k0, dirs_off.data() + k0, (size_t)(k1 - k0) * 8,
-                                          cudaMemcpyHostToDevice, g.st));
+            a.off0 = d_off0 + k0; a.off1 = d_off1 + k0; a.len0 = d_len0 + k0; a.len1 = d_len1 + k0;
+            a.npairs = k1 - k0;
+            a.dirs = d_dirs; a.dirs_off = want_trace ? d_dirs_off + k0 : nullptr;
+            a.maxsorce = d_ms + k0; a.corner = d_corner + k0;
+            TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 8, g.st));
+            TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
+            if (want_trace) {
+                if (packed && dual) {   // short reads: two pairs per warp; the step ring is 16 KB (Cd = 4) or 32 KB (Cd = 8) per warp
+                    if (Cd == 4) psa_batch16_dual_kernel<4, true, 4><<<blocks, 128, 0, g.st>>>(a);
+                    else psa_batch16_dual_kernel<8, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
+                } else if (packed) {   // two warps per CTA: the step ring of direction words is 16 KB per warp
+                    if (C == 2) psa_batch16_kernel<2, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
+                    else psa_batch16_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
+                } else if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
+                else launch_batch<8, true, kBatchWarps>(prmt, blocks, g.st, a);
+                PsaBatchTraceArgs t{};
+                t.enc = packed ? 1 : 0;
+                t.dirs = d_dirs; t.dirs_off = d_dirs_off + k0;
+                t.len0 = d_len0 + k0; t.len1 = d_len1 + k0; t.npairs = k1 - k0;
+                t.cols_per_band = band_cols;
+                t.ops = d_ops; t.ops_off = d_ops_off + k0; t.alen = d_alen + k0;
+                psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
+            } else if (packed && dual) {
+                // short reads: two pairs per warp (psa_sweep_dual16), 32*Cd columns each
+                if (Cd == 4) psa_batch16_dual_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+                else psa_batch16_dual_kernel<8, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            } else if (packed) {
+                if (C == 2) psa_batch16_kernel<2, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+                else if (C == 4) psa_batch16_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+                else psa_batch16_kernel<8, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
+            } else {
+                if (C == 4) launch_batch<4, false, kBatchWarps>(prmt, blocks, g.st, a);
+                else launch_batch<8, false, kBatchWarps>(prmt, blocks, g.st, a);
+            }
+            cudaError_t le = cudaGetLastError();
+            TSTA_CUDA_TRY(cudaEventRecord(g.e1, g.st));
+            cudaError_t se = cudaStreamSynchronize(g.st);
+            TSTA_CUDA_TRY(le);
+            TSTA_CUDA_TRY(se);
+            float ms = 0.f;
+            TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, g.e0, g.e1));
+            total_ms += ms;
+            k0 = k1;
         }
-        a.off0 = d_off0 + k0; a.off1 = d_off1 + k0; a.len0 = d_len0 + k0; a.len1 = d_len1 + k0;
-        a.npairs = k1 - k0;
-        a.dirs = d_dirs; a.dirs_off = want_trace ? d_dirs_off + k0 : nullptr;
-        a.maxsorce = d_ms + k0; a.corner = d_corner + k0;
-        TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 8, g.st));
-        TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
-        if (want_trace) {
-            if (packed && dual) {   // short reads: two pairs per warp; the step ring is 16 KB (Cd = 4) or 32 KB (Cd = 8) per warp
-                if (Cd == 4) psa_batch16_dual_kernel<4, true, 4><<<blocks, 128, 0, g.st>>>(a);
-                else psa_batch16_dual_kernel<8, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
-            } else if (packed) {   // two warps per CTA: the step ring of direction words is 16 KB per warp
-                if (C == 2) psa_batch16_kernel<2, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
-                else psa_batch16_kernel<4, true, 2><<<blocks * 2, 64, 0, g.st>>>(a);
-            } else if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
-            else launch_batch<8, true, kBatchWarps>(prmt, blocks, g.st, a);
-            PsaBatchTraceArgs t{};
-            t.enc = packed ? 1 : 0;
-            t.dirs = d_dirs; t.dirs_off = d_dirs_off + k0;
-            t.len0 = d_len0 + k0; t.len1 = d_len1 + k0; t.npairs = k1 - k0;
-            t.cols_per_band = band_cols;
-            t.ops = d_ops; t.ops_off = d_ops_off + k0; t.alen = d_alen + k0;
-            psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
-        } else if (packed && dual) {
-            // short reads: two pairs per warp (psa_sweep_dual16), 32*Cd columns each
-            if (Cd == 4) psa_batch16_dual_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
-            else psa_batch16_dual_kernel<8, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
-        } else if (packed) {
-            if (C == 2) psa_batch16_kernel<2, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
-            else if (C == 4) psa_batch16_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
-            else psa_batch16_kernel<8, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
-        } else {
-            if (C == 4) launch_batch<4, false, kBatchWarps>(prmt, blocks, g.st, a);
-            else launch_batch<8, false, kBatchWarps>(prmt, blocks, g.st, a);
+        // ---- results of a finished chunk travel back while the next one is computed --------------
+        if (want_trace && nch > 1) {
+            int64_t lo = INT64_MAX, hi = 0;
+            for (int64_t k = kb[c]; k < kend; k++) {
+                lo = std::min<int64_t>(lo, ops_off[k]);
+                hi = std::max<int64_t>(hi, ops_off[k] + len0[k] + len1[k]);
+            }
+            if (hi > lo) TSTA_CUDA_TRY(cudaMemcpyAsync(ops + lo, d_ops + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, g_ctx.dh));
         }
-        cudaError_t le = cudaGetLastError();
-        TSTA_CUDA_TRY(cudaEventRecord(g.e1, g.st));
-        cudaError_t se = cudaStreamSynchronize(g.st);
-        TSTA_CUDA_TRY(le);
-        TSTA_CUDA_TRY(se);
-        float ms = 0.f;
-        TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, g.e0, g.e1));
-        total_ms += ms;
-        k0 = k1;
     }
     TSTA_CUDA_TRY(cudaMemcpyAsync(maxsorce, d_ms, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
     TSTA_CUDA_TRY(cudaMemcpyAsync(corner, d_corner, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
     if (want_trace) {
         TSTA_CUDA_TRY(cudaMemcpyAsync(alen, d_alen, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
-        TSTA_CUDA_TRY(cudaMemcpyAsync(ops, d_ops, (size_t)ops_total, cudaMemcpyDeviceToHost, g.st));
+        if (nch == 1) TSTA_CUDA_TRY(cudaMemcpyAsync(ops, d_ops, (size_t)ops_total, cudaMemcpyDeviceToHost, g.st));
     }
     TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(g_ctx.dh));
     if (kernel_ms) *kernel_ms = total_ms;
     return TSTA_OK;
 }
