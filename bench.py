@@ -317,6 +317,9 @@ def msa_node_cells(fasta_path: str, device: int | None = None):
     raise RuntimeError("TSTA_msa timing line missing: " + p.stderr.decode()[-300:])
 
 
+MSA_LAST = {}
+
+
 def run_msa_once(fasta_path: str, out_path: str, device: int):
     """One TSTA_msa process on `device`: (wall s, kernel s, node-cells, launches)."""
     env = dict(os.environ, TSTA_MSA_TIMING="1")
@@ -333,10 +336,13 @@ def run_msa_once(fasta_path: str, out_path: str, device: int):
         raise RuntimeError("TSTA_msa failed: " + p.stderr.decode()[-300:])
     fill_ms = walk_ms = cells = 0.0
     loop_s = None
+    global MSA_LAST
     for line in p.stderr.decode().splitlines():
         if line.startswith("kernels:"):
             parts = line.replace(",", " ").split()
             fill_ms, walk_ms, cells = float(parts[2]), float(parts[5]), float(parts[7])
+            MSA_LAST = {"fill_ms": fill_ms, "walk_ms": walk_ms, "node_cells": cells,
+                        "edge_cells": float(parts[-2]) if parts[-1] == "edge-cells" else None}
         if line.startswith("timing:"):
             w = line.split()
             loop_s = sum(float(w[k]) for k in (2, 4, 6, 8, 10))
@@ -629,10 +635,16 @@ def main():
         pk = peaks()
         achieved = fill_rate * LANE_OPS_PER_CELL / 1e12
         if kind == "msa":
-            roof = {"bound": "int_alu", "bound_note": "int32 ALU issue, latency bound (POA fill; in-degree dependent)", "achieved": fill_rate / 1e9,
-                    "peak": None, "unit": "GCUPS", "frac": None, "kernel": kernel_name, "kernel_ms": fill_only,
-                    "traffic": None, "note": "no algorithmic op count is defined for the graph DP (2*in+5 int ops per cell, "
-                                             "SURVEY.md 8d); see profiles/ for the ncu summary"}
+            # algorithmic work of the graph DP: 2*in + 5 int32 lane-ops per cell, i.e.
+            # 2 per edge-cell + 5 per node-cell; int32 kernel -> held against the measured VIADDMNMX rate
+            ec, nc, fm = MSA_LAST.get("edge_cells"), MSA_LAST.get("node_cells"), MSA_LAST.get("fill_ms")
+            ach = (2.0 * ec + 5.0 * nc) / (fm * 1e-3) / 1e12 if ec and nc and fm else None
+            roof = {"bound": "int_alu", "bound_note": "int32 ALU issue; the kernel is latency bound (one warp per SM sub-partition, DESIGN.md 6)",
+                    "achieved": ach, "peak": dpx_peak / 1e12, "unit": "Tlaneop/s", "frac": (ach / (dpx_peak / 1e12)) if ach else None,
+                    "peak_source": "measured live: dependency-free VIADDMNMX loop (tsta_measure_dpx_peak)",
+                    "algorithmic_ops": "2 per edge-cell + 5 per node-cell (SURVEY.md 8d)", "edge_cells": ec, "node_cells": nc,
+                    "kernel": kernel_name, "kernel_ms": fm, "fill_gcups": fill_rate / 1e9, "traffic": None,
+                    "note": "profiles/r01_poa_fill_16x20k_bytekeys.md: 636 cycles per row-step of 128 cells for 193 instructions"}
         else:
             # The packed kernels advance two cells per lane-op (int16 x 2), so their issue roofline is
             # twice the measured int32 VIADDMNMX rate; int32 kernels (fallback) are held against the rate itself.

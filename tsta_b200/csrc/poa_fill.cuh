@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
     const uint32_t bring_addr = (uint32_t)__cvta_generic_to_shared(&sm.bring[0]);
     const uint32_t tr_addr = (uint32_t)__cvta_generic_to_shared(&sm.tr[0][0]) + lane * (C * 2);
     const unsigned ep16 = a.epoch << 1;
+    // "no predecessor" is the same -infinity for every lane: all lanes read ONE address (a broadcast,
+    // one wavefront) instead of their own copy 32 bytes apart (two-way bank conflicts on every load)
+    const uint32_t none_addr = hist_addr + kPoaSlotNone * kSlotBytes + 32;
     // flags (descriptor bits 16..) that take a lane out of the PLAIN step: slow / spilled rows always,
     // late heads only in the lanes that own column L-1 or L; every row when the strip has an 'N'
     const unsigned unplain = hasN ? 0xffffffffu : (((kPoaSlow | kPoaKeep) | (hasL ? kPoaLate : 0u)) << 16);
@@ -328,7 +331,8 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 #pragma unroll
                 for (int j = 1; j < kPoaFast; j++) {
                     if (j == 3 && !any4) continue;
-                    const uint32_t A = my_hist + ((dsc.y >> (8 * j)) & 0xffu) * kSlotBytes;
+                    const uint32_t slot = (dsc.y >> (8 * j)) & 0xffu;
+                    const uint32_t A = slot == kPoaSlotNone ? none_addr : my_hist + slot * kSlotBytes;
                     const int Hd0 = lds_s32(A + 24);
                     const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
                     const int wd = 192 + 63 - j, we = 64 + 63 - j;
@@ -380,7 +384,8 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 #pragma unroll
                     for (int j = 1; j < kPoaFast; j++) {
                         if ((j == 2 && !any3) || (j == 3 && !any4)) continue;
-                        const uint32_t A = my_hist + ((dsc.y >> (8 * j)) & 0xffu) * kSlotBytes;
+                        const uint32_t slot = (dsc.y >> (8 * j)) & 0xffu;
+                        const uint32_t A = slot == kPoaSlotNone ? none_addr : my_hist + slot * kSlotBytes;
                         const int Hd0 = lds_s32(A + 24);
                         const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
                         const int wd = 192 + 63 - j, we = 64 + 63 - j;
