@@ -40,6 +40,7 @@ struct BatchCtx {
     cudaEvent_t evc[kMaxChunks] = {};      // chunk c uploaded and its alphabet scanned
     DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs;
     int* h_present = nullptr;   // pinned, 8 words per chunk
+    std::vector<cudaEvent_t> ev;   // timing events, two per kernel slice, grown on demand
     void release()
     {
         DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs};
@@ -47,6 +48,8 @@ struct BatchCtx {
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         for (auto& e : evc) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : ev) cudaEventDestroy(e);
+        ev.clear();
         if (st) cudaStreamDestroy(st);
         if (cp) cudaStreamDestroy(cp);
         if (dh) cudaStreamDestroy(dh);
@@ -209,7 +212,19 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         dirs_budget = (size_t)((double)(free_b + g_ctx.dirs.cap) * 0.8);
     }
 
-    float total_ms = 0.f;
+    // No host synchronisation inside the loop: the host prepares chunk c+1 (slice layout, alphabet)
+    // while the kernels of chunk c run; kernel time is summed from event pairs at the end.
+    size_t nev = 0;
+    auto next_event = [&](cudaEvent_t* out) -> cudaError_t {
+        if (nev == g_ctx.ev.size()) {
+            cudaEvent_t e;
+            cudaError_t rc = cudaEventCreate(&e);
+            if (rc != cudaSuccess) return rc;
+            g_ctx.ev.push_back(e);
+        }
+        *out = g_ctx.ev[nev++];
+        return cudaSuccess;
+    };
     for (int c = 0; c < nch; c++) {
         // ---- this chunk's alphabet decides its kernels -------------------------------------------
         TSTA_CUDA_TRY(cudaEventSynchronize(g_ctx.evc[c]));
@@ -243,6 +258,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
             slice_target = std::min(dirs_budget, (total + nslices - 1) / nslices + ((size_t)64 << 20));
         }
         int64_t k0 = kb[c];
+        cudaEvent_t last_done = nullptr;
         while (k0 < kend) {
             int64_t k1 = kend;
             size_t slice_bytes = 0;
@@ -265,8 +281,11 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
             a.npairs = k1 - k0;
             a.dirs = d_dirs; a.dirs_off = want_trace ? d_dirs_off + k0 : nullptr;
             a.maxsorce = d_ms + k0; a.corner = d_corner + k0;
+            cudaEvent_t ea, eb;
+            TSTA_CUDA_TRY(next_event(&ea));
+            TSTA_CUDA_TRY(next_event(&eb));
             TSTA_CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 8, g.st));
-            TSTA_CUDA_TRY(cudaEventRecord(g.e0, g.st));
+            TSTA_CUDA_TRY(cudaEventRecord(ea, g.st));
             if (want_trace) {
                 if (packed && dual) {   // short reads: two pairs per warp; the step ring is 16 KB (Cd = 4) or 32 KB (Cd = 8) per warp
                     if (Cd == 4) psa_batch16_dual_kernel<4, true, 4><<<blocks, 128, 0, g.st>>>(a);
@@ -296,13 +315,9 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                 else launch_batch<8, false, kBatchWarps>(prmt, blocks, g.st, a);
             }
             cudaError_t le = cudaGetLastError();
-            TSTA_CUDA_TRY(cudaEventRecord(g.e1, g.st));
-            cudaError_t se = cudaStreamSynchronize(g.st);
+            TSTA_CUDA_TRY(cudaEventRecord(eb, g.st));
             TSTA_CUDA_TRY(le);
-            TSTA_CUDA_TRY(se);
-            float ms = 0.f;
-            TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, g.e0, g.e1));
-            total_ms += ms;
+            last_done = eb;
             k0 = k1;
         }
         // ---- results of a finished chunk travel back while the next one is computed --------------
@@ -312,6 +327,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                 lo = std::min<int64_t>(lo, ops_off[k]);
                 hi = std::max<int64_t>(hi, ops_off[k] + len0[k] + len1[k]);
             }
+            if (last_done) TSTA_CUDA_TRY(cudaStreamWaitEvent(g_ctx.dh, last_done, 0));
             if (hi > lo) TSTA_CUDA_TRY(cudaMemcpyAsync(ops + lo, d_ops + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, g_ctx.dh));
         }
     }
@@ -323,6 +339,12 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     }
     TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
     TSTA_CUDA_TRY(cudaStreamSynchronize(g_ctx.dh));
+    float total_ms = 0.f;
+    for (size_t i = 0; i + 1 < nev; i += 2) {
+        float ms = 0.f;
+        TSTA_CUDA_TRY(cudaEventElapsedTime(&ms, g_ctx.ev[i], g_ctx.ev[i + 1]));
+        total_ms += ms;
+    }
     if (kernel_ms) *kernel_ms = total_ms;
     return TSTA_OK;
 }
