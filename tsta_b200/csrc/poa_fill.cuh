@@ -95,6 +95,7 @@ struct PoaSmem {
     uint16_t tr[kPoaTrRing][32 * kPoaC];     // trace ring
     int2 bring[kPoaBndRing];                 // left boundary keys (H(r, j0-1)*256, Fg(r, j0)*256 + 64) by row
     uint4 desc[kPoaDescRing];                // row descriptors
+    int kconst[8];                           // scoring constants, read back once (see the kernel)
 };
 
 // boundary element: low word = key of H (H*256); high word: bits 0-15 Fg-H, bits 17-31 epoch.
@@ -133,7 +134,8 @@ __device__ __forceinline__ void sts_s4(uint32_t addr, int x, int y, int z, int w
 template <int C, bool QUIRKS>
 __device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], const uint8_t (&rc)[C], const bool (&isL)[C],
                                         const bool (&isLm1)[C], const int b, const int MS, const int XS, const int ES,
-                                        const int OES, const int Fadj, int& Fk, int& Hleft, int (&ko)[2 * C], uint32_t (&tw)[C / 2])
+                                        const int ES64, const int ES128, const int OES, const int Fadj, int& Fk, int& Hleft,
+                                        int (&ko)[2 * C], uint32_t (&tw)[C / 2])
 {
     uint32_t lo8[C], hi8[C];
 #pragma unroll
@@ -151,10 +153,10 @@ __device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], 
         const int H256 = Hk & ~255;
         const int t = H256 + OES;                                     // (H+O+E)*256 + 64: Fg / Eout opened from here
         const int kem = ke[c] & ~255;
-        const int WE = __viaddmax_s32(kem, ES + 128, t);              // low byte 128 iff be+E >= H+O+E, else 64
-        int WF = __viaddmax_s32(Fk, ES + 64, t);                      // low byte 128 iff Fg+E >= H+O+E, else 64
+        const int WE = __viaddmax_s32(kem, ES128, t);              // low byte 128 iff be+E >= H+O+E, else 64
+        int WF = __viaddmax_s32(Fk, ES64, t);                      // low byte 128 iff Fg+E >= H+O+E, else 64
         ko[2 * c] = H256;
-        ko[2 * c + 1] = __viaddmax_s32(kem, ES + 64, t);              // Eout*256 + 64
+        ko[2 * c + 1] = __viaddmax_s32(kem, ES64, t);              // Eout*256 + 64
         const int Fn = __viaddmax_s32(Fk, ES, t);                     // Fg(c+1)*256 + 64
         if (QUIRKS && isLm1[c] && Fadj != 0) {
             // the next column re-bases F: its |fsource| == 2 test sees the re-based value (c-t-simd.c:228-233)
@@ -184,7 +186,16 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 
     const int E = a.E, O = a.O, OE = a.O + a.E, M = a.M, X = a.X;
     const int R = a.nrows, len = a.len, L = a.L;
-    const int MS = 256 * M, XS = 256 * X, ES = 256 * E, OES = 256 * OE + 64;
+    // Scoring constants go through shared memory once: values the compiler can trace back to the
+    // kernel parameters are re-derived inside the step (an LDC from the parameter bank plus a shift,
+    // with their latency on the row's dependency chain) instead of being kept in registers.
+    if (lane == 0) {
+        sm.kconst[0] = 256 * M; sm.kconst[1] = 256 * X; sm.kconst[2] = 256 * E; sm.kconst[3] = 256 * OE + 64;
+        sm.kconst[4] = 256 * E + 64; sm.kconst[5] = 256 * E + 128;
+    }
+    __syncwarp();
+    const volatile int* kc = sm.kconst;
+    const int MS = kc[0], XS = kc[1], ES = kc[2], OES = kc[3], ES64 = kc[4], ES128 = kc[5];
     const int j0 = (band * 32 + lane) * C;
     uint8_t rc[C];                       // read bytes of this lane's columns (0 = pad: matches nothing)
     bool isL[C], isLm1[C];               // column == L / L-1 (the late-head quirk re-bases F at column L)
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 int ko[2 * C];
                 uint32_t tw[C / 2];
                 int Hl = Hleft_in;
-                poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, OES, 0, Fk, Hl, ko, tw);
+                poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, ES64, ES128, OES, 0, Fk, Hl, ko, tw);
                 Hout = Hl; Fout = Fk;
                 const uint32_t own = my_hist + ((uint32_t)r & (kPoaHist - 1)) * kSlotBytes;
                 sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
@@ -442,9 +453,9 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 // the two quirks (late heads re-base F at column L, 'N' columns copy H) touch a handful of
                 // cells of a whole job: they get their own copy of the row code, the common one is free of them
                 if (hasN || (hasL && (flags & kPoaLate)))
-                    poa_row<C, true>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, OES, (flags & kPoaLate) ? 256 * O : 0, Fk, Hleft, ko, tw);
+                    poa_row<C, true>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, ES64, ES128, OES, (flags & kPoaLate) ? 256 * O : 0, Fk, Hleft, ko, tw);
                 else
-                    poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, OES, 0, Fk, Hleft, ko, tw);
+                    poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, ES64, ES128, OES, 0, Fk, Hleft, ko, tw);
                 Hout = Hleft; Fout = Fk;
                 // history ring (own columns + the band's left edge), HBM spill for far successors, trace ring
                 {
