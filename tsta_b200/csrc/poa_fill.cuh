@@ -47,7 +47,7 @@ constexpr int kPoaSlotNone = 32;    // extra history slots: "no predecessor" (ke
 constexpr int kPoaSlotHead = 33;    // the virtual row above a head node,
 constexpr int kPoaSlotLate = 34;    // and its late-head variant (quirk Q1)
 constexpr int kPoaSlots = 35;
-constexpr int kPoaFast = 4;         // predecessors the unrolled fast path handles
+constexpr int kPoaFast = 8;         // predecessors the unrolled fast path handles
 constexpr int kPoaChunk = 16;       // rows per staging chunk
 constexpr int kPoaBndRing = 64;     // boundary ring (rows)
 constexpr int kPoaTrRing = 64;      // trace ring (rows)
@@ -59,12 +59,13 @@ constexpr int kPoaSlotBytes = 33 * kPoaC * 8 + 16;   // 1072
 // ahead of the wavefront, so that the inner loop never waits for a dependent global load:
 //   x: base | in-degree << 8 | flags << 16
 //   y: history slot of predecessor 0..3 (one byte each; kPoaSlotNone when absent, the
-//      virtual-row slots for heads) -- the fast path needs nothing else
-//   z: first CSR edge of the row (slow path)
+//      virtual-row slots for heads)
+//   z: history slot of predecessor 4..7 -- the fast path needs nothing else; rows flagged kPoaSlow
+//      carry the first CSR edge of the row here instead (generic loop)
 //   w: for rows flagged kPoaKeep: their row in the HBM spill
 constexpr unsigned kPoaHead = 1u;        // in == 0
 constexpr unsigned kPoaKeep = 2u;        // some successor is further away than the history ring: also store the keys in HBM
-constexpr unsigned kPoaSlow = 4u;        // more than four predecessors, or one further back than the ring: generic loop
+constexpr unsigned kPoaSlow = 4u;        // more than eight predecessors, or one further back than the ring: generic loop
 constexpr unsigned kPoaLate = 8u;        // head with row index >= L (quirk Q1)
 
 struct PoaFillArgs {
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
             // MSA graph have one, 19 % two, 3 % three: the fourth round of the reduction is skipped
             // warp-wide whenever no lane needs it)
             const int npre_l = active ? (int)((dsc.x >> 8) & 0xffu) : 0;
-            const bool any3 = __any_sync(kFullMask, npre_l >= 3), any4 = __any_sync(kFullMask, npre_l >= 4);
+            const int maxnp = __reduce_max_sync(kFullMask, npre_l);   // warp-uniform: rounds beyond it are skipped
             // PLAIN step: every lane active, at most four near predecessors, no spill, no quirk -- the
             // whole step is one straight-line block (selects and predicated stores instead of branches)
             const bool plain = active && !(dsc.x & unplain) && !hasN;
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 }
 #pragma unroll
                 for (int j = 1; j < kPoaFast; j++) {
-                    if (j == 3 && !any4) continue;
-                    const uint32_t slot = (dsc.y >> (8 * j)) & 0xffu;
+                    if (j >= 3 && j >= maxnp) break;
+                    const uint32_t slot = ((j < 4 ? dsc.y : dsc.z) >> (8 * (j & 3))) & 0xffu;
                     const uint32_t A = slot == kPoaSlotNone ? none_addr : my_hist + slot * kSlotBytes;
                     const int Hd0 = lds_s32(A + 24);
                     const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     }
 #pragma unroll
                     for (int j = 1; j < kPoaFast; j++) {
-                        if ((j == 2 && !any3) || (j == 3 && !any4)) continue;
-                        const uint32_t slot = (dsc.y >> (8 * j)) & 0xffu;
+                        if (j >= 2 && j >= maxnp) break;
+                        const uint32_t slot = ((j < 4 ? dsc.y : dsc.z) >> (8 * (j & 3))) & 0xffu;
                         const uint32_t A = slot == kPoaSlotNone ? none_addr : my_hist + slot * kSlotBytes;
                         const int Hd0 = lds_s32(A + 24);
                         const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);

@@ -76,7 +76,7 @@ void tsta_poa_destroy(tsta_poa* p)
         fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s\n",
                 p->t_desc, p->t_alloc, p->t_run);
     if (p && getenv("TSTA_POA_TIMING"))
-        fprintf(stderr, "tsta_poa rows %lld: in-degree>3 %lld, with a far predecessor %lld, spilled %lld; in-degree histogram 1:%lld 2:%lld 3:%lld 4:%lld 5:%lld 6:%lld 7+:%lld\n",
+        fprintf(stderr, "tsta_poa rows %lld: in-degree>8 %lld, with a far predecessor %lld, spilled %lld; in-degree histogram 1:%lld 2:%lld 3:%lld 4:%lld 5:%lld 6:%lld 7+:%lld\n",
                 p->n_rows, p->n_wide, p->n_far, p->n_keep, p->n_deg[1], p->n_deg[2], p->n_deg[3], p->n_deg[4], p->n_deg[5], p->n_deg[6], p->n_deg[7]);
     poa_free(p);
 }
@@ -106,8 +106,9 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     p->h_desc.assign((size_t)nrows, make_uint4(0, 0, 0, 0));
     for (int r = 0; r < nrows; r++) {
         const int e0 = row_ptr[r], np = row_ptr[r + 1] - e0;
-        unsigned flags = 0, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone};
-        static_assert(kPoaFast == 4, "descriptor word y holds four slot bytes");
+        unsigned flags = 0, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone,
+                                              kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone};
+        static_assert(kPoaFast == 8, "descriptor words y and z hold eight slot bytes");
         if (pred_row[e0] < 0) {
             flags |= kPoaHead;
             if (L > 0 && r >= L) flags |= kPoaLate;                 // quirk Q1
@@ -134,7 +135,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         uint4& q = p->h_desc[(size_t)r];
         q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16);
         q.y = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
-        q.z = (unsigned)e0;
+        q.z = (flags & kPoaSlow) ? (unsigned)e0 : (slot[4] | (slot[5] << 8) | (slot[6] << 16) | (slot[7] << 24));
     }
     // rows with a successor further away than the history ring get a row of the HBM spill
     size_t nkeep = 0;
