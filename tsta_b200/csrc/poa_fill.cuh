@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
             // warp-wide whenever no lane needs it)
             const int npre_l = active ? (int)((dsc.x >> 8) & 0xffu) : 0;
             const int maxnp = __reduce_max_sync(kFullMask, npre_l);   // warp-uniform: rounds beyond it are skipped
-            // PLAIN step: every lane active, at most four near predecessors, no spill, no quirk -- the
+            // PLAIN step: every lane active, at most eight near predecessors, no spill, no quirk -- the
             // whole step is one straight-line block (selects and predicated stores instead of branches)
             const bool plain = active && !(dsc.x & unplain) && !hasN;
             if (__all_sync(kFullMask, plain)) {
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
 
                 int kd[C], ke[C];
                 if (!(flags & kPoaSlow)) {
-                    // ---- fast path: up to four predecessors, all inside the history ring -----------
+                    // ---- fast path: up to eight predecessors, all inside the history ring ----------
                     {   // predecessor 0: every row has one (heads: the virtual row's slot)
                         const uint32_t A = my_hist + (dsc.y & 0xffu) * kSlotBytes;
                         const int Hd0 = lds_s32(A + 24);
