@@ -158,7 +158,7 @@ int tsta_oracle_psa(const char* s0, int64_t n, const char* s1, int64_t m,
 {
     uint8_t* nib = NULL;
     if (want_trace || dirs_out) {
-        nib = dirs_out ? dirs_out : (uint8_t*)malloc((size_t)n * m ? (size_t)n * m : 1);
+        nib = dirs_out ? dirs_out : (uint8_t*)malloc((n > 0 && m > 0) ? (size_t)n * (size_t)m : 1);
         if (!nib) return -1;
     }
     psa_fill(s0, n, s1, m, M, X, E, O, nib, NULL, lastrow, res);
