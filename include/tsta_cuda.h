@@ -70,6 +70,10 @@ typedef struct tsta_psa_result {
  * want_trace = 0 behaves like TSTA_psa_notrace, 1 like TSTA_psa. */
 int  tsta_psa_align(const tsta_params* p, const char* s0, int64_t n, const char* s1, int64_t m,
                     int want_trace, tsta_psa_result* out);
+/* tsta_psa_align keeps one plan per (calling thread, trace mode) so that repeated calls reuse the
+ * device buffers (a traced 100 kbp pair keeps ~7 GB of directions).  They are freed when the
+ * thread exits, or right away by this call (calling thread's plans only). */
+void tsta_psa_release_cache(void);
 void tsta_psa_result_free(tsta_psa_result* r);
 
 /* Plan API: device-resident state that can be run repeatedly (what bench.py times).
@@ -95,6 +99,10 @@ int  tsta_psa_plan_info(tsta_psa_plan* plan, int* launches, int* cols_per_lane, 
 /* 1 when the last upload selected the packed int16x2 kernels (two cells per register; small
  * alphabets and score ranges, csrc/psa_fill16.cuh), 0 for the int32 kernels. */
 int  tsta_psa_plan_packed(tsta_psa_plan* plan);
+/* diagnostics: with TSTA_PSA_TIMELINE=1 in the environment every band of the last run left 8 globaltimer
+ * stamps (ns): entry, first boundary rows in, start of chunks 1..5, end; then stale polls, cycles spent
+ * importing the left boundary, number of imports.  out = [bands][16]. */
+int  tsta_psa_plan_timeline(tsta_psa_plan* plan, unsigned long long* out);
 void tsta_psa_plan_destroy(tsta_psa_plan* plan);
 
 /* One long pair spread over several GPUs as COLUMN SLICES (score-only): GPU g

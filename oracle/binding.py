@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         _LIB.tsta_oracle_psa_ref3.argtypes = [
             C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
             C.POINTER(_Result), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        _LIB.tsta_oracle_psa_scores.restype = C.c_int
+        _LIB.tsta_oracle_psa_scores.argtypes = [
+            C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+            C.POINTER(_Result), C.c_void_p]
         _LIB.tsta_oracle_free.argtypes = [C.c_void_p]
     return _LIB
 
@@ -69,6 +73,17 @@ class PsaResult:
 def order_pair(x: bytes, y: bytes):
     """Reference psa/psa.c:194-199: the longer read becomes s0 (columns); ties keep order."""
     return (y, x) if len(y) > len(x) else (x, y)
+
+
+def psa_scores(x: bytes, y: bytes, M=2, X=-5, E=-2, O=-4) -> PsaResult:
+    """Score-only oracle for the full BASELINE sizes (no direction bookkeeping): maxsorce, corner,
+    the whole last row."""
+    s0, s1 = order_pair(x, y)
+    n, m = len(s0), len(s1)
+    r = _Result()
+    lastrow = np.zeros(n, dtype=np.int32)
+    lib().tsta_oracle_psa_scores(s0, n, s1, m, M, X, E, O, C.byref(r), lastrow.ctypes.data)
+    return PsaResult(r.maxsorce, r.corner, r.lastrow_fnv, lastrow=lastrow)
 
 
 def psa(x: bytes, y: bytes, M=2, X=-5, E=-2, O=-4, trace=True, want_lastrow=False,

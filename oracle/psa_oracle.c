@@ -130,6 +130,67 @@ static void psa_fill(const char* s0, int64_t n, const char* s1, int64_t m,
     free(Hrow); free(Erow); free(fbrow); free(ebprev);
 }
 
+/*
+ * Score-only form of psa_fill(): the same recurrences (psa/psa.c:219-363) without the direction
+ * bookkeeping, so that the full BASELINE sizes (1e10 cells) finish in well under a minute.
+ * tests/test_oracle_psa.py requires it to agree with psa_fill() on maxsorce, corner and the
+ * whole last row.
+ */
+static void psa_fill_scores(const char* s0, int64_t n, const char* s1, int64_t m,
+                            int M, int X, int E, int O, int32_t* lastrow, tsta_oracle_result* res)
+{
+    const int OE = O + E;
+    int32_t* Hrow = (int32_t*)malloc((size_t)(n + 1) * sizeof(int32_t)); /* H(i-1, j), index j+1 */
+    int32_t* Erow = (int32_t*)malloc((size_t)(n + 1) * sizeof(int32_t)); /* Eg(i-1, j)           */
+    int ms = MS_SEED;
+    Hrow[0] = 0;
+    for (int64_t j = 0; j < n; j++) {
+        Hrow[j + 1] = O + (int)(j + 1) * E;
+        Erow[j] = NEG_INF;
+    }
+    int32_t* T = (int32_t*)malloc((size_t)(n + 1) * sizeof(int32_t));    /* max(h, Eg) of the current row */
+    for (int64_t i = 0; i < m; i++) {
+        const char c1 = s1[i];
+        /* pass 1 (no dependency along the row): Eg and the diagonal candidate from row i-1 */
+        for (int64_t j = 0; j < n; j++) {
+            const int Eg = imax(Erow[j] + E, Hrow[j + 1] + OE);
+            const int h = Hrow[j] + (s0[j] == c1 ? M : X);
+            Erow[j] = Eg;
+            T[j] = imax(h, Eg);
+        }
+        /* pass 2: the horizontal gap chain */
+        /* Fg(i,j+1) = max(Fg(i,j)+E, H(i,j)+OE) with H = max(T, Fg) and O <= 0 is max(Fg(i,j)+E, T(j)+OE):
+         * two operations on the serial chain instead of five */
+        int Fg = O + (int)(i + 1) * E + OE;                      /* Fg(i,0) = H(i,-1)+O+E */
+        for (int64_t j = 0; j < n; j++) {
+            const int H = imax(T[j], Fg);
+            Fg = imax(Fg + E, T[j] + OE);
+            ms = imax(ms, H);
+            Hrow[j + 1] = H;
+        }
+        Hrow[0] = O + (int)(i + 1) * E;
+    }
+    free(T);
+    res->maxsorce = ms;
+    res->corner = (n > 0 && m > 0) ? Hrow[n] : 0;
+    uint64_t h = 1469598103934665603ULL;
+    for (int64_t j = 0; j < n; j++) {
+        h = fnv1a_i32(h, Hrow[j + 1]);
+        if (lastrow) lastrow[j] = Hrow[j + 1];
+    }
+    res->lastrow_fnv = h;
+    res->alen = 0;
+    free(Hrow); free(Erow);
+}
+
+/* Score-only entry point (maxsorce, corner, last row); see psa_fill_scores(). */
+int tsta_oracle_psa_scores(const char* s0, int64_t n, const char* s1, int64_t m,
+                           int M, int X, int E, int O, tsta_oracle_result* res, int32_t* lastrow)
+{
+    psa_fill_scores(s0, n, s1, m, M, X, E, O, lastrow, res);
+    return 0;
+}
+
 /* Turn a reversed op list (0 left, 1 diag, 2 up) into the two aligned strings. */
 static void emit_strings(const char* s0, int64_t n, const char* s1, int64_t m,
                          const uint8_t* ops, int64_t nops, char** a_out, char** b_out)

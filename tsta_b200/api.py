@@ -18,7 +18,8 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "_build" / "libtsta_cuda.so"
+import os as _os
+LIB_PATH = Path(_os.environ["TSTA_LIB"]) if _os.environ.get("TSTA_LIB") else _PKG / "_build" / "libtsta_cuda.so"   # (TSTA_LIB: experiment builds)
 _lib = None
 
 

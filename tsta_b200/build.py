@@ -55,6 +55,17 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defs) -> Path:
+    """Experiment builds (tools/): the same library with -D overrides, as _build/libtsta_cuda_<name>.so;
+    select it at run time with TSTA_LIB=<path>."""
+    OUT.mkdir(exist_ok=True)
+    out = OUT / f"libtsta_cuda_{name}.so"
+    srcs = sorted(CSRC.glob("*.cu"))
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-I", str(ROOT / "include"), "-o", str(out)] + [str(s) for s in srcs]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build_host(force: bool = False) -> list:
     """C drivers (the reference's three executables) linked against the C ABI."""
     OUT.mkdir(exist_ok=True)

@@ -8,6 +8,8 @@
 #include <string.h>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects its library
+
 #include "../../include/tsta_cuda.h"
 
 namespace tsta {
@@ -40,6 +42,15 @@ inline int set_error(int code, const char* fmt, ...)
     } while (0)
 
 int ensure_device();  // TSTA_OK when a CUDA device is usable, TSTA_ENODEV otherwise
+
+// NVTX range over the ENQUEUE of a phase (fill / traceback / graph DP): Nsight timelines then name the
+// kernels of one alignment; the reference has no tracing at all.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Growable device buffer (never shrinks); freed by the owner's destructor.
 struct DevBuf {

@@ -80,10 +80,13 @@ __device__ __forceinline__ int2 bnd_unpack(unsigned long long v, bool trace)
     const int d = (int)(short)(unsigned short)(v >> 32);
     return make_int2(H, (trace ? (H & ~1) : H) + d);
 }
+#ifndef TSTA_BND_LD_SCOPE
+#define TSTA_BND_LD_SCOPE "sys"     // the producer may be a peer GPU (column slices)
+#endif
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");   // sys: the producer may be a peer GPU
+    asm volatile("ld.relaxed." TSTA_BND_LD_SCOPE ".global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
@@ -137,6 +140,9 @@ struct PsaBand {
     int col_off = 0;
     bool has_left = false;  // band 0 gets its left boundary from bnd_in (the neighbour GPU's stores)
     bool has_right = false; // the last band exports its right boundary to bnd_out (peer memory)
+    int* abort_flag = nullptr;          // see PsaPairArgs
+    unsigned long long timeout_ns = 0;
+    unsigned long long* timeline = nullptr;
 };
 
 // Fills the 256-entry byte -> substitution-table map (PRMT mode).
@@ -417,6 +423,11 @@ struct PsaPairArgs {
     int col_off;
     const unsigned long long* inbox;
     unsigned long long* outbox;
+    // hand-off watchdog (packed kernels): a band that polls its left neighbour longer than timeout_ns
+    // raises *abort_flag and stops waiting (results are then garbage and the host reports TSTA_ECUDA)
+    int* abort_flag;
+    unsigned long long timeout_ns;
+    unsigned long long* timeline;   // optional (TSTA_PSA_TIMELINE=1): 8 globaltimer stamps per band, see tools/timeline.py
 };
 
 template <int C, bool TRACE, bool PRMT, int CH>

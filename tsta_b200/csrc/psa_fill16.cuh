@@ -39,6 +39,35 @@
 //   * the 4-bit codes of a lane's C columns are assembled with IMADs (FMA pipe) and leave through
 //     a shared-memory ring indexed by STEP (one store per step, no address arithmetic); the flush
 //     that writes whole rows to HBM with 128-bit stores does the lane -> row transposition.
+//     (TM == 1: batches of pairs.)
+//
+// Traceback variant of ONE LONG PAIR (TM == 2, "skewed" direction layout): the direction words
+// never meet shared memory.  Every step each lane stores its word straight to HBM at
+// [band][step][lane] -- 128 contiguous bytes per warp and step -- so row r of virtual lane v sits
+// in the word of step r + v; the traceback kernel undoes the skew while it stages the few
+// windows the path actually crosses (psa_trace.cuh), which moves the lane -> row transposition
+// from 1e10 cells to ~1e8.  The cell code holds what the cell itself knows:
+//     bits 0-1  back tag (3 diagonal, 2 left, 1 up)
+//     bit 2     wf: a walk that ENTERS this cell by a left move keeps moving left
+//               (= cF of the cell to the right)
+//     bit 3     we: a walk that enters this cell by an up move keeps moving up (= cE of the cell below)
+// so nothing is carried from row to row or lane to lane for the codes, and F takes the textbook
+// form max(Fg+E, H+O+E) from the tagged H:  per packed column
+//     hs3 = D + sub            Ec1 = (Et & ~3) | 1        Fc2 = Fin | 2
+//     Hp  = max3(hs3, Fc2, Ec1)                            VIMNMX3.S16x2, winner's tag = back
+//     Hn  = Hp & ~3            T2 = Hn + 4(O+E)+2
+//     F'  = max(Fc2 + 4E-2, T2)    En = max(Ec1 + 4E-1, T2)
+//     WE  = max(Et + 4E+1, T2)     WF = max(Fin + 4E+1, T2)      bit 0 = we / wf
+// = 14.5 ALU-pipe instructions against 17.5 of the TM == 1 form.
+//
+// Ramp-in without masks (CK == 2): the rows above row 0 that the skewed lanes would "work on"
+// during the first 63 steps are made FIXED POINTS of the recurrence -- their substitution table
+// holds -128 for every symbol, every lane starts with the right-edge values of row -1 in its
+// hand-off registers, and then H(r, j) = H(-1, j), Eg = H(-1, j)+O+E (opened), Fg(r, j+1) = H(-1, j)+E
+// reproduce themselves for every r < 0 (O <= 0, E <= 0).  Only the running maximum is masked.  The
+// time a band needs until its first boundary rows are out is what every later band waits for
+// (measured: the masked start-up cost 2.3 x a steady step and set 80 of the 180 steps of
+// effective lag per band, profiles/r02_calibration.md).
 #pragma once
 #include "psa_fill.cuh"
 
@@ -73,7 +102,7 @@ __device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b) { r
 __device__ __forceinline__ void st_relaxed_pair_if(unsigned long long* p, uint32_t lo, uint32_t hi, bool doit)
 {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.b64 v, {%1, %2};\n\t"
-                 "@p st.relaxed.sys.global.b64 [%0], v;\n\t}"
+                 "@p st.relaxed." TSTA_BND_LD_SCOPE ".global.b64 [%0], v;\n\t}"
                  ::"l"(p), "r"(lo), "r"(hi), "r"((unsigned)doit) : "memory");
 }
 template <class SM>
@@ -85,11 +114,11 @@ __device__ __forceinline__ void ring16_put(SM& sm, int row, uint2 v)
 }
 
 // Per-warp shared-memory workspace of the packed sweep.
-template <int C, bool TRACE>
+template <int C, bool RING>
 struct __align__(16) PsaWarpSmem16 {
-    // TRACE: [step & 127][lane] direction words of one step: C <= 4: one word (low 16 bits = the
-    // low virtual lane's C codes, high 16 bits = the high one's); C == 8: two words (low, high)
-    uint32_t dirw[TRACE ? kDirSteps * 32 * (C == 8 ? 2 : 1) : 4];
+    // RING (TM == 1): [step & 127][lane] direction words of one step: C <= 4: one word (low 16 bits =
+    // the low virtual lane's C codes, high 16 bits = the high one's); C == 8: two words (low, high)
+    uint32_t dirw[RING ? kDirSteps * 32 * (C == 8 ? 2 : 1) : 4];
     // [r & 127] = (table of row r, table of row r-32), 4 x int8 each; the first 32 entries are
     // mirrored behind the ring so that "entry of row r0 + s" is ring[(r0 & 127) + s] with a
     // compile-time s (no wrap inside a chunk)
@@ -142,28 +171,45 @@ __host__ __device__ inline bool psa16_fits(int M, int X, int E, int O, int S, in
 
 // Scoring constants of a sweep, packed in both halves.
 struct PsaConst16 {
-    uint32_t E2;      // score-only: E;    TRACE: 4E-1
-    uint32_t OE2;     // score-only: O+E;  TRACE: 4(O+E)+2 ("opened")
-    uint32_t Kf2;     // TRACE: max(4E, 4(O+E)+2) - 2
-    uint32_t E1;      // TRACE: 4E+1
+    uint32_t E2;      // score-only: E;    traced: 4E-1
+    uint32_t OE2;     // score-only: O+E;  traced: 4(O+E)+2 ("opened")
+    uint32_t Kf2;     // TM 1: max(4E, 4(O+E)+2) - 2;  TM 2: 4E-2
+    uint32_t E1;      // traced: 4E+1
 };
 constexpr uint32_t kM1 = 0x00010001u, kM2 = 0x00020002u, kM3 = 0x00030003u;
+constexpr uint32_t kFakeTab = 0x80808080u;   // substitution table of the rows above row 0: -128 for every symbol
+
+// TM (trace mode): 0 score-only, 1 traced through the shared-memory step ring (batches), 2 traced with
+// the skewed direct-to-HBM layout (one long pair).
+// CK: 0 steady state (no predication), 1 ramp chunks with full masking (lanes outside [0, m) keep
+// their state), 2 ramp-IN chunks of the fixed-point start-up (only the running maximum and the
+// boundary export are masked).
+__device__ __forceinline__ void stg_cs_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_cs_u2(uint32_t* p, uint32_t x, uint32_t y)
+{
+    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
 
 // One wavefront step: row t-k of the low virtual lane and row t-k-32 of the high one.
 //   in_addr   sm.in of this chunk (entry s = the band's left boundary of row t)
 //   ring_next ring entry of this lane's NEXT row at s = 0
 //   bnd_row   boundary element of the row virtual lane 63 works on at s = 0
-//   dir_addr  TRACE: this lane's direction word of step s = 0 in the step ring
+//   dir_addr  TM 1: this lane's direction word of step s = 0 in the step ring
+//   dir_g     TM 2: this lane's direction word of step s = 0 in HBM ([band][step][lane])
 //   DUAL      the two halves are two independent PAIRS (short reads): no low -> high hand-off in lane 0,
 //             both halves work on row t-k, the boundary of both comes from sm.in2, m_hi = rows of pair B
-template <int C, bool TRACE, bool CHECK, bool DUAL = false>
+template <int C, int TM, int CK, bool DUAL = false>
 __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const int s, const int m, const int lane,
                                            const PsaConst16& k, const uint32_t selH, const uint32_t selF,
                                            const int src_lane, const uint32_t in_addr, const uint32_t ring_next,
                                            unsigned long long* bnd_row, const bool store_right,
                                            const uint32_t outHF, const unsigned epoch, const uint32_t dir_addr,
-                                           const int m_hi = 0)
+                                           uint32_t* dir_g = nullptr, const int m_hi = 0)
 {
+    constexpr bool CHECK = CK == 1;
     const uint32_t rH = __shfl_sync(kFullMask, L.Hout, src_lane);
     const uint32_t rF = __shfl_sync(kFullMask, L.Fout, src_lane);
     uint32_t in, inF;                                             // broadcast: the band's left boundary
@@ -173,15 +219,16 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
     L.Tnext = lds_u2(ring_next + s * 8);
 
     uint32_t mask = 0xffffffffu;
-    if (CHECK) {
-        const bool lo = (unsigned)(t - lane) < (unsigned)m;
-        const bool hi = DUAL ? (unsigned)(t - lane) < (unsigned)m_hi : (unsigned)(t - lane - 32) < (unsigned)m;
+    if (CK != 0) {
+        const bool lo = CK == 2 ? t >= lane : (unsigned)(t - lane) < (unsigned)m;
+        const bool hi = DUAL ? (unsigned)(t - lane) < (unsigned)m_hi
+                             : (CK == 2 ? t >= lane + 32 : (unsigned)(t - lane - 32) < (unsigned)m);
         mask = (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
     }
     uint32_t Hn[C];
     uint32_t Hin, F;
 
-    if constexpr (!TRACE) {
+    if constexpr (TM == 0) {
         // ---- F-independent pre-work ---------------------------------------------------------
         uint32_t hE[C];
 #pragma unroll
@@ -201,7 +248,7 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
             const uint32_t En = vaddmax2(L.Et[c], k.E2, Hn[c]);
             L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
         }
-    } else {
+    } else if constexpr (TM == 1) {
         // ---- F-independent pre-work ---------------------------------------------------------
         // tags in the two low bits: 4h+3 (the table entries carry the +3), 4Fg+2, 4Eg+1
         uint32_t hEt[C], Ec1[C], g[C];
@@ -244,23 +291,54 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
         else sts_u32(dir_addr + s * 128, acc[0]);
         // the cF flag of the next lane's first column rides in bit 0 of the H hand-off
         L.Hout = f1;                                              // merged below
+    } else {
+        // ---- TM 2: everything a cell's code needs is known in the cell itself -----------------
+        uint32_t hs3[C], Ec1[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            hs3[c] = vadd2(c == 0 ? L.diag : L.Hup[c - 1], prmtu(T.x, T.y, L.sel[c]));   // 4h+3
+            Ec1[c] = (L.Et[c] & ~kM3) | kM1;                      // 4Eg+1
+        }
+        Hin = prmtu(rH, in, selH);                                // multiples of four
+        F = prmtu(rF, inF, selF);                                 // flagged Fg state
+        uint32_t acc[(C + 3) / 4];
+#pragma unroll
+        for (int q = 0; q < (C + 3) / 4; q++) acc[q] = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t Fin = F;
+            const uint32_t Fc2 = Fin | kM2;                       // 4Fg+2
+            const uint32_t Hp = vmax3_2(hs3[c], Fc2, Ec1[c]);     // winner tagged 3 / 2 / 1: psa.c:294-298
+            Hn[c] = Hp & ~kM3;
+            const uint32_t T2 = vadd2(Hn[c], k.OE2);              // 4(H+O+E)+2
+            F = vaddmax2(Fc2, k.Kf2, T2);                         // max(4(Fg+E), 4(H+O+E)+2)
+            const uint32_t En = vaddmax2(Ec1[c], k.E2, T2);       // max(4(Eg+E), 4(H+O+E)+2)
+            const uint32_t WE = vaddmax2(L.Et[c], k.E1, T2);      // bit 0: we of this cell
+            const uint32_t WF = vaddmax2(Fin, k.E1, T2);          // bit 0: wf of this cell
+            const uint32_t x = (Hp & kM3) + (WF & kM1) * 4u + (WE & kM1) * 8u;
+            acc[c / 4] += x << (4 * (c & 3));
+            L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
+        }
+        // (halves on rows outside [0, m) store garbage nobody reads)
+        if (C > 4) stg_cs_u2(dir_g + s * 64, prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x5410u), prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x7632u));
+        else stg_cs_u32(dir_g + s * 32, acc[0]);
     }
     uint32_t msn = L.ms;
 #pragma unroll
     for (int c = 0; c + 1 < C; c += 2) msn = vmax3_2(msn, Hn[c], Hn[c + 1]);
     if (C & 1) msn = __vmaxs2(msn, Hn[C - 1]);
-    const uint32_t Ho = TRACE ? (Hn[C - 1] | L.Hout) : Hn[C - 1];
+    const uint32_t Ho = TM == 1 ? (Hn[C - 1] | L.Hout) : Hn[C - 1];
     if (CHECK) {
 #pragma unroll
         for (int c = 0; c < C; c++) L.Hup[c] = bsel(mask, Hn[c], L.Hup[c]);
         L.ms = bsel(mask, msn, L.ms);
         L.diag = bsel(mask, Hin, L.diag);
-        L.Hout = bsel(mask, Ho, TRACE ? 0u : L.Hout);
+        L.Hout = bsel(mask, Ho, TM == 1 ? 0u : L.Hout);
         L.Fout = bsel(mask, F, L.Fout);
     } else {
 #pragma unroll
         for (int c = 0; c < C; c++) L.Hup[c] = Hn[c];
-        L.ms = msn;
+        L.ms = CK == 2 ? bsel(mask, msn, L.ms) : msn;
         L.diag = Hin;
         L.Hout = Ho;
         L.Fout = F;
@@ -268,7 +346,7 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
     // right edge of the band = high halves of lane 31, row t-63: (H | Fg << 16) absolute modulo 2^16
     if (!DUAL) {
         const uint32_t e = vadd2(prmtu(L.Hout, L.Fout, 0x7632u), outHF);
-        const bool doit = store_right && (!CHECK || (unsigned)(t - 63) < (unsigned)m);
+        const bool doit = store_right && (CK == 0 || (unsigned)(t - 63) < (unsigned)m);
         st_relaxed_pair_if(bnd_row + s, e, epoch, doit);
     }
 }
@@ -351,18 +429,37 @@ __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint
 }
 
 // One band (64*C columns) of one pair.  Returns the band's maximum H in absolute (scaled) units.
-template <int C, bool TRACE, bool PIPE, int CH>
+//   TM    0 score-only, 1 traced through the step ring (b.dirs row-major), 2 traced, skewed layout
+//         (b.dirs = this band's [step][lane] words)
+//   PIPE  one long pair: bands are separate warps, the left boundary arrives in tagged elements and is
+//         imported in groups of kImportGroup rows (short lag behind the producing band)
+#ifndef TSTA_IMPORT_GROUP
+#define TSTA_IMPORT_GROUP 32
+#endif
+#ifndef TSTA_SCORE_UNROLL
+#define TSTA_SCORE_UNROLL 32       // steps of the score-only steady-state loop that are unrolled (32 = the whole chunk)
+#endif
+#ifndef TSTA_FAST_RAMP
+#define TSTA_FAST_RAMP 1
+#endif
+constexpr int kImportGroup = TSTA_IMPORT_GROUP;
+template <int C, int TM, bool PIPE, int CH>
 __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScoring& sc, const uint32_t* tab4,
-                                                PsaWarpSmem16<C, TRACE>& sm, const int lane)
+                                                PsaWarpSmem16<C, TM == 1>& sm, const int lane)
 {
+    constexpr bool TRACE = TM != 0;
     constexpr int S = TRACE ? 4 : 1;
+    constexpr int G = kImportGroup < CH ? kImportGroup : CH;
     static_assert(CH == 16 || CH == 32, "chunk rows");
-    static_assert(!TRACE || C == 2 || C == 4 || C == 8, "traced strips pack to 8 / 16 / 32 bits per virtual lane");
+    static_assert(TM != 1 || C == 2 || C == 4 || C == 8, "ring-traced strips pack to 8 / 16 / 32 bits per virtual lane");
+    static_assert(TM != 2 || C <= 8, "skewed direction words hold at most 8 columns per virtual lane");
+    static_assert(TM != 2 || PIPE, "the skewed layout belongs to the single-pair kernel");
     const int m = b.m;
     const int Es = S * sc.E, OEs = S * (sc.O + sc.E) + (TRACE ? 2 : 0);
     PsaConst16 k;
-    // TRACE folds the candidates' tags into the constants: Eg+1 extends by 4E-1, Fg+2 by Kf-2
-    k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.Kf2 = dup16(max(Es, OEs) - 2); k.E1 = dup16(Es + 1);
+    // traced: the candidates' tags are folded into the constants: Eg+1 extends by 4E-1, Fg+2 by Kf-2
+    k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.E1 = dup16(Es + 1);
+    k.Kf2 = dup16(TM == 2 ? Es - 2 : max(Es, OEs) - 2);
     const int shiftOE = TRACE ? 0 : OEs;                         // score-only: gap states are carried minus (O+E)
     const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, S);
     const int jlo = (b.band * 64 + lane) * C, jhi = jlo + 32 * C;
@@ -396,8 +493,16 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         L.diag = pack16(da - base - (jlo >= b.n ? padlow : 0), dh - base - (jhi >= b.n ? padlow : 0));
     }
     L.ms = kMin16x2;
-    L.Hout = 0;
-    L.Fout = 0;
+    {
+        // right edge of row -1 as this lane would hand it on: H(-1, last column) and the F state of the
+        // column after it.  The mask-free start-up (CK == 2) relies on it; masked start-ups ignore it.
+        const int la = goff + jlo + C - 1, lh = goff + jhi + C - 1;              // last columns (global)
+        const int Ha = S * (sc.O + (la + 1) * sc.E), Hh = S * (sc.O + (lh + 1) * sc.E);
+        // F state: max(Fg + E, H + O + E) of row -1, where Fg(-1, j) = H(-1, j)
+        const int Fa = max(Ha + Es, Ha + OEs) - shiftOE, Fh = max(Hh + Es, Hh + OEs) - shiftOE;
+        L.Hout = pack16(Ha - base, Hh - base);
+        L.Fout = pack16(Fa - base, Fh - base);
+    }
     int ms32 = INT_MIN;
 
     const int nsteps = m + 63;                                   // virtual lane 63 finishes row m-1 at step m+62
@@ -409,23 +514,70 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in);
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
     const uint32_t dirw_addr = (uint32_t)__cvta_generic_to_shared(sm.dirw) + lane * (C == 8 ? 8 : 4);
+    uint32_t* const dir_lane = TM == 2 ? reinterpret_cast<uint32_t*>(b.dirs) + lane * (C > 4 ? 2 : 1) : nullptr;
     const uint32_t selH = lane == 0 ? 0x1054u : 0x3210u;         // lane 0: lo <- boundary H, hi <- lane 31's low half
     const uint32_t selF = lane == 0 ? 0x1076u : 0x3210u;
     const int src_lane = (lane + 31) & 31;
     const int mrows = m + 32;                                    // rows whose table entry is read (high halves lag by 32)
+    // mask-free start-up: single-pair bands without pad columns (the pad trick above lowers row -1,
+    // which the fixed-point rows would undo); the band that holds the pads is the last one, nobody waits for it
+    const bool fast_ramp = TSTA_FAST_RAMP && PIPE && (b.band + 1) * 64 * C <= b.n && m >= 64 + CH;
 
     // ---- prologue: row tables of chunk 0; prefetch for chunk 1 / boundary of chunk 0 -----------
     __syncwarp();
     const bool stager = lane < CH;
-    if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, 0u));   // rows < 32: no high row yet
+    // rows above row 0 (read by lanes whose first row is still to come): the fixed-point table
+    sm.rowring[kRing16 - 32 + lane] = make_uint2(kFakeTab, kFakeTab);
+    if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, kFakeTab));   // rows < 32: no high row yet
     uint32_t raw_next = (stager && CH + lane < m) ? b.s1[CH + lane] : 0xffffffffu;
+    // left boundary: PIPE imports it in groups of G rows (lanes 0..G-1 hold the group that is consumed
+    // next); sequential mode (batches) reads whole chunks of its own parked column
     unsigned long long bnd_next = 0;
-    if (import_left && stager && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
+    if (import_left && (PIPE ? lane < G : stager) && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
     __syncwarp();
-    L.Tnext = sm.rowring[0];
+    L.Tnext = sm.rowring[(0 - lane) & (kRing16 - 1)];            // table of this lane's row at step 0 (row -lane)
 
+    // PIPE: make rows [row0, row0 + G) of the left boundary available in sm.in[slot0 ..] and prefetch the next group
+    auto import_group = [&](const int row0, const int slot0, const int cur_base) {
+        const int row = row0 + lane;
+        const bool mine = lane < G && row < m;
+        unsigned spins = 0;
+        unsigned long long t_wait = 0;
+        const long long dbg_c0 = b.timeline ? clock64() : 0;
+        while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
+            __nanosleep(20);
+            if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
+            if ((++spins & 0xfffu) == 0 && b.abort_flag) {       // watchdog: never hang the GPU on a neighbour that does not come
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t_wait == 0) t_wait = now;
+                int stop = *reinterpret_cast<volatile int*>(b.abort_flag);
+                if (now - t_wait > b.timeout_ns) { stop = 1; if (lane == 0) atomicExch(b.abort_flag, 1); }
+                if (__any_sync(kFullMask, stop != 0)) break;
+            }
+        }
+        // absolute modulo 2^16 -> relative to this warp's base (score-only: Ft = Fg - (O+E))
+        if (mine) sm.in[slot0 + lane] = vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE));
+        __syncwarp();
+        if (lane < G && row + G < m) bnd_next = ld_relaxed_u64(b.bnd_in + row + G);
+        if (b.timeline && lane == 0) {   // diagnostics: polls that found stale rows, cycles spent importing, imports
+            b.timeline[b.band * 16 + 8] += spins;
+            b.timeline[b.band * 16 + 9] += (unsigned long long)(clock64() - dbg_c0);
+            b.timeline[b.band * 16 + 10] += 1;
+        }
+    };
+
+    auto stamp = [&](int slot) {
+        if (PIPE && b.timeline && lane == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            b.timeline[b.band * 16 + slot] = now;
+        }
+    };
+    stamp(0);
     for (int ch = 0; ch < nchunks; ch++) {
         const int t0 = ch * CH;
+        if (ch >= 1 && ch <= 5) stamp(1 + ch);                      // 2..6: start of chunks 1..5
         // ---- re-centre on lane 0's current row -------------------------------------------------
         {
             int delta = lo16(__shfl_sync(kFullMask, L.Et[0], 0));   // column j0 of the band is never a pad column
@@ -444,63 +596,84 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         {
             const int rown = t0 + CH + lane;                    // row of the next chunk
             if (stager && rown < mrows) {
-                const uint32_t hi_tab = rown >= 32 ? sm.rowring[(rown - 32) & (kRing16 - 1)].x : 0u;
+                const uint32_t hi_tab = rown >= 32 ? sm.rowring[(rown - 32) & (kRing16 - 1)].x : kFakeTab;
                 ring16_put(sm, rown, make_uint2(rown < m ? tab4[raw_next & 0xffu] : 0u, hi_tab));
             }
             const int rownn = rown + CH;
             raw_next = (stager && rownn < m) ? b.s1[rownn] : 0u;
             const int row = stager ? t0 + lane : m;
-            if (import_left) {
-                if (PIPE) {
-                    while (!__all_sync(kFullMask, row >= m || (unsigned)(bnd_next >> 32) == epoch)) {
-                        __nanosleep(20);
-                        if (row < m && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
-                    }
-                }
-                // absolute modulo 2^16 -> relative to this warp's base (score-only: Ft = Fg - (O+E))
+            if (import_left && PIPE) {
+                if (t0 < m) import_group(t0, 0, base);          // (also orders the ring stores above)
+                if (ch == 0) stamp(1);                          // the first rows of the left boundary have arrived
+            } else if (import_left) {
                 if (row < m) sm.in[lane] = vadd2((uint32_t)bnd_next, pack16(-base, -base - shiftOE));
+                const int rowp = row + CH;
+                if (stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
             } else if (row < m) {
                 const int hb = S * (sc.O + (row + 1) * sc.E) - base;   // H(i,-1); Fg(i,0) = H(i,-1)+O+E, opened
                 sm.in[lane] = pack16(hb, hb + OEs - shiftOE);
             }
-            const int rowp = row + CH;
-            if (import_left && stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
         }
         __syncwarp();
         const uint32_t outHF = pack16(base, base + shiftOE);      // relative (H, F state) -> absolute
         const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
         unsigned long long* bnd_row = b.bnd_out + (t0 - 63);
         const uint32_t dir_addr = dirw_addr + (t0 & (kDirSteps - 1)) * (C == 8 ? 256 : 128);
+        uint32_t* const dir_g = TM == 2 ? dir_lane + (long long)t0 * (C > 4 ? 64 : 32) : nullptr;
+        const bool groups = import_left && PIPE;
 
-        if (t0 >= 63 && t0 + CH - 1 < m) {
+        if (t0 + CH - 1 < m && (t0 >= 63 || fast_ramp)) {
             // score-only: the whole chunk is unrolled (every address becomes an immediate);
-            // the traced step is four times as long, so it is unrolled just enough to overlap
+            // the traced step is several times as long, so it is unrolled just enough to overlap
             // neighbouring steps without outgrowing the instruction cache
-            if constexpr (!TRACE) {
+            if (t0 >= 63) {
+                if constexpr (!TRACE && TSTA_SCORE_UNROLL >= CH) {
 #pragma unroll
-                for (int s = 0; s < CH; s++)
-                    psa_step16<C, TRACE, false>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                                bnd_row, store_right, outHF, epoch, dir_addr);
+                    for (int s = 0; s < CH; s++) {
+                        if (s > 0 && s % G == 0 && groups) import_group(t0 + s, s, base);
+                        psa_step16<C, TM, 0>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                             bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+                    }
+                } else {
+                    constexpr int U = G < 8 ? G : 8;
+#pragma unroll 1
+                    for (int s0 = 0; s0 < CH; s0 += U) {
+                        if (s0 > 0 && s0 % G == 0 && groups) import_group(t0 + s0, s0, base);
+#pragma unroll
+                        for (int q = 0; q < U; q++)
+                            psa_step16<C, TM, 0>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                 bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+                    }
+                }
             } else {
-#pragma unroll 2
-                for (int s = 0; s < CH; s++)
-                    psa_step16<C, TRACE, false>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                                bnd_row, store_right, outHF, epoch, dir_addr);
+                // mask-free start-up chunks (t0 < 63): lanes whose first row is still to come sit on fixed-point rows
+                constexpr int U = G < 8 ? G : 8;
+#pragma unroll 1
+                for (int s0 = 0; s0 < CH; s0 += U) {
+                    if (s0 > 0 && s0 % G == 0 && groups) import_group(t0 + s0, s0, base);
+#pragma unroll
+                    for (int q = 0; q < U; q++)
+                        psa_step16<C, TM, 2>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                             bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+                }
             }
         } else {
 #pragma unroll 1
-            for (int s = 0; s < CH; s++)
-                psa_step16<C, TRACE, true>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                           bnd_row, store_right, outHF, epoch, dir_addr);
+            for (int s = 0; s < CH; s++) {
+                if (s > 0 && s % G == 0 && groups && t0 + s < m) import_group(t0 + s, s, base);
+                psa_step16<C, TM, 1>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                     bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+            }
         }
         __syncwarp();
-        if (TRACE) {
+        if constexpr (TM == 1) {
             // rows every virtual lane has finished: [t0 - 63, t0 + CH - 63)
             psa_flush_dirs16<C>(sm.dirw, b, min(m, max(0, t0 - 63)), min(m, max(0, t0 + CH - 63)), lane);
             __syncwarp();
         }
     }
     ms32 = max(ms32, max(lo16(L.ms), hi16(L.ms)) + base);
+    stamp(7);
 
     if (b.lastrow) {
 #pragma unroll
@@ -615,19 +788,19 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
             if constexpr (!TRACE) {
 #pragma unroll
                 for (int s = 0; s < CH; s++)
-                    psa_step16<C, TRACE, false, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
-                                                      nullptr, false, 0u, 0u, dir_addr, mB);
+                    psa_step16<C, TRACE ? 1 : 0, 0, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                      nullptr, false, 0u, 0u, dir_addr, nullptr, mB);
             } else {
 #pragma unroll 2
                 for (int s = 0; s < CH; s++)
-                    psa_step16<C, TRACE, false, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
-                                                      nullptr, false, 0u, 0u, dir_addr, mB);
+                    psa_step16<C, TRACE ? 1 : 0, 0, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                      nullptr, false, 0u, 0u, dir_addr, nullptr, mB);
             }
         } else {
 #pragma unroll 1
             for (int s = 0; s < CH; s++)
-                psa_step16<C, TRACE, true, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
-                                                 nullptr, false, 0u, 0u, dir_addr, mB);
+                psa_step16<C, TRACE ? 1 : 0, 1, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                                                 nullptr, false, 0u, 0u, dir_addr, nullptr, mB);
         }
         __syncwarp();
         if (TRACE) {
@@ -669,16 +842,16 @@ __device__ __forceinline__ void psa_build_tab4(uint32_t* tab4, const PsaScoring&
 // ---------------------------------------------------------------------------------------
 // one long pair: one warp (= one CTA) per band of 64*C columns
 // ---------------------------------------------------------------------------------------
-template <int C, bool TRACE, int CH>
+template <int C, int TM, int CH>
 __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ PsaPairArgs a)
 {
-    __shared__ PsaWarpSmem16<C, TRACE> sm;
+    __shared__ PsaWarpSmem16<C, TM == 1> sm;
     __shared__ uint32_t tab4[256];
     const int lane = threadIdx.x;
     int band = 0;
     if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
     band = __shfl_sync(kFullMask, band, 0);
-    psa_build_tab4(tab4, a.sc, TRACE ? 4 : 1, lane, 32);
+    psa_build_tab4(tab4, a.sc, TM != 0 ? 4 : 1, lane, 32);
     __syncwarp();
 
     PsaBand b;
@@ -690,12 +863,21 @@ __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ 
     b.bnd_in = band == 0 ? a.inbox : a.bnd + (long long)(band - 1) * a.bnd_stride;
     b.bnd_out = (band == a.nbands - 1 && a.outbox) ? a.outbox : a.bnd + (long long)band * a.bnd_stride;
     b.epoch = a.epoch;
-    b.dirs = a.dirs; b.dirs_stride = a.dirs_stride;
+    b.abort_flag = a.abort_flag; b.timeout_ns = a.timeout_ns; b.timeline = a.timeline;
+    // TM 2: dirs_stride = bytes of one band's [step][lane] region (psa_skew_band_bytes)
+    b.dirs = TM == 2 ? a.dirs + (long long)band * a.dirs_stride : a.dirs;
+    b.dirs_stride = a.dirs_stride;
     b.lastrow = a.lastrow; b.lastrow_col0 = 0;
-    int ms = psa_sweep_band16<C, TRACE, true, CH>(b, a.sc, tab4, sm, lane);
+    int ms = psa_sweep_band16<C, TM, true, CH>(b, a.sc, tab4, sm, lane);
     ms = warp_max(ms);
     if (lane == 0) atomicMax(a.out_max, ms);
 }
+
+// Skewed direction layout of one long pair (TM 2): band b, step t, lane k -> one word (C <= 4: low
+// 16 bits = virtual lane k, high 16 bits = virtual lane k+32, nibble c = column c) or two words
+// (C > 4: word 0 = virtual lane k, word 1 = virtual lane k+32).  Row r of virtual lane v is in step r + v.
+__host__ __device__ inline long long psa_skew_steps(long long m) { return (m + 63 + 31) & ~31LL; }   // whole chunks: every step of every chunk stores
+__host__ __device__ inline long long psa_skew_band_bytes(long long m, int C) { return psa_skew_steps(m) * 32 * (C > 4 ? 8 : 4); }
 
 // ---------------------------------------------------------------------------------------
 // a batch of independent pairs: persistent warps, one pair at a time per warp
@@ -735,7 +917,7 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch16_kernel(const __grid_co
             for (int band = 0; band < nbands; band++) {
                 b.band = band;
                 b.lastrow = (band == nbands - 1) ? lastrow : nullptr;
-                ms = max(ms, psa_sweep_band16<C, TRACE, false, 32>(b, a.sc, tab4, sm[w], lane));
+                ms = max(ms, psa_sweep_band16<C, TRACE ? 1 : 0, false, 32>(b, a.sc, tab4, sm[w], lane));
             }
         }
         ms = warp_max(ms);

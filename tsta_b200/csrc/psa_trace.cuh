@@ -34,6 +34,10 @@ struct PsaTraceArgs {
     int start_forced;        // 0 free, 2 forced left, 1 forced up (tag form)
     int enc;                 // back code: 0 = (1 diagonal, 0 left, 2 up), 1 = (3 diagonal, 2 left, 1 up)
     long long* dbg;          // optional: walker cycles, total cycles, windows, prefetch hits
+    // skewed layout (psa_trace_skew_kernel): bytes of one band's [step][lane] region, steps per band, bands
+    long long skew_band_bytes;
+    long long skew_steps;
+    int skew_bands;
 };
 
 // `back` bits of a packed code -> move (1 diagonal, 0 left, 2 up) for either encoding
@@ -90,6 +94,13 @@ __device__ __forceinline__ unsigned trace_bsel(unsigned m, unsigned a, unsigned 
     unsigned d;
     asm volatile("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
     return d;
+}
+
+__device__ __forceinline__ uint2 trace_lds_u2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
 
 // One thread walks (3-state automaton of oracle/psa_oracle.c) while the other warps already
@@ -192,6 +203,229 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_kernel(const P
         a.out[1] = s_i;
         a.out[2] = s_j;
         a.out[3] = s_forced;
+        if (a.dbg) {
+            a.dbg[0] = dbg_walk; a.dbg[1] = clock64() - dbg_total0; a.dbg[2] = dbg_windows; a.dbg[3] = dbg_hits;
+        }
+    }
+}
+
+
+// =========================================================================================
+// Skewed direction layout (psa_fill16.cuh, TM 2): dirs[band][step][lane] words, row r of
+// virtual lane v in the word of step r + v; cell code = back tag | wf << 2 | we << 3, where
+// wf / we say "a walk that ENTERS this cell by a left / up move keeps going" (the same
+// automaton as above, read at the entered cell instead of the cell that was left).
+//
+// Staging a window is two phases: (1) the stripe of steps of every band under the window is
+// copied as it lies in HBM (contiguous, coalesced 16-byte loads) into a raw shared buffer,
+// (2) the window is assembled row-major, 4 bits per cell, from the raw words: one task =
+// one row x 8 virtual lanes = 8C columns = C whole 32-bit words, so nothing is read-modify-
+// written.  The walker is the only consumer, and it keeps just two rows in registers: the
+// current one and the one above (the row two above is re-loaded every step while the step's own chain
+// runs; an up move shifts the rows by bit-selects).  Moves leave as one tag byte each.
+// =========================================================================================
+template <int C>
+struct PsaSkewGeom {
+    static constexpr int kBandCols = 64 * C;
+    static constexpr int kGroupCols = 8 * C;                                  // one assembly task
+    static constexpr int kAlign = (kGroupCols % 16 == 0) ? kGroupCols : 2 * kGroupCols;   // window start granularity (columns)
+    static constexpr int kWinCols = (2 * kTraceBytes / kAlign) * kAlign;      // 512 or 480
+    static constexpr int kWords = C > 4 ? 2 : 1;                              // words per lane and step
+    static constexpr int kLineBytes = 128 * kWords;
+    static constexpr int kMaxBands = (kBandCols - kAlign + kWinCols + kBandCols - 1) / kBandCols;
+    static constexpr int kRawLines = (kTraceRows - 1) * kMaxBands + kWinCols / C;
+    static constexpr int kRawBytes = kRawLines * kLineBytes;
+    static constexpr int kSmemBytes = 2 * kTraceBufStride + kRawBytes;
+};
+
+template <int C>
+__device__ __forceinline__ void psa_skew_place(int i, int j, int& R0, int& C0)
+{
+    using G = PsaSkewGeom<C>;
+    R0 = max(0, i + 1 - kTraceRows);
+    C0 = max(0, (j / G::kAlign + 1) * G::kAlign - G::kWinCols);
+}
+
+// Stages rows [R0, R0+128) x columns [C0, C0+kWinCols) into `buf` (row pitch kTraceBytes).
+// Called by `nthreads` threads that share named barrier `bar_id`.
+template <int C>
+__device__ __forceinline__ void psa_skew_stage(const PsaTraceArgs& a, uint8_t* buf, uint8_t* raw, int R0, int C0,
+                                               int tid, int nthreads, int bar_id)
+{
+    using G = PsaSkewGeom<C>;
+    const long long T = a.skew_steps;
+    const int b0 = C0 / G::kBandCols;
+    // ---- phase 1: raw stripes.  Band b of the window needs virtual lanes [vlo, vhi] and steps R0+vlo .. R0+127+vhi
+    int line0 = 0;
+#pragma unroll
+    for (int bb = 0; bb < G::kMaxBands; bb++) {
+        const int b = b0 + bb;
+        const int cb0 = max(C0, b * G::kBandCols), cb1 = min(C0 + G::kWinCols, (b + 1) * G::kBandCols);
+        if (cb0 >= cb1) break;
+        const int vlo = (cb0 - b * G::kBandCols) / C, vhi = (cb1 - 1 - b * G::kBandCols) / C;
+        const int nlines = kTraceRows + vhi - vlo;
+        const long long tlo = (long long)R0 + vlo;
+        const int units = nlines * (G::kLineBytes / 16);
+        const uint4* src = reinterpret_cast<const uint4*>(a.dirs + (long long)b * a.skew_band_bytes + tlo * G::kLineBytes);
+        uint4* dst = reinterpret_cast<uint4*>(raw + (size_t)line0 * G::kLineBytes);
+        const bool have = b < a.skew_bands;
+        for (int u = tid; u < units; u += nthreads) {
+            const long long t = tlo + u / (G::kLineBytes / 16);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (have && t < T) v = __ldcs(src + u);
+            dst[u] = v;
+        }
+        line0 += nlines;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    // ---- phase 2: assembly.  Task (row rho, group gamma): 8 virtual lanes -> C words of the window row
+    constexpr int kGroups = G::kWinCols / G::kGroupCols;
+    const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw);
+    for (int task = tid; task < kTraceRows * kGroups; task += nthreads) {
+        const int rho = task / kGroups, gamma = task - rho * kGroups;
+        const int col = C0 + gamma * G::kGroupCols;
+        const int b = col / G::kBandCols;
+        const int v0 = (col - b * G::kBandCols) / C;               // multiple of 8
+        // raw line of (band b, row rho, virtual lane v): lines of the bands before b, then rho + v - vlo(b)
+        int lbase = 0;
+#pragma unroll
+        for (int bb = 0; bb < G::kMaxBands - 1; bb++) {
+            const int bq = b0 + bb;
+            if (bq < b) {
+                const int cb0 = max(C0, bq * G::kBandCols), cb1 = min(C0 + G::kWinCols, (bq + 1) * G::kBandCols);
+                lbase += kTraceRows + (cb1 - 1 - bq * G::kBandCols) / C - (cb0 - bq * G::kBandCols) / C;
+            }
+        }
+        const int vlo = (max(C0, b * G::kBandCols) - b * G::kBandCols) / C;
+        unsigned long long acc = 0;
+        int fill = 0, outw = 0;
+        uint32_t* dstw = reinterpret_cast<uint32_t*>(buf + rho * kTraceBytes + (gamma * G::kGroupCols) / 2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int v = v0 + e;
+            const int line = lbase + rho + v - vlo;
+            uint32_t w = raw32[(size_t)line * (32 * G::kWords) + (v & 31) * G::kWords + (G::kWords == 2 ? (v >> 5) : 0)];
+            if (G::kWords == 1) w = (v >> 5) ? (w >> 16) : (w & 0xffffu);
+            constexpr uint32_t kPiece = 4 * C < 32 ? (1u << ((4 * C) & 31)) - 1u : 0xffffffffu;   // 4C bits
+            w &= kPiece;
+            // a tag of 0 never comes out of a fill; turn it into a diagonal so that even a corrupt
+            // matrix (or the zero fill outside it) cannot stall the walk
+            w |= (~(w | (w >> 1)) & (0x11111111u & kPiece)) * 3u;
+            acc |= (unsigned long long)w << fill;
+            fill += 4 * C;
+            if (fill >= 32) {
+                dstw[outw++] = (uint32_t)acc;
+                acc >>= 32;
+                fill -= 32;
+            }
+        }
+    }
+}
+
+template <int C>
+static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(const PsaTraceArgs a)
+{
+    using G = PsaSkewGeom<C>;
+    extern __shared__ __align__(16) uint8_t trace_smem[];      // two window buffers (each behind an apron), then the raw stripes
+    __shared__ int s_i, s_j, s_arr, s_nops;
+    uint8_t* const raw = trace_smem + 2 * kTraceBufStride;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        s_i = a.start_i;
+        s_j = a.start_j;
+        s_arr = a.start_forced ? a.start_forced : 3;           // how the walk entered the start cell: 3 free, 2 by a left move, 1 by an up move
+        s_nops = 0;
+    }
+    __syncthreads();
+    int cur = 0, R0, C0;
+    long long dbg_walk = 0, dbg_total0 = clock64();
+    int dbg_windows = 0, dbg_hits = 0;
+    psa_skew_place<C>(s_i, s_j, R0, C0);
+    psa_skew_stage<C>(a, trace_smem + kTraceApron, raw, R0, C0, tid, kTraceThreads, 1);
+    __syncthreads();
+
+    while (true) {
+        const int i0 = s_i, j0 = s_j;
+        if (i0 < 0 || j0 < 0) break;
+        // where the path is expected to leave this window: through the top, about one column per row
+        int NR0, NC0;
+        psa_skew_place<C>(R0 - 1, max(0, j0 - (i0 - R0 + 1) + G::kWinCols / 4), NR0, NC0);
+        if (tid >= 32) {
+            if (R0 > 0) psa_skew_stage<C>(a, trace_smem + kTraceApron + (cur ^ 1) * kTraceBufStride, raw, NR0, NC0,
+                                           tid - 32, kTraceThreads - 32, 2);
+        } else if (tid == 0) {
+            const long long dbg_t0 = clock64();
+            dbg_windows++;
+            const uint8_t* win = trace_smem + kTraceApron + cur * kTraceBufStride;
+            int i = i0, j = j0;
+            unsigned nops = (unsigned)s_nops;
+            unsigned mvp = (unsigned)s_arr;                    // previous move (3 diagonal / start, 2 left, 1 up)
+            const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
+            unsigned sh = 4u - mvp, nf = 6u >> mvp;
+            uint8_t* out = a.ops + nops;
+            while (i >= R0 && j >= C0) {
+                const int j16 = j & ~15;
+                const uint32_t colbase = win_s + (uint32_t)((j16 - C0) >> 1);
+                int q = (i - R0) * kTraceBytes;                      // row offset inside the window; an up move subtracts one row
+                uint2 cw = trace_lds_u2(colbase + q);
+                uint2 u1 = trace_lds_u2(colbase + q - kTraceBytes);  // (rows above R0 are the apron: loaded, never used)
+                int pos = 4 * (j - j16);
+                const int q0 = q;
+                // A step uses up at most one row and one column, so min(rows, columns) steps need no exit test at all:
+                // the loop branch does not depend on the moves, and the only chain that spans iterations is
+                // code -> forced? -> move -> row select / column shift.  The row two above is loaded at the top and
+                // only used by the selects at the bottom, so its latency hides behind that chain.
+                int safe = min(q / kTraceBytes, pos >> 2) + 1;
+                while (safe > 0) {
+#pragma unroll 2
+                    for (int s = 0; s < safe; s++) {
+                        const uint2 u2 = trace_lds_u2(colbase + q - 2 * kTraceBytes);
+                        const unsigned c = (unsigned)((((unsigned long long)cw.y << 32) | cw.x) >> pos);   // low nibble = code
+                        // forced: entered by a left move and wf (bit 2) set, or by an up move and we (bit 3) set
+                        unsigned f, mv, um;
+                        asm volatile("lop3.b32 %0, %1, %2, 1, 0x80;" : "=r"(f) : "r"(c >> sh), "r"(nf));        // (c >> sh) & nf & 1
+                        const unsigned c3 = c & 3u;
+                        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(mv) : "r"(f), "r"(mvp - c3), "r"(c3));   // f ? mvp : c3, no predicate
+                        asm volatile("bfe.s32 %0, %1, 0, 1;" : "=r"(um) : "r"(mv));                               // 0 - (mv & 1): up / diagonal
+                        out[s] = (uint8_t)mv;                        // tags; the host maps them to 1 / 0 / 2
+                        cw.x = trace_bsel(um, u1.x, cw.x);
+                        cw.y = trace_bsel(um, u1.y, cw.y);
+                        u1.x = trace_bsel(um, u2.x, u1.x);
+                        u1.y = trace_bsel(um, u2.y, u1.y);
+                        q += (int)um * kTraceBytes;
+                        asm volatile("mad.lo.s32 %0, %1, -2, %2;" : "=r"(pos) : "r"(mv & 2u), "r"(pos));
+                        mvp = mv;
+                        sh = 4u - mv;
+                        nf = 6u >> mv;
+                    }
+                    out += safe;
+                    safe = (q | pos) < 0 ? 0 : min(q / kTraceBytes, pos >> 2) + 1;
+                }
+                i -= (q0 - q) / kTraceBytes;
+                j = j16 + (pos >> 2);
+            }
+            nops = (unsigned)(out - a.ops);
+            s_i = i; s_j = j; s_arr = (int)mvp; s_nops = (int)nops;
+            dbg_walk += clock64() - dbg_t0;
+        }
+        __syncthreads();
+        const int i1 = s_i, j1 = s_j;
+        if (i1 < 0 || j1 < 0) break;
+        if (R0 > 0 && i1 >= NR0 && i1 < NR0 + kTraceRows && j1 >= NC0 && j1 < NC0 + G::kWinCols) {
+            cur ^= 1; R0 = NR0; C0 = NC0;                       // the prefetched window fits
+            dbg_hits++;
+        } else {
+            psa_skew_place<C>(i1, j1, R0, C0);
+            psa_skew_stage<C>(a, trace_smem + kTraceApron + cur * kTraceBufStride, raw, R0, C0, tid, kTraceThreads, 1);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.out[0] = s_nops;
+        a.out[1] = s_i;
+        a.out[2] = s_j;
+        a.out[3] = s_arr == 3 ? 0 : s_arr;
         if (a.dbg) {
             a.dbg[0] = dbg_walk; a.dbg[1] = clock64() - dbg_total0; a.dbg[2] = dbg_windows; a.dbg[3] = dbg_hits;
         }

@@ -207,7 +207,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     a.ticket = p->d_ctl.as<unsigned>();
     a.lastsorce = p->d_last.as<int>();
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
-    poa_fill_kernel<<<p->nbands, 32, sizeof(PoaSmem), p->stream>>>(a);
+    { NvtxRange range("tsta_poa fill"); poa_fill_kernel<<<p->nbands, 32, sizeof(PoaSmem), p->stream>>>(a); }
     TSTA_CUDA_TRY(cudaGetLastError());
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(lastsorce, p->d_last.p, (size_t)nrows * 4, cudaMemcpyDeviceToHost, p->stream));
@@ -234,7 +234,7 @@ int tsta_poa_walk(tsta_poa* p, int start_row, tsta_poa_step* path, int* nsteps, 
     w.path = p->d_path.as<PoaStep>();
     w.nsteps = p->d_ctl.as<int>() + 4;
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
-    poa_walk_kernel<<<1, kPoaWalkThreads, 0, p->stream>>>(w);
+    { NvtxRange range("tsta_poa walk"); poa_walk_kernel<<<1, kPoaWalkThreads, 0, p->stream>>>(w); }
     TSTA_CUDA_TRY(cudaGetLastError());
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
     int n = 0;

@@ -104,6 +104,7 @@ struct tsta_psa_plan {
     bool prmt = true;
     bool packed = false;           // int16 x 2 kernels (psa_fill16.cuh); else int32 (psa_fill.cuh)
     int scale = 1;                 // score scale of the device results (1 score-only, 2 int32 traced, 4 packed traced)
+    bool skew = false;             // traced + packed: skewed direction layout, 2-bit moves (psa_trace_skew_kernel)
     // column slice of a pair spread over several GPUs (tsta_psa_plan_upload_slice)
     int64_t col0 = 0, n_total = 0;
     bool has_left = false, has_right = false;
@@ -116,7 +117,7 @@ struct tsta_psa_plan {
     int launches = 0;
     unsigned epoch = 0;            // boundary tag of the last run (see psa_fill.cuh: bnd_pack)
     std::vector<char> h_s0, h_s1;  // host copies for string emission
-    DevBuf d_s0, d_s1, d_bnd, d_ctl, d_dirs, d_ops, d_lastrow;
+    DevBuf d_s0, d_s1, d_bnd, d_ctl, d_dirs, d_ops, d_lastrow, d_timeline;
     // d_ctl layout (ints): [0] ticket, [1] out_max, [2..4] trace out, [8..15] presence
     int* h_small = nullptr;  // pinned, 16 ints
 };
@@ -126,7 +127,7 @@ static void plan_free(tsta_psa_plan* p)
     if (!p) return;
     cudaSetDevice(p->device);
     p->d_s0.release(); p->d_s1.release(); p->d_bnd.release(); p->d_ctl.release();
-    p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release(); p->d_inbox.release();
+    p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release(); p->d_inbox.release(); p->d_timeline.release();
     if (p->outbox_open) cudaIpcCloseMemHandle(p->outbox);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -150,23 +151,29 @@ static void launch_pair(const tsta_psa_plan* p, const PsaPairArgs& fa)
     }
 }
 
-template <int C, bool TRACE>
+template <int C, int TM>
 static void launch_pair16(const tsta_psa_plan* p, const PsaPairArgs& fa)
 {
-    // 32-row hand-off chunks: fewer re-centrings / stagings per row beat the shorter inter-band lag of 16
-    if (p->CH == 16) psa_pair16_kernel<C, TRACE, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
-    else psa_pair16_kernel<C, TRACE, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    // 32-row chunks (re-centring, row tables); the left boundary is imported in groups of 8 rows
+    if (p->CH == 16) psa_pair16_kernel<C, TM, 16><<<fa.nbands, 32, 0, p->stream>>>(fa);
+    else psa_pair16_kernel<C, TM, 32><<<fa.nbands, 32, 0, p->stream>>>(fa);
+}
+
+template <int C>
+static cudaError_t launch_trace_skew(const PsaTraceArgs& ta, cudaStream_t st)
+{
+    // (function attributes are per device: set it on every launch, it costs nothing)
+    cudaError_t e = cudaFuncSetAttribute(psa_trace_skew_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PsaSkewGeom<C>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    psa_trace_skew_kernel<C><<<1, kTraceThreads, PsaSkewGeom<C>::kSmemBytes, st>>>(ta);
+    return cudaGetLastError();
 }
 
 // Packed kernels: 64*C columns per band; the smallest strip that keeps one band per SM
-// sub-partition, as below.  Traced strips pack to whole 8/16/32-bit direction words.
-static int choose_strip16(int64_t n, int sms, bool trace)
+// sub-partition, as below (traced pairs too: the skewed direction layout takes any strip width).
+static int choose_strip16(int64_t n, int sms)
 {
     const int64_t slots = (int64_t)sms * 4;
-    if (trace) {
-        for (int c : {2, 4}) if (n <= 64 * c * slots) return c;
-        return 8;
-    }
     for (int c : {2, 3, 4, 6}) if (n <= 64 * c * slots) return c;
     return 8;
 }
@@ -181,6 +188,61 @@ static int choose_strip(int64_t n, int sms, bool trace)
     if (!trace && n <= 32 * 6 * slots) return 6;   // 6-column strips do not pack to whole direction words
     if (n <= 32 * 8 * slots) return 8;
     return 16;
+}
+
+// Plans cached by tsta_psa_align, one per (thread, trace mode); freed at thread exit or on request.
+struct AlignCache {
+    tsta_psa_plan* plan[2] = {nullptr, nullptr};
+    void release() { for (auto& q : plan) { plan_free(q); q = nullptr; } }
+    ~AlignCache() { release(); }
+};
+static thread_local AlignCache g_align_cache;
+
+// Traceback kernel of a plan (whole pair or one column slice), starting in the slice's last column.
+static int launch_walk(tsta_psa_plan* p, int64_t start_i, int start_state)
+{
+    NvtxRange range("tsta_psa traceback");
+    int* ctl = p->d_ctl.as<int>();
+    PsaTraceArgs ta{};
+    ta.dirs = p->d_dirs.as<uint8_t>();
+    ta.dirs_stride = p->n_pad / 2;
+    ta.n = (int)p->n; ta.m = (int)p->m;
+    ta.ops = p->d_ops.as<uint8_t>();
+    ta.out = ctl + 2;
+    ta.enc = p->packed ? 1 : 0;
+    ta.start_i = (int)start_i; ta.start_j = (int)p->n - 1; ta.start_forced = start_state;
+    if (getenv("TSTA_TRACE_DEBUG")) { if (!tsta::g_trace_dbg) cudaMalloc(&tsta::g_trace_dbg, 64); ta.dbg = tsta::g_trace_dbg; }
+    if (p->skew) {
+        ta.skew_band_bytes = psa_skew_band_bytes(p->m, p->C);
+        ta.skew_steps = psa_skew_steps(p->m);
+        ta.skew_bands = p->nbands;
+        cudaError_t e;
+        if (p->C == 2) e = launch_trace_skew<2>(ta, p->stream);
+        else if (p->C == 3) e = launch_trace_skew<3>(ta, p->stream);
+        else if (p->C == 4) e = launch_trace_skew<4>(ta, p->stream);
+        else if (p->C == 6) e = launch_trace_skew<6>(ta, p->stream);
+        else e = launch_trace_skew<8>(ta, p->stream);
+        TSTA_CUDA_TRY(e);
+    } else {
+        // (function attributes are per device: set it on every launch, it costs nothing)
+        TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
+        psa_trace_kernel<<<1, kTraceThreads, kTraceSmemBytes, p->stream>>>(ta);
+        TSTA_CUDA_TRY(cudaGetLastError());
+    }
+    return TSTA_OK;
+}
+
+// Moves of the last walk as one byte each (1 diagonal, 0 left, 2 up), walk order.  The skewed-layout
+// walker writes the tags (3 diagonal, 2 left, 1 up).
+static int fetch_moves(tsta_psa_plan* p, uint8_t* out, int64_t nops)
+{
+    if (nops <= 0) return TSTA_OK;
+    TSTA_CUDA_TRY(cudaMemcpy(out, p->d_ops.p, (size_t)nops, cudaMemcpyDeviceToHost));
+    if (p->skew) {
+        static const uint8_t kMove[4] = {1, 2, 0, 1};   // tag -> move (tag 0 never occurs)
+        for (int64_t k = 0; k < nops; k++) out[k] = kMove[out[k] & 3u];
+    }
+    return TSTA_OK;
 }
 
 extern "C" {
@@ -308,7 +370,8 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
     if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
     if (int rc = check_params(prm)) return rc;
     if (n < 0 || m < 0 || (n > 0 && !s0) || (m > 0 && !s1)) return set_error(TSTA_EINVAL, "bad sequence arguments");
-    if (n_total < m) return set_error(TSTA_EINVAL, "s0 must be the longer read (n=%lld < m=%lld); swap like psa.c:194-199",
+    if (n_total < m && !getenv("TSTA_PSA_ALLOW_TALL"))   // (experiments only: tools/calib.py times few bands over many rows)
+        return set_error(TSTA_EINVAL, "s0 must be the longer read (n=%lld < m=%lld); swap like psa.c:194-199",
                                       (long long)n_total, (long long)m);
     // int32 headroom: doubled scores, worst step 2*127 per row/column
     if ((n_total + m) > (int64_t)4000000) return set_error(TSTA_EINVAL, "n+m=%lld exceeds the supported 4e6", (long long)(n_total + m));
@@ -351,10 +414,10 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
     p->packed = false;
     {
         const bool tr = p->want_trace != 0;
-        int c16 = choose_strip16(n, p->sms, tr);
+        int c16 = choose_strip16(n, p->sms);
         if (const char* e = getenv("TSTA_PSA_C16")) {
             const int c = atoi(e);
-            if (c == 2 || c == 4 || c == 8 || (!tr && (c == 3 || c == 6))) c16 = c;
+            if (c == 2 || c == 3 || c == 4 || c == 6 || c == 8) c16 = c;
         }
         const char* off = getenv("TSTA_PSA_PACKED");
         if (!(off && atoi(off) == 0) && psa16_fits(prm->M, prm->X, prm->E, prm->O, tr ? 4 : 1, c16, K)) {
@@ -363,6 +426,7 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
         }
     }
     p->scale = p->packed && p->want_trace ? 4 : S;
+    p->skew = p->packed && p->want_trace;
     const int band_cols = (p->packed ? 64 : 32) * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
     p->n_pad = p->nbands * band_cols;
@@ -382,13 +446,16 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
         if (need > p->d_bnd.cap) {
             if (int rc = p->d_bnd.reserve(need + need / 4)) return rc;
             TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
-            p->epoch = 0;
+            // (the epoch stays monotonic: fresh memory carries tag 0, which no run uses, and the slices of
+            // one pair on other GPUs keep counting in step with this plan)
         }
     }
     if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
     if (p->want_trace) {
-        if (int rc = p->d_dirs.reserve((size_t)m * (size_t)(p->n_pad / 2))) return rc;
-        if (int rc = p->d_ops.reserve((size_t)(n + m))) return rc;
+        const size_t dir_bytes = p->skew ? (size_t)p->nbands * (size_t)psa_skew_band_bytes(m, p->C)
+                                         : (size_t)m * (size_t)(p->n_pad / 2);
+        if (int rc = p->d_dirs.reserve(dir_bytes)) return rc;
+        if (int rc = p->d_ops.reserve((size_t)(n + m) + 64)) return rc;
     }
     p->uploaded = true;
     return TSTA_OK;
@@ -407,7 +474,11 @@ int tsta_psa_plan_wait(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     if (trace_ms) *trace_ms = 0.f;
     if (p->n == 0 || p->m == 0) { p->ran = true; return TSTA_OK; }
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small + 6, p->d_ctl.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (p->h_small[6] != 0)
+        return set_error(TSTA_ECUDA, "boundary hand-off timed out: a band (or column slice) waited for its left neighbour in vain "
+                                     "(slices of one pair must be launched together and run the same number of times)");
     if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
         long long h[4] = {0, 0, 0, 0};
         using tsta::g_trace_dbg;
@@ -432,6 +503,7 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
     TSTA_CUDA_TRY(cudaMemsetAsync(ctl, 0, 8 * sizeof(int), p->stream));
     if (++p->epoch > 0xffffu) {
         TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+        if (p->d_inbox.p) TSTA_CUDA_TRY(cudaMemsetAsync(p->d_inbox.p, 0, p->d_inbox.cap, p->stream));
         p->epoch = 1;
     }
     p->h_small[0] = INT_MIN;
@@ -447,7 +519,16 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
     fa.epoch = p->epoch;
     fa.ticket = reinterpret_cast<unsigned*>(ctl);
     fa.dirs = p->d_dirs.as<uint8_t>();
-    fa.dirs_stride = p->n_pad / 2;
+    fa.dirs_stride = p->skew ? psa_skew_band_bytes(p->m, p->C) : p->n_pad / 2;
+    fa.abort_flag = ctl + 6;
+    fa.timeout_ns = 10000000000ull;   // a band that waits this long for its left neighbour gives up (TSTA_ECUDA instead of a hang)
+    if (const char* e = getenv("TSTA_HANDOFF_TIMEOUT_MS")) fa.timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
+    fa.timeline = nullptr;
+    if (getenv("TSTA_PSA_TIMELINE")) {   // experiments: per-band time stamps, read back with tsta_psa_plan_timeline
+        if (int rc = p->d_timeline.reserve((size_t)p->nbands * 16 * sizeof(unsigned long long))) return rc;
+        TSTA_CUDA_TRY(cudaMemsetAsync(p->d_timeline.p, 0, (size_t)p->nbands * 128, p->stream));
+        fa.timeline = p->d_timeline.as<unsigned long long>();
+    }
     fa.out_max = ctl + 1;
     fa.lastrow = p->d_lastrow.as<int>();
     fa.col_off = (int)p->col0;
@@ -456,43 +537,35 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
     if (p->has_right && !p->outbox) return set_error(TSTA_EINVAL, "slice has a right neighbour but tsta_psa_plan_connect_right was not called");
 
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+    nvtxRangePushA("tsta_psa fill");
     if (p->want_trace && p->packed) {
-        if (p->C == 2) launch_pair16<2, true>(p, fa);
-        else if (p->C == 4) launch_pair16<4, true>(p, fa);
-        else launch_pair16<8, true>(p, fa);
+        if (p->C == 2) launch_pair16<2, 2>(p, fa);
+        else if (p->C == 3) launch_pair16<3, 2>(p, fa);
+        else if (p->C == 4) launch_pair16<4, 2>(p, fa);
+        else if (p->C == 6) launch_pair16<6, 2>(p, fa);
+        else launch_pair16<8, 2>(p, fa);
     } else if (p->want_trace) {
         if (p->C == 4) launch_pair<4, true>(p, fa);
         else if (p->C == 8) launch_pair<8, true>(p, fa);
         else launch_pair<16, true>(p, fa);
     } else if (p->packed) {
-        if (p->C == 2) launch_pair16<2, false>(p, fa);
-        else if (p->C == 3) launch_pair16<3, false>(p, fa);
-        else if (p->C == 4) launch_pair16<4, false>(p, fa);
-        else if (p->C == 6) launch_pair16<6, false>(p, fa);
-        else launch_pair16<8, false>(p, fa);
+        if (p->C == 2) launch_pair16<2, 0>(p, fa);
+        else if (p->C == 3) launch_pair16<3, 0>(p, fa);
+        else if (p->C == 4) launch_pair16<4, 0>(p, fa);
+        else if (p->C == 6) launch_pair16<6, 0>(p, fa);
+        else launch_pair16<8, 0>(p, fa);
     } else {
         if (p->C == 4) launch_pair<4, false>(p, fa);
         else if (p->C == 6) launch_pair<6, false>(p, fa);
         else if (p->C == 8) launch_pair<8, false>(p, fa);
         else launch_pair<16, false>(p, fa);
     }
+    nvtxRangePop();
     TSTA_CUDA_TRY(cudaGetLastError());
     p->launches++;
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
     if (p->want_trace && !(p->has_left || p->has_right)) {   // (slices are walked later, right to left: tsta_psa_plan_trace_from)
-        PsaTraceArgs ta{};
-        ta.dirs = fa.dirs;
-        ta.dirs_stride = fa.dirs_stride;
-        ta.n = fa.n; ta.m = fa.m;
-        ta.ops = p->d_ops.as<uint8_t>();
-        ta.out = ctl + 2;
-        ta.enc = p->packed ? 1 : 0;
-        ta.start_i = fa.m - 1; ta.start_j = fa.n - 1; ta.start_forced = 0;
-        if (getenv("TSTA_TRACE_DEBUG")) { if (!tsta::g_trace_dbg) cudaMalloc(&tsta::g_trace_dbg, 64); ta.dbg = tsta::g_trace_dbg; }
-        // (function attributes are per device: set it on every launch, it costs nothing)
-        TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
-        psa_trace_kernel<<<1, kTraceThreads, kTraceSmemBytes, p->stream>>>(ta);
-        TSTA_CUDA_TRY(cudaGetLastError());
+        if (int rc = launch_walk(p, fa.m - 1, 0)) return rc;
         p->launches++;
     }
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
@@ -523,8 +596,7 @@ int tsta_psa_plan_fetch(tsta_psa_plan* p, tsta_psa_result* out)
             fi = p->h_small[3];
             fj = p->h_small[4];
             ops.resize((size_t)(n + m));
-            if (nops > 0)
-                TSTA_CUDA_TRY(cudaMemcpy(ops.data(), p->d_ops.p, (size_t)nops, cudaMemcpyDeviceToHost));
+            if (int rc = fetch_moves(p, ops.data(), nops)) return rc;
         }
     }
     if (p->want_trace && !(p->has_left || p->has_right)) {   // (slices: tsta_psa_plan_trace_from / _ops)
@@ -564,6 +636,31 @@ int tsta_psa_plan_dirs(tsta_psa_plan* p, uint8_t* out)
     if (!p || !out || !p->ran || !p->want_trace) return set_error(TSTA_EINVAL, "plan not run with traceback");
     if (p->n == 0 || p->m == 0) return TSTA_OK;
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    const int64_t n = p->n, m = p->m;
+    if (p->skew) {
+        // skewed layout: band b, step t = row + virtual lane, lane; the cell holds back tag | wf << 2 | we << 3.
+        // Reported in the oracle's form: cF(i,j) = wf(i,j-1), cE(i,j) = we(i-1,j) (see psa_fill16.cuh).
+        const int C = p->C, W = C > 4 ? 2 : 1;
+        const size_t band_bytes = (size_t)psa_skew_band_bytes(m, C);
+        const int64_t T = psa_skew_steps(m);
+        std::vector<uint32_t> raw((size_t)p->nbands * band_bytes / 4);
+        TSTA_CUDA_TRY(cudaMemcpy(raw.data(), p->d_dirs.p, raw.size() * 4, cudaMemcpyDeviceToHost));
+        auto cell = [&](int64_t i, int64_t j) -> unsigned {
+            const int64_t b = j / (64 * C), v = (j % (64 * C)) / C, c = j % C;
+            const size_t w = ((size_t)b * (size_t)T + (size_t)(i + v)) * 32 * W + (size_t)(v & 31) * W + (W == 2 ? (size_t)(v >> 5) : 0);
+            const unsigned sh = (unsigned)(4 * c + (W == 1 ? 16 * (v >> 5) : 0));
+            return (raw[w] >> sh) & 15u;
+        };
+        for (int64_t i = 0; i < m; i++)
+            for (int64_t j = 0; j < n; j++) {
+                const unsigned c = cell(i, j);
+                unsigned code = (0x48u >> (2 * (c & 3))) & 3u;                   // tags 3 / 2 / 1 -> 1 diagonal, 0 left, 2 up
+                if (j >= 1 && (cell(i, j - 1) & 4u)) code |= 4u;
+                if (i >= 1 && (cell(i - 1, j) & 8u)) code |= 8u;
+                out[(size_t)i * n + j] = (uint8_t)code;
+            }
+        return TSTA_OK;
+    }
     const size_t stride = (size_t)p->n_pad / 2;
     std::vector<uint8_t> packed((size_t)p->m * stride);
     TSTA_CUDA_TRY(cudaMemcpy(packed.data(), p->d_dirs.p, packed.size(), cudaMemcpyDeviceToHost));
@@ -588,6 +685,14 @@ int tsta_psa_plan_info(tsta_psa_plan* p, int* launches, int* cols_per_lane, int*
 
 int tsta_psa_plan_packed(tsta_psa_plan* p) { return p && p->packed ? 1 : 0; }
 
+int tsta_psa_plan_timeline(tsta_psa_plan* p, unsigned long long* out)   // [bands][16]: 8 globaltimer stamps (ns), then import statistics (TSTA_PSA_TIMELINE=1)
+{
+    if (!p || !out || !p->d_timeline.p) return set_error(TSTA_EINVAL, "no timeline recorded (set TSTA_PSA_TIMELINE=1)");
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    TSTA_CUDA_TRY(cudaMemcpy(out, p->d_timeline.p, (size_t)p->nbands * 128, cudaMemcpyDeviceToHost));
+    return TSTA_OK;
+}
+
 int tsta_psa_plan_trace_from(tsta_psa_plan* p, int64_t start_i, int start_forced,
                              int64_t* end_i, int* end_forced, int64_t* nops, float* ms)
 {
@@ -597,18 +702,8 @@ int tsta_psa_plan_trace_from(tsta_psa_plan* p, int64_t start_i, int start_forced
         return set_error(TSTA_EINVAL, "bad start of the walk (row %lld, state %d)", (long long)start_i, start_forced);
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     int* ctl = p->d_ctl.as<int>();
-    PsaTraceArgs ta{};
-    ta.dirs = p->d_dirs.as<uint8_t>();
-    ta.dirs_stride = p->n_pad / 2;
-    ta.n = (int)p->n; ta.m = (int)p->m;
-    ta.ops = p->d_ops.as<uint8_t>();
-    ta.out = ctl + 2;
-    ta.enc = p->packed ? 1 : 0;
-    ta.start_i = (int)start_i; ta.start_j = (int)p->n - 1; ta.start_forced = start_forced;
-    TSTA_CUDA_TRY(cudaFuncSetAttribute(psa_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTraceSmemBytes));
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
-    psa_trace_kernel<<<1, kTraceThreads, kTraceSmemBytes, p->stream>>>(ta);
-    TSTA_CUDA_TRY(cudaGetLastError());
+    if (int rc = launch_walk(p, start_i, start_forced)) return rc;
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small, ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
@@ -623,8 +718,7 @@ int tsta_psa_plan_ops(tsta_psa_plan* p, uint8_t* out, int64_t nops)
 {
     if (!p || !out || !p->want_trace || nops < 0 || nops > p->n + p->m) return set_error(TSTA_EINVAL, "bad arguments");
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
-    if (nops > 0) TSTA_CUDA_TRY(cudaMemcpy(out, p->d_ops.p, (size_t)nops, cudaMemcpyDeviceToHost));
-    return TSTA_OK;
+    return fetch_moves(p, out, nops);
 }
 
 void tsta_psa_result_free(tsta_psa_result* r)
@@ -639,15 +733,18 @@ int tsta_psa_align(const tsta_params* prm, const char* s0, int64_t n, const char
                    int want_trace, tsta_psa_result* out)
 {
     if (!out) return set_error(TSTA_EINVAL, "result pointer is NULL");
-    // one cached plan per (thread, trace mode): repeated calls reuse device buffers
-    thread_local tsta_psa_plan* cache[2] = {nullptr, nullptr};
+    // one cached plan per (thread, trace mode): repeated calls reuse device buffers (a traced 100 kbp
+    // pair keeps its ~7 GB direction matrix; tsta_psa_release_cache() or thread exit returns it)
     const int k = want_trace ? 1 : 0;
-    if (!cache[k]) {
-        if (int rc = tsta_psa_plan_create(&cache[k], k)) return rc;
+    tsta_psa_plan*& plan = g_align_cache.plan[k];
+    if (!plan) {
+        if (int rc = tsta_psa_plan_create(&plan, k)) return rc;
     }
-    if (int rc = tsta_psa_plan_upload(cache[k], prm, s0, n, s1, m)) return rc;
-    if (int rc = tsta_psa_plan_run(cache[k], nullptr, nullptr)) return rc;
-    return tsta_psa_plan_fetch(cache[k], out);
+    if (int rc = tsta_psa_plan_upload(plan, prm, s0, n, s1, m)) return rc;
+    if (int rc = tsta_psa_plan_run(plan, nullptr, nullptr)) return rc;
+    return tsta_psa_plan_fetch(plan, out);
 }
+
+void tsta_psa_release_cache(void) { g_align_cache.release(); }
 
 }  // extern "C"

@@ -64,7 +64,17 @@ struct Guard {   // shim over the persistent context: same call sites as a scope
     BatchCtx& c;
     cudaStream_t& st;
     cudaEvent_t &e0, &e1;
+    bool done = false;   // set on the success path, which has synchronised already
     explicit Guard(BatchCtx& ctx) : c(ctx), st(ctx.st), e0(ctx.e0), e1(ctx.e1) {}
+    // every early error return leaves copies and kernels in flight that read or write the CALLER's buffers
+    // (asynchronous when they are page-locked): wait for them before the caller may free those buffers
+    ~Guard()
+    {
+        if (done) return;
+        if (c.cp) cudaStreamSynchronize(c.cp);
+        if (c.st) cudaStreamSynchronize(c.st);
+        if (c.dh) cudaStreamSynchronize(c.dh);
+    }
     template <class T> int alloc(T** out, size_t count, DevBuf& buf)
     {
         if (int rc = buf.reserve(std::max<size_t>(count, 1) * sizeof(T))) return rc;
@@ -101,7 +111,10 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         max0 = std::max<int64_t>(max0, len0[k]);
         max1 = std::max<int64_t>(max1, len1[k]);
         cells += (double)len0[k] * (double)len1[k];
-        if (want_trace) ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
+        if (want_trace) {
+            if (ops_off[k] < 0) return set_error(TSTA_EINVAL, "pair %lld: negative ops_off", (long long)k);
+            ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
+        }
     }
     const int S = want_trace ? 2 : 1;
 
@@ -346,5 +359,6 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         total_ms += ms;
     }
     if (kernel_ms) *kernel_ms = total_ms;
+    g.done = true;
     return TSTA_OK;
 }

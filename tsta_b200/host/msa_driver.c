@@ -34,6 +34,8 @@ static void print_usage(void)
     printf("example:\n./TSTA_msa -i seq.fa -o output.txt\n");
 }
 
+#define MSA_ETOOMANY (-77)
+
 /* control() without the tile loop (c-t-simd.c:979-1049) */
 static int align_read(poa_graph* g, const char* read, int num, const msa_params* p, const msa_backend* be)
 {
@@ -54,7 +56,7 @@ static int align_read(poa_graph* g, const char* read, int num, const msa_params*
         t_walk += now_s() - t0;
         t0 = now_s();
         if (nsteps < 0) rc = nsteps;
-        else poa_graph_fuse(g, read, num, path, nsteps);
+        else if (poa_graph_fuse(g, read, num, path, nsteps) != 0) rc = MSA_ETOOMANY;
         t_fuse += now_s() - t0;
     }
     free(path);
@@ -114,6 +116,11 @@ int msa_main(int argc, char* argv[], const msa_backend* be)
         printf("\n");
         rc = align_read(&g, f.rec[n - 1].seq, n - 1, &prm, be);
         poa_graph_sort(&g, 1);
+    }
+    if (rc == MSA_ETOOMANY) {
+        fprintf(stderr, "TSTA_msa: more than %d different symbols aligned in one column (the reference's mismatch_node[4] limit); "
+                        "upper-case the input or remove ambiguity codes\n", POA_MM_MAX + 1);
+        return 2;
     }
     if (rc != 0) {
         fprintf(stderr, "TSTA_msa: %s\n", be->error ? be->error(be->ctx) : "alignment failed");

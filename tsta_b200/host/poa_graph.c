@@ -238,10 +238,11 @@ static void realize(poa_graph* g, int id, int num, int* l, int set_sub)
     (*l)++;
 }
 
-void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, int nsteps)
+int poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, int nsteps)
 {
     const int len_b = (int)strlen(b);
-    if (len_b == 0) return;
+    if (len_b == 0) return 0;
+    int overflow = 0;
     /* one provisional node per read base, chained (c-t-simd.c:685-726) */
     int* seq = (int*)malloc((size_t)len_b * sizeof(int));
     for (int i = 0; i < len_b; i++) seq[i] = node_new(g, (unsigned char)b[i]);
@@ -366,6 +367,10 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
             realize(g, seq[num2], num, &l, 1);
             poa_node* c = &g->node[cur];
             poa_node* nn = &g->node[seq[num2]];
+            /* The reference keeps the group in mismatch_node[4] (msa/poa.h:100-134) and writes past it when a
+             * sixth distinct symbol lands in one column (soft-masked FASTA, IUPAC codes, proteins); here the
+             * read is refused instead of corrupting the graph. */
+            if (c->mm_num >= POA_MM_MAX) { overflow = 1; break; }
             c->mm_num++;
             c->mm[c->mm_num - 1] = seq[num2];
             nn->mm_num = c->mm_num;
@@ -381,6 +386,7 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
         if (P_sub == -1) ended_at_sentinel = 1;
     }
     (void)ended_at_sentinel;
+    if (overflow) { free(seq); return -1; }     /* (the graph is left half fused: the caller stops) */
     /* read bases the path never reached become a new head chain (959-972) */
     while (num2 > -1) {
         realize(g, seq[num2], num, &l, 0);
@@ -388,6 +394,7 @@ void poa_graph_fuse(poa_graph* g, const char* b, int num, const poa_step* path, 
     }
     g->len += l;
     free(seq);
+    return 0;
 }
 
 /* ------------------------------------------------------------------------------------------

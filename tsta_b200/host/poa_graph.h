@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#define POA_MM_MAX 4        /* reference: mismatch_node[4] -- at most five alternatives per alignment column */
 #define POA_SENTINEL (-1)   /* virtual predecessor of a head node (reference: `init`, sub == -1) */
 
 typedef struct {
@@ -28,7 +29,7 @@ typedef struct {
     int pre_cap;
     int* next;      /* successor node ids, append order */
     int out, next_cap;
-    int mm[4];      /* other members of this node's mismatch group */
+    int mm[POA_MM_MAX];   /* other members of this node's mismatch group */
     int mm_num;
     unsigned char base;
     int sub;        /* row index in the current topological order */
@@ -88,8 +89,9 @@ void poa_csr_free(poa_csr* c);
 int poa_graph_pick_start(const poa_graph* g, const int32_t* lastsorce);
 
 /* Fuse read `num` (0-based record index) along `path` (nsteps steps, from the end of the read
- * backwards, as walked).  Mirrors node_fuse(). */
-void poa_graph_fuse(poa_graph* g, const char* read, int num, const poa_step* path, int nsteps);
+ * backwards, as walked).  Mirrors node_fuse().  Returns 0, or -1 when a column would collect more than
+ * POA_MM_MAX + 1 distinct symbols (the reference overflows mismatch_node[4] there). */
+int poa_graph_fuse(poa_graph* g, const char* read, int num, const poa_step* path, int nsteps);
 
 /* t_sort(): `final` != 0 runs the consensus variant (toposort1 + modify). */
 void poa_graph_sort(poa_graph* g, int final);

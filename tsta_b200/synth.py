@@ -78,3 +78,17 @@ def read_pair(length_a: int, length_b: int, seed: int, divergence: float | None 
     else:
         b = mutate(a, divergence, seed)
     return a, b
+
+
+def random_bulk(count: int, seed: int) -> np.ndarray:
+    """`count` uniform random ACGT bases as a uint8 array, for the batch workloads (1e8..1e9 bases):
+    numpy's PCG64 stream instead of the xorshift64* lanes above, which generate ~20 MB/s."""
+    if count <= 0:
+        return np.zeros(0, dtype=np.uint8)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = np.empty(count, dtype=np.uint8)
+    step = 1 << 26
+    for o in range(0, count, step):
+        k = min(step, count - o)
+        out[o:o + k] = _ACGT[rng.integers(0, 4, size=k, dtype=np.uint8)]
+    return out
