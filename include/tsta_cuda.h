@@ -99,6 +99,13 @@ int  tsta_psa_plan_info(tsta_psa_plan* plan, int* launches, int* cols_per_lane, 
 /* 1 when the last upload selected the packed int16x2 kernels (two cells per register; small
  * alphabets and score ranges, csrc/psa_fill16.cuh), 0 for the int32 kernels. */
 int  tsta_psa_plan_packed(tsta_psa_plan* plan);
+/* Traced pairs on one GPU use the CHECKPOINTED traceback (csrc/psa_fill16.cuh): a score-only fill that saves
+ * the lane registers every 128 wavefront steps, then the traced form of the tiles in a corridor around the
+ * path, then the walk; a walk that leaves its corridor is resumed in a new one.  This reports the last run:
+ * corridors used (1 = the first one sufficed; 0 = another traceback mode ran) and tiles re-run in total.
+ * Environment (experiments / tests): TSTA_PSA_TRACE_MODE=full keeps the direction words of the whole matrix,
+ * TSTA_PSA_CORRIDOR=<columns> the corridor's margin (default 2048, at least 1024), TSTA_PSA_TILE_BUDGET_MB. */
+int  tsta_psa_plan_trace_stats(tsta_psa_plan* plan, int* corridors, long long* tiles, long long* tiles_of_matrix);
 /* diagnostics: with TSTA_PSA_TIMELINE=1 in the environment every band of the last run left 8 globaltimer
  * stamps (ns): entry, first boundary rows in, start of chunks 1..5, end; then stale polls, cycles spent
  * importing the left boundary, number of imports.  out = [bands][16]. */

@@ -142,3 +142,76 @@ def test_dual_pair_mode_with_traceback(gpu, env, lens):
             assert (r.maxsorce[k], r.corner[k]) == (o.maxsorce, o.corner), (k, len(x), len(y), prm)
             assert r.output_bytes(k) == o.output_bytes(), (k, len(x), len(y), prm)
             assert r1.output_bytes(k) == o.output_bytes()
+
+
+@pytest.fixture
+def trace_env():
+    keys = ("TSTA_PSA_TRACE_MODE", "TSTA_PSA_CORRIDOR", "TSTA_PSA_TILE_BUDGET_MB", "TSTA_PSA_C16")
+    saved = {k: os.environ.get(k) for k in keys}
+    yield os.environ
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def _traced(gpu, x, y, prm=(2, -5, -2, -4)):
+    plan = gpu.PsaPlan(True)
+    plan.upload(x, y, *prm)
+    plan.run()
+    r = plan.fetch()
+    st = plan.trace_stats()
+    plan.close()
+    return r, st
+
+
+def test_checkpointed_traceback_leaves_and_reenters_corridor(gpu, trace_env):
+    """A 3000-base deletion moves the path 3000 columns sideways: the walk leaves the first corridor
+    (margin 1024) and is resumed in new ones; the alignment is the oracle's byte for byte."""
+    trace_env["TSTA_PSA_CORRIDOR"] = "1024"
+    x = synth.random_read(20_000, 71)
+    y = x[:8_000] + x[11_000:]
+    o = ob.psa(x, y)
+    r, st = _traced(gpu, x, y)
+    assert (r.maxsorce, r.corner) == (o.maxsorce, o.corner)
+    assert r.output_bytes() == o.output_bytes()
+    assert st["corridors"] >= 2 and st["tiles"] < st["tiles_of_matrix"]
+    # an insertion instead (the path moves up), and both in one pair
+    y2 = x[:5_000] + synth.random_read(2_500, 72) + x[5_000:14_000] + x[16_500:]
+    o2 = ob.psa(x, y2)
+    r2, st2 = _traced(gpu, x, y2)
+    assert r2.output_bytes() == o2.output_bytes() and st2["corridors"] >= 2
+
+
+def test_checkpointed_traceback_tile_budget(gpu, trace_env):
+    """A tile budget far below one corridor: the walk is resumed stage after stage."""
+    trace_env["TSTA_PSA_TILE_BUDGET_MB"] = "16"
+    for c16 in ("2", "3", "6"):
+        trace_env["TSTA_PSA_C16"] = c16
+        x, y = synth.read_pair(30_000, 29_000, 81, 0.1)
+        o = ob.psa(x, y)
+        r, st = _traced(gpu, x, y)
+        assert r.output_bytes() == o.output_bytes() and r.maxsorce == o.maxsorce
+        assert st["corridors"] >= 2
+
+
+@pytest.mark.parametrize("mode", ["full", "ckpt"])
+def test_trace_modes_agree_with_oracle(gpu, trace_env, mode):
+    """Both traceback modes of the packed kernels (direction words of the whole matrix / checkpoints +
+    corridor) against the oracle, every strip width, linear and affine gaps, ragged shapes."""
+    if mode == "full":
+        trace_env["TSTA_PSA_TRACE_MODE"] = "full"
+    rnd = random.Random(7)
+    for c16 in (2, 3, 4, 6, 8):
+        trace_env["TSTA_PSA_C16"] = str(c16)
+        band = 64 * c16
+        for k, (la, lb) in enumerate([(1, 1), (band + 1, 70), (3 * band + 17, 300), (1500, 1400), (700, 699), (5000, 4100)]):
+            x, y = synth.read_pair(la, lb, 500 + 10 * c16 + k, rnd.choice([None, 0.05, 0.2]))
+            y = y or b"G"
+            for prm in [(2, -5, -2, -4), (2, -5, -2, 0)]:
+                o = ob.psa(x, y, *prm)
+                r, st = _traced(gpu, x, y, prm)
+                assert (r.maxsorce, r.corner) == (o.maxsorce, o.corner), (mode, c16, la, lb, prm)
+                assert r.output_bytes() == o.output_bytes(), (mode, c16, la, lb, prm)
+                assert (st["corridors"] >= 1) == (mode == "ckpt")

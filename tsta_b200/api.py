@@ -211,6 +211,14 @@ class PsaPlan:
         return {"launches": a.value, "cols_per_lane": b.value, "bands": c.value,
                 "packed": bool(load().tsta_psa_plan_packed(self._h))}
 
+    def trace_stats(self):
+        """Checkpointed traceback of the last run: corridors used, tiles re-run, tiles of the whole matrix."""
+        a, b, c = C.c_int(), C.c_longlong(), C.c_longlong()
+        L = load()
+        L.tsta_psa_plan_trace_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.tsta_psa_plan_trace_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"corridors": a.value, "tiles": b.value, "tiles_of_matrix": c.value}
+
     def close(self) -> None:
         if self._h:
             load().tsta_psa_plan_destroy(self._h)

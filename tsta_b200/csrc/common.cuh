@@ -79,6 +79,15 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Checkpointed traceback of one long pair (psa_fill16.cuh / psa_trace.cuh): direction words exist only
+// for TILES = (band, range of 128 wavefront steps).  One row of the tile table describes the tiles of
+// one step range: bands [bmin, bmax] in consecutive slots starting at slot0; bmin > bmax = none.
+struct PsaTileRow {
+    int bmin, bmax;
+    long long slot0;
+};
+constexpr int kTileSteps = 128;
+
 // ---------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------

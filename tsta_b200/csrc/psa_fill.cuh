@@ -143,6 +143,13 @@ struct PsaBand {
     int* abort_flag = nullptr;          // see PsaPairArgs
     unsigned long long timeout_ns = 0;
     unsigned long long* timeline = nullptr;
+    // checkpointed traceback (psa_fill16.cuh): chunk range of this sweep, the checkpoints the score-only
+    // pass leaves behind, the checkpoint a retrace sweep resumes from
+    int ch_begin = 0, ch_end = INT_MAX;
+    uint32_t* ckpt_out = nullptr;        // this band's checkpoints [k][words][32 lanes] (k = step / 128, k >= 1)
+    const uint32_t* ckpt_in = nullptr;   // the checkpoint of chunk ch_begin, in the score-only pass's form
+    bool bnd_unscaled = false;           // traced sweep over boundary columns a score-only pass wrote
+    long long dir_step0 = 0;             // TM 2: `dirs` starts at this step
 };
 
 // Fills the 256-entry byte -> substitution-table map (PRMT mode).
@@ -428,6 +435,8 @@ struct PsaPairArgs {
     int* abort_flag;
     unsigned long long timeout_ns;
     unsigned long long* timeline;   // optional (TSTA_PSA_TIMELINE=1): 8 globaltimer stamps per band, see tools/timeline.py
+    uint32_t* ckpt;                 // optional: lane-register checkpoints every 128 steps, [band][k][words][32] (psa_fill16.cuh)
+    long long ckpt_band_words;
 };
 
 template <int C, bool TRACE, bool PRMT, int CH>

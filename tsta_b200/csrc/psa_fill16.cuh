@@ -60,6 +60,18 @@
 //     WE  = max(Et + 4E+1, T2)     WF = max(Fin + 4E+1, T2)      bit 0 = we / wf
 // = 14.5 ALU-pipe instructions against 17.5 of the TM == 1 form.
 //
+// Checkpointed traceback (the default for one long pair on one GPU).  A traced cell costs 14.5
+// ALU-pipe instructions against 6.5 score-only, and a traceback visits ~2(n+m) of the n*m cells.  So the
+// whole matrix is filled SCORE-ONLY (TM 0) while every band saves its lane registers every 128 steps
+// (kCkptWords<C> words per lane: H and E state of the lane's C columns, the diagonal input, the right-edge
+// hand-off pair, the warp's base) next to the boundary columns the bands exchange anyway.  Any TILE
+// = (band, 128 steps) can then be re-run on its own in the traced form (TM 2): psa_retrace16_kernel
+// resumes the sweep from the tile's checkpoint, takes the left boundary from the stored column, and
+// writes the tile's direction words.  Only the tiles in a corridor around the path are re-run (a few
+// per cent of the matrix, all independent -> the whole GPU works on them), and if the walk leaves the
+// corridor the host re-centres it and resumes (tsta_psa.cu).  The score-only state converts exactly:
+// scores times four; a gap state carried minus (O+E) is "opened" iff it equals the H it was derived from.
+//
 // Ramp-in without masks (CK == 2): the rows above row 0 that the skewed lanes would "work on"
 // during the first 63 steps are made FIXED POINTS of the recurrence -- their substitution table
 // holds -128 for every symbol, every lane starts with the right-edge values of row -1 in its
@@ -76,6 +88,8 @@ namespace tsta {
 constexpr int kRing16 = 128;          // row-table ring (rows)
 constexpr uint32_t kMin16x2 = 0x80008000u;
 constexpr int kDirSteps = 128;        // TRACE: ring of per-step direction words (steps)
+constexpr int kCkptChunks = kTileSteps / 32;          // checkpoint every 4 chunks of 32 steps
+template <int C> constexpr int kCkptWords = 2 * C + 4;   // per lane: Hup[C], Et[C], diag, Hout, Fout, base
 
 __device__ __forceinline__ uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
@@ -504,6 +518,28 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         L.Fout = pack16(Fa - base, Fh - base);
     }
     int ms32 = INT_MIN;
+    const int t_begin = b.ch_begin * CH;
+    if constexpr (TM == 2) {
+        if (b.ckpt_in) {
+            // resume from the score-only pass's lane registers at the start of chunk ch_begin: scores times four;
+            // a gap state (carried minus O+E there) is "opened" iff it equals the H it was derived from
+            const uint32_t* ck = b.ckpt_in + lane;
+            const uint32_t oe1 = dup16(sc.O + sc.E);
+            auto up4 = [](uint32_t h) { return (h & 0x3fff3fffu) << 2; };
+            auto gap4 = [&](uint32_t g, uint32_t h) { return vadd2(up4(vadd2(g, oe1)), __vcmpeq2(g, h) & kM2); };
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const uint32_t h = __ldcs(ck + c * 32), e = __ldcs(ck + (C + c) * 32);
+                L.Hup[c] = up4(h);
+                L.Et[c] = gap4(e, h);
+            }
+            const uint32_t ho = __ldcs(ck + (2 * C + 1) * 32), fo = __ldcs(ck + (2 * C + 2) * 32);
+            L.diag = up4(__ldcs(ck + 2 * C * 32));
+            L.Hout = up4(ho);
+            L.Fout = gap4(fo, ho);
+            base = 4 * (int)__ldcs(ck + (2 * C + 3) * 32);
+        }
+    }
 
     const int nsteps = m + 63;                                   // virtual lane 63 finishes row m-1 at step m+62
     const int nchunks = (nsteps + CH - 1) / CH;
@@ -526,16 +562,23 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     // ---- prologue: row tables of chunk 0; prefetch for chunk 1 / boundary of chunk 0 -----------
     __syncwarp();
     const bool stager = lane < CH;
-    // rows above row 0 (read by lanes whose first row is still to come): the fixed-point table
-    sm.rowring[kRing16 - 32 + lane] = make_uint2(kFakeTab, kFakeTab);
-    if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, kFakeTab));   // rows < 32: no high row yet
-    uint32_t raw_next = (stager && CH + lane < m) ? b.s1[CH + lane] : 0xffffffffu;
+    if (t_begin == 0) {
+        // rows above row 0 (read by lanes whose first row is still to come): the fixed-point table
+        sm.rowring[kRing16 - 32 + lane] = make_uint2(kFakeTab, kFakeTab);
+        if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, kFakeTab));   // rows < 32: no high row yet
+    } else {
+        // resumed sweep (t_begin >= 128): the steps of the first chunk read the entries of rows t_begin-31 .. t_begin+31
+        const int ra = t_begin - 32 + lane, rb = t_begin + lane;
+        ring16_put(sm, ra, make_uint2(ra < m ? tab4[b.s1[ra]] : 0u, ra - 32 < m ? tab4[b.s1[ra - 32]] : 0u));
+        ring16_put(sm, rb, make_uint2(rb < m ? tab4[b.s1[rb]] : 0u, rb - 32 < m ? tab4[b.s1[rb - 32]] : 0u));
+    }
+    uint32_t raw_next = (stager && t_begin + CH + lane < m) ? b.s1[t_begin + CH + lane] : 0xffffffffu;
     // left boundary: PIPE imports it in groups of G rows (lanes 0..G-1 hold the group that is consumed
     // next); sequential mode (batches) reads whole chunks of its own parked column
     unsigned long long bnd_next = 0;
-    if (import_left && (PIPE ? lane < G : stager) && lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + lane);
+    if (import_left && (PIPE ? lane < G : stager) && t_begin + lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + t_begin + lane);
     __syncwarp();
-    L.Tnext = sm.rowring[(0 - lane) & (kRing16 - 1)];            // table of this lane's row at step 0 (row -lane)
+    L.Tnext = sm.rowring[(t_begin - lane) & (kRing16 - 1)];      // table of this lane's row at the first step (row t_begin - lane)
 
     // PIPE: make rows [row0, row0 + G) of the left boundary available in sm.in[slot0 ..] and prefetch the next group
     auto import_group = [&](const int row0, const int slot0, const int cur_base) {
@@ -557,7 +600,14 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             }
         }
         // absolute modulo 2^16 -> relative to this warp's base (score-only: Ft = Fg - (O+E))
-        if (mine) sm.in[slot0 + lane] = vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE));
+        if (TM == 2 && b.bnd_unscaled) {
+            // the column was written by the score-only pass (unscaled H | Fg): times four, and Fg is "opened"
+            // iff it equals H + O + E
+            const uint32_t raw = (uint32_t)bnd_next;
+            const uint32_t rel = vadd2(raw, dup16(-(cur_base >> 2)));
+            const uint32_t opened = (((raw >> 16) - raw - (uint32_t)(sc.O + sc.E)) & 0xffffu) == 0u ? 0x00020000u : 0u;
+            if (mine) sm.in[slot0 + lane] = ((rel & 0x3fff3fffu) << 2) + opened;
+        } else if (mine) sm.in[slot0 + lane] = vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE));
         __syncwarp();
         if (lane < G && row + G < m) bnd_next = ld_relaxed_u64(b.bnd_in + row + G);
         if (b.timeline && lane == 0) {   // diagnostics: polls that found stale rows, cycles spent importing, imports
@@ -575,7 +625,8 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         }
     };
     stamp(0);
-    for (int ch = 0; ch < nchunks; ch++) {
+    const int ch_last = min(nchunks, b.ch_end);
+    for (int ch = b.ch_begin; ch < ch_last; ch++) {
         const int t0 = ch * CH;
         if (ch >= 1 && ch <= 5) stamp(1 + ch);                      // 2..6: start of chunks 1..5
         // ---- re-centre on lane 0's current row -------------------------------------------------
@@ -591,6 +642,18 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             L.Fout = vadd2(L.Fout, nd);
             L.ms = kMin16x2;
             base += delta;
+        }
+        // ---- checkpoint (score-only pass of a traced pair): lane registers at the start of every 128th step ----
+        if constexpr (TM == 0 && PIPE && CH == 32) {
+            if (b.ckpt_out && ch > 0 && (ch % kCkptChunks) == 0) {
+                uint32_t* ck = b.ckpt_out + (size_t)(ch / kCkptChunks) * (kCkptWords<C> * 32) + lane;
+#pragma unroll
+                for (int c = 0; c < C; c++) { __stcs(ck + c * 32, L.Hup[c]); __stcs(ck + (C + c) * 32, L.Et[c]); }
+                __stcs(ck + 2 * C * 32, L.diag);
+                __stcs(ck + (2 * C + 1) * 32, L.Hout);
+                __stcs(ck + (2 * C + 2) * 32, L.Fout);
+                __stcs(ck + (2 * C + 3) * 32, (uint32_t)base);
+            }
         }
         // ---- stage: next chunk's row tables, this chunk's left boundary -------------------------
         {
@@ -619,7 +682,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         const uint32_t ring_next = ring_addr + (((t0 + 1 - lane) & (kRing16 - 1)) << 3);
         unsigned long long* bnd_row = b.bnd_out + (t0 - 63);
         const uint32_t dir_addr = dirw_addr + (t0 & (kDirSteps - 1)) * (C == 8 ? 256 : 128);
-        uint32_t* const dir_g = TM == 2 ? dir_lane + (long long)t0 * (C > 4 ? 64 : 32) : nullptr;
+        uint32_t* const dir_g = TM == 2 ? dir_lane + ((long long)t0 - b.dir_step0) * (C > 4 ? 64 : 32) : nullptr;
         const bool groups = import_left && PIPE;
 
         if (t0 + CH - 1 < m && (t0 >= 63 || fast_ramp)) {
@@ -868,6 +931,7 @@ __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ 
     b.dirs = TM == 2 ? a.dirs + (long long)band * a.dirs_stride : a.dirs;
     b.dirs_stride = a.dirs_stride;
     b.lastrow = a.lastrow; b.lastrow_col0 = 0;
+    b.ckpt_out = (TM == 0 && a.ckpt) ? a.ckpt + (long long)band * a.ckpt_band_words : nullptr;
     int ms = psa_sweep_band16<C, TM, true, CH>(b, a.sc, tab4, sm, lane);
     ms = warp_max(ms);
     if (lane == 0) atomicMax(a.out_max, ms);
@@ -878,6 +942,62 @@ __global__ void __launch_bounds__(32) psa_pair16_kernel(const __grid_constant__ 
 // (C > 4: word 0 = virtual lane k, word 1 = virtual lane k+32).  Row r of virtual lane v is in step r + v.
 __host__ __device__ inline long long psa_skew_steps(long long m) { return (m + 63 + 31) & ~31LL; }   // whole chunks: every step of every chunk stores
 __host__ __device__ inline long long psa_skew_band_bytes(long long m, int C) { return psa_skew_steps(m) * 32 * (C > 4 ? 8 : 4); }
+
+// Checkpointed traceback: geometry of the checkpoints and of the tiles' direction words.
+__host__ __device__ inline long long psa_tile_rows(long long m) { return (psa_skew_steps(m) + kTileSteps - 1) / kTileSteps; }
+__host__ __device__ inline long long psa_ckpt_band_words(long long m, int C) { return psa_tile_rows(m) * (2 * C + 4) * 32; }
+__host__ __device__ inline long long psa_tile_bytes(int C) { return (long long)kTileSteps * 32 * (C > 4 ? 8 : 4); }
+
+struct PsaRetraceArgs {
+    PsaScoring sc;
+    const uint8_t* s0;
+    const uint8_t* s1;
+    int n, m, nbands;
+    const unsigned long long* bnd;   // boundary columns of the score-only pass (all rows present, tagged `epoch`)
+    long long bnd_stride;
+    unsigned epoch;
+    const uint32_t* ckpt;
+    long long ckpt_band_words;
+    const PsaTileRow* rows;          // [nrows] tile table (one row per 128-step range)
+    int nrows;
+    uint8_t* dirs;                   // slot s holds psa_tile_bytes(C) bytes: [step & 127][lane] words
+    int* abort_flag;
+    unsigned long long timeout_ns;
+};
+
+// One warp (= one CTA) per tile: blockIdx.y picks the step range (last range first: the walk starts there),
+// blockIdx.x the band inside the range's corridor.
+template <int C>
+__global__ void __launch_bounds__(32) psa_retrace16_kernel(const __grid_constant__ PsaRetraceArgs a)
+{
+    __shared__ PsaWarpSmem16<C, false> sm;
+    __shared__ uint32_t tab4[256];
+    const int lane = threadIdx.x;
+    const int k = a.nrows - 1 - (int)blockIdx.y;
+    const PsaTileRow row = a.rows[k];
+    const int band = row.bmin + (int)blockIdx.x;
+    if (band > row.bmax) return;
+    psa_build_tab4(tab4, a.sc, 4, lane, 32);
+    __syncwarp();
+
+    PsaBand b;
+    b.s0 = a.s0; b.s1 = a.s1; b.n = a.n; b.m = a.m;
+    b.band = band; b.nbands = a.nbands;
+    b.col_off = 0;
+    b.has_left = false; b.has_right = false;
+    b.bnd_in = band == 0 ? nullptr : a.bnd + (long long)(band - 1) * a.bnd_stride;
+    b.bnd_out = nullptr;
+    b.epoch = a.epoch;
+    b.abort_flag = a.abort_flag; b.timeout_ns = a.timeout_ns; b.timeline = nullptr;
+    b.dirs = a.dirs + (row.slot0 + blockIdx.x) * psa_tile_bytes(C);
+    b.dirs_stride = 0;
+    b.dir_step0 = (long long)k * kTileSteps;
+    b.lastrow = nullptr; b.lastrow_col0 = 0;
+    b.ch_begin = k * kCkptChunks; b.ch_end = b.ch_begin + kCkptChunks;
+    b.ckpt_in = k > 0 ? a.ckpt + (long long)band * a.ckpt_band_words + (long long)k * (kCkptWords<C> * 32) : nullptr;
+    b.bnd_unscaled = true;
+    psa_sweep_band16<C, 2, true, 32>(b, a.sc, tab4, sm, lane);
+}
 
 // ---------------------------------------------------------------------------------------
 // a batch of independent pairs: persistent warps, one pair at a time per warp

@@ -38,6 +38,13 @@ struct PsaTraceArgs {
     long long skew_band_bytes;
     long long skew_steps;
     int skew_bands;
+    // checkpointed traceback: direction words exist for the tiles of this table only (common.cuh: PsaTileRow);
+    // NULL = the whole matrix is there, band after band (skew_band_bytes)
+    const PsaTileRow* tile_rows;
+    long long tile_bytes;
+    int start_nops;          // moves already written by an earlier walk of the same alignment
+    // out[5] (status): 0 = the walk reached row -1 or column -1; 1 = it ran into cells without direction words:
+    // out[0..3] then describe the entry of the last window it could stage, from where the walk can be resumed
 };
 
 // `back` bits of a packed code -> move (1 diagonal, 0 left, 2 up) for either encoding
@@ -238,6 +245,18 @@ struct PsaSkewGeom {
     static constexpr int kSmemBytes = 2 * kTraceBufStride + kRawBytes;
 };
 
+// Direction words of (band b, step t): one line of 32 lanes, or NULL when they do not exist.
+template <int C>
+__device__ __forceinline__ const uint4* psa_skew_line(const PsaTraceArgs& a, int b, long long t)
+{
+    using G = PsaSkewGeom<C>;
+    if (b >= a.skew_bands || t >= a.skew_steps) return nullptr;
+    if (!a.tile_rows) return reinterpret_cast<const uint4*>(a.dirs + (long long)b * a.skew_band_bytes + t * G::kLineBytes);
+    const PsaTileRow r = a.tile_rows[t / kTileSteps];
+    if (b < r.bmin || b > r.bmax) return nullptr;
+    return reinterpret_cast<const uint4*>(a.dirs + (r.slot0 + (b - r.bmin)) * a.tile_bytes + (t % kTileSteps) * G::kLineBytes);
+}
+
 template <int C>
 __device__ __forceinline__ void psa_skew_place(int i, int j, int& R0, int& C0)
 {
@@ -253,7 +272,6 @@ __device__ __forceinline__ void psa_skew_stage(const PsaTraceArgs& a, uint8_t* b
                                                int tid, int nthreads, int bar_id)
 {
     using G = PsaSkewGeom<C>;
-    const long long T = a.skew_steps;
     const int b0 = C0 / G::kBandCols;
     // ---- phase 1: raw stripes.  Band b of the window needs virtual lanes [vlo, vhi] and steps R0+vlo .. R0+127+vhi
     int line0 = 0;
@@ -266,14 +284,33 @@ __device__ __forceinline__ void psa_skew_stage(const PsaTraceArgs& a, uint8_t* b
         const int nlines = kTraceRows + vhi - vlo;
         const long long tlo = (long long)R0 + vlo;
         const int units = nlines * (G::kLineBytes / 16);
-        const uint4* src = reinterpret_cast<const uint4*>(a.dirs + (long long)b * a.skew_band_bytes + tlo * G::kLineBytes);
         uint4* dst = reinterpret_cast<uint4*>(raw + (size_t)line0 * G::kLineBytes);
-        const bool have = b < a.skew_bands;
-        for (int u = tid; u < units; u += nthreads) {
-            const long long t = tlo + u / (G::kLineBytes / 16);
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (have && t < T) v = __ldcs(src + u);
-            dst[u] = v;
+        constexpr int kUnitsPerLine = G::kLineBytes / 16;
+        // the stripe (at most 128 + 63 steps) touches at most three step ranges: their first lines are looked up
+        // once, so that the loads below do not wait for a table entry each
+        const long long k0 = tlo / kTileSteps;
+        const uint4* first[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) first[q] = psa_skew_line<C>(a, b, (k0 + q) * kTileSteps);
+        // all loads of a batch are issued before the first is stored: a stripe costs about one HBM round trip
+        constexpr int kBatch = 6;
+        for (int u0 = tid; u0 < units; u0 += kBatch * nthreads) {
+            uint4 v[kBatch];
+#pragma unroll
+            for (int e = 0; e < kBatch; e++) {
+                const int u = u0 + e * nthreads;
+                const long long t = tlo + u / kUnitsPerLine;
+                const int q = (int)(t / kTileSteps - k0);
+                const uint4* src = q == 0 ? first[0] : (q == 1 ? first[1] : first[2]);
+                // (cells without direction words read as code 0, which no fill produces: the walker stops on them)
+                v[e] = make_uint4(0, 0, 0, 0);
+                if (u < units && src && t < a.skew_steps) v[e] = __ldcs(src + (t % kTileSteps) * kUnitsPerLine + u % kUnitsPerLine);
+            }
+#pragma unroll
+            for (int e = 0; e < kBatch; e++) {
+                const int u = u0 + e * nthreads;
+                if (u < units) dst[u] = v[e];
+            }
         }
         line0 += nlines;
     }
@@ -308,9 +345,6 @@ __device__ __forceinline__ void psa_skew_stage(const PsaTraceArgs& a, uint8_t* b
             if (G::kWords == 1) w = (v >> 5) ? (w >> 16) : (w & 0xffffu);
             constexpr uint32_t kPiece = 4 * C < 32 ? (1u << ((4 * C) & 31)) - 1u : 0xffffffffu;   // 4C bits
             w &= kPiece;
-            // a tag of 0 never comes out of a fill; turn it into a diagonal so that even a corrupt
-            // matrix (or the zero fill outside it) cannot stall the walk
-            w |= (~(w | (w >> 1)) & (0x11111111u & kPiece)) * 3u;
             acc |= (unsigned long long)w << fill;
             fill += 4 * C;
             if (fill >= 32) {
@@ -322,27 +356,37 @@ __device__ __forceinline__ void psa_skew_stage(const PsaTraceArgs& a, uint8_t* b
     }
 }
 
+// The walker's warp has an SM sub-partition to itself: warps 4, 8, 12 (which would share warp 0's scheduler)
+// only wait at the barriers, the other nine stage windows.
+constexpr int kSkewWarps = 13;
+constexpr int kSkewThreads = 32 * kSkewWarps;
+constexpr int kSkewStagers = 32 * 9;
+
 template <int C>
-static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(const PsaTraceArgs a)
+static __global__ void __launch_bounds__(kSkewThreads) psa_trace_skew_kernel(const PsaTraceArgs a)
 {
     using G = PsaSkewGeom<C>;
     extern __shared__ __align__(16) uint8_t trace_smem[];      // two window buffers (each behind an apron), then the raw stripes
-    __shared__ int s_i, s_j, s_arr, s_nops;
+    __shared__ int s_i, s_j, s_arr, s_nops, s_status;
     uint8_t* const raw = trace_smem + 2 * kTraceBufStride;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const bool stager = warp > 0 && (warp & 3) != 0;
+    const int stid = (warp - 1 - (warp >> 2)) * 32 + (tid & 31);   // 0 .. kSkewStagers-1 over the staging warps
 
     if (tid == 0) {
         s_i = a.start_i;
         s_j = a.start_j;
         s_arr = a.start_forced ? a.start_forced : 3;           // how the walk entered the start cell: 3 free, 2 by a left move, 1 by an up move
-        s_nops = 0;
+        s_nops = a.start_nops;
+        s_status = 0;
     }
     __syncthreads();
     int cur = 0, R0, C0;
     long long dbg_walk = 0, dbg_total0 = clock64();
     int dbg_windows = 0, dbg_hits = 0;
     psa_skew_place<C>(s_i, s_j, R0, C0);
-    psa_skew_stage<C>(a, trace_smem + kTraceApron, raw, R0, C0, tid, kTraceThreads, 1);
+    if (stager) psa_skew_stage<C>(a, trace_smem + kTraceApron, raw, R0, C0, stid, kSkewStagers, 1);
     __syncthreads();
 
     while (true) {
@@ -351,9 +395,9 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(co
         // where the path is expected to leave this window: through the top, about one column per row
         int NR0, NC0;
         psa_skew_place<C>(R0 - 1, max(0, j0 - (i0 - R0 + 1) + G::kWinCols / 4), NR0, NC0);
-        if (tid >= 32) {
+        if (stager) {
             if (R0 > 0) psa_skew_stage<C>(a, trace_smem + kTraceApron + (cur ^ 1) * kTraceBufStride, raw, NR0, NC0,
-                                           tid - 32, kTraceThreads - 32, 2);
+                                           stid, kSkewStagers, 1);
         } else if (tid == 0) {
             const long long dbg_t0 = clock64();
             dbg_windows++;
@@ -364,6 +408,7 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(co
             const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
             unsigned sh = 4u - mvp, nf = 6u >> mvp;
             uint8_t* out = a.ops + nops;
+            unsigned bad = 0;                                  // sign bit: a code without a back tag was read (no direction words there)
             while (i >= R0 && j >= C0) {
                 const int j16 = j & ~15;
                 const uint32_t colbase = win_s + (uint32_t)((j16 - C0) >> 1);
@@ -386,6 +431,7 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(co
                         unsigned f, mv, um;
                         asm volatile("lop3.b32 %0, %1, %2, 1, 0x80;" : "=r"(f) : "r"(c >> sh), "r"(nf));        // (c >> sh) & nf & 1
                         const unsigned c3 = c & 3u;
+                        bad |= c3 - 1u;
                         asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(mv) : "r"(f), "r"(mvp - c3), "r"(c3));   // f ? mvp : c3, no predicate
                         asm volatile("bfe.s32 %0, %1, 0, 1;" : "=r"(um) : "r"(mv));                               // 0 - (mv & 1): up / diagonal
                         out[s] = (uint8_t)mv;                        // tags; the host maps them to 1 / 0 / 2
@@ -400,16 +446,19 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(co
                         nf = 6u >> mv;
                     }
                     out += safe;
-                    safe = (q | pos) < 0 ? 0 : min(q / kTraceBytes, pos >> 2) + 1;
+                    safe = ((q | pos) < 0 || (int)bad < 0) ? 0 : min(q / kTraceBytes, pos >> 2) + 1;
                 }
+                if ((int)bad < 0) break;
                 i -= (q0 - q) / kTraceBytes;
                 j = j16 + (pos >> 2);
             }
             nops = (unsigned)(out - a.ops);
-            s_i = i; s_j = j; s_arr = (int)mvp; s_nops = (int)nops;
+            if ((int)bad < 0) s_status = 1;                    // (s_i, s_j, s_arr, s_nops keep describing the entry of this window)
+            else { s_i = i; s_j = j; s_arr = (int)mvp; s_nops = (int)nops; }
             dbg_walk += clock64() - dbg_t0;
         }
         __syncthreads();
+        if (s_status) break;
         const int i1 = s_i, j1 = s_j;
         if (i1 < 0 || j1 < 0) break;
         if (R0 > 0 && i1 >= NR0 && i1 < NR0 + kTraceRows && j1 >= NC0 && j1 < NC0 + G::kWinCols) {
@@ -417,7 +466,7 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(co
             dbg_hits++;
         } else {
             psa_skew_place<C>(i1, j1, R0, C0);
-            psa_skew_stage<C>(a, trace_smem + kTraceApron + cur * kTraceBufStride, raw, R0, C0, tid, kTraceThreads, 1);
+            if (stager) psa_skew_stage<C>(a, trace_smem + kTraceApron + cur * kTraceBufStride, raw, R0, C0, stid, kSkewStagers, 1);
         }
         __syncthreads();
     }
@@ -426,6 +475,7 @@ static __global__ void __launch_bounds__(kTraceThreads) psa_trace_skew_kernel(co
         a.out[1] = s_i;
         a.out[2] = s_j;
         a.out[3] = s_arr == 3 ? 0 : s_arr;
+        a.out[5] = s_status;
         if (a.dbg) {
             a.dbg[0] = dbg_walk; a.dbg[1] = clock64() - dbg_total0; a.dbg[2] = dbg_windows; a.dbg[3] = dbg_hits;
         }

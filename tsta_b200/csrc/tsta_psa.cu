@@ -105,6 +105,17 @@ struct tsta_psa_plan {
     bool packed = false;           // int16 x 2 kernels (psa_fill16.cuh); else int32 (psa_fill.cuh)
     int scale = 1;                 // score scale of the device results (1 score-only, 2 int32 traced, 4 packed traced)
     bool skew = false;             // traced + packed: skewed direction layout, 2-bit moves (psa_trace_skew_kernel)
+    // traced + packed + whole pair on this GPU: checkpointed traceback (psa_fill16.cuh) -- score-only fill that
+    // leaves checkpoints, then the traced form of the tiles in a corridor around the path, then the walk
+    bool ckpt = false;
+    int64_t corridor_w = 2048;     // columns added on both sides of the expected path
+    long long max_slots = 0;       // tile budget of one corridor
+    long long slots = 0;           // tiles of the current corridor
+    int rounds = 0;                // corridors the last run needed (1 = the walk never left the first one)
+    long long tiles_run = 0;       // tiles re-run by the last run, all corridors
+    DevBuf d_ckpt, d_tilerows;
+    PsaTileRow* h_rows = nullptr;  // pinned, [rows_cap]
+    size_t rows_cap = 0;
     // column slice of a pair spread over several GPUs (tsta_psa_plan_upload_slice)
     int64_t col0 = 0, n_total = 0;
     bool has_left = false, has_right = false;
@@ -128,6 +139,8 @@ static void plan_free(tsta_psa_plan* p)
     cudaSetDevice(p->device);
     p->d_s0.release(); p->d_s1.release(); p->d_bnd.release(); p->d_ctl.release();
     p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release(); p->d_inbox.release(); p->d_timeline.release();
+    p->d_ckpt.release(); p->d_tilerows.release();
+    if (p->h_rows) cudaFreeHost(p->h_rows);
     if (p->outbox_open) cudaIpcCloseMemHandle(p->outbox);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -165,7 +178,7 @@ static cudaError_t launch_trace_skew(const PsaTraceArgs& ta, cudaStream_t st)
     // (function attributes are per device: set it on every launch, it costs nothing)
     cudaError_t e = cudaFuncSetAttribute(psa_trace_skew_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PsaSkewGeom<C>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    psa_trace_skew_kernel<C><<<1, kTraceThreads, PsaSkewGeom<C>::kSmemBytes, st>>>(ta);
+    psa_trace_skew_kernel<C><<<1, kSkewThreads, PsaSkewGeom<C>::kSmemBytes, st>>>(ta);
     return cudaGetLastError();
 }
 
@@ -198,8 +211,87 @@ struct AlignCache {
 };
 static thread_local AlignCache g_align_cache;
 
-// Traceback kernel of a plan (whole pair or one column slice), starting in the slice's last column.
-static int launch_walk(tsta_psa_plan* p, int64_t start_i, int start_state)
+// Tiles around the path of a walk that starts in (i, j), checkpointed traceback: for every range of 128 steps the
+// bands between the two straight lines the path is expected to stay near -- the diagonal through (i, j) (related
+// reads keep their offset) and the line to the origin (unrelated reads drift back to it) -- widened by W columns on
+// both sides.  Ranges are filled from the start of the walk upwards until the slot budget is used up.
+static long long build_corridor(const tsta_psa_plan* p, int64_t i, int64_t j, PsaTileRow* rows, int* k_low, int* width)
+{
+    const int K = (int)psa_tile_rows(p->m);
+    const int64_t band_cols = 64 * p->C, W = p->corridor_w;
+    long long slots = 0;
+    bool full = false;
+    *k_low = K;
+    *width = 0;
+    for (int k = K - 1; k >= 0; k--) {
+        rows[k] = PsaTileRow{1, 0, 0};
+        // rows whose cells can lie in the range's steps (step = row + virtual lane, 64 virtual lanes)
+        const int64_t r_lo = std::max<int64_t>(0, (int64_t)k * kTileSteps - 63), r_hi = std::min<int64_t>(i, (int64_t)k * kTileSteps + kTileSteps - 1);
+        if (r_lo > i || full) continue;
+        auto diag = [&](int64_t r) { return j - (i - r); };
+        auto orig = [&](int64_t r) { return j * (r + 1) / (i + 1); };
+        int64_t c_lo = std::min(diag(r_lo), orig(r_lo)) - W, c_hi = std::max(diag(r_hi), orig(r_hi)) + W;
+        c_lo = std::min(std::max<int64_t>(c_lo, 0), j);
+        c_hi = std::min(std::max<int64_t>(c_hi, 0), j);
+        const int bmin = (int)(c_lo / band_cols), bmax = (int)(c_hi / band_cols);
+        if (slots + (bmax - bmin + 1) > p->max_slots) { full = true; continue; }
+        rows[k] = PsaTileRow{bmin, bmax, slots};
+        slots += bmax - bmin + 1;
+        *k_low = k;
+        *width = std::max(*width, bmax - bmin + 1);
+    }
+    return slots;
+}
+
+template <int C>
+static void launch_retrace(const PsaRetraceArgs& ra, int width, int nranges, cudaStream_t st)
+{
+    psa_retrace16_kernel<C><<<dim3((unsigned)width, (unsigned)nranges), 32, 0, st>>>(ra);
+}
+
+static int launch_walk(tsta_psa_plan* p, int64_t start_i, int64_t start_j, int start_state, int64_t start_nops);
+
+// Checkpointed traceback: the traced form of the corridor's tiles, then the walk from (i, j).
+static int launch_corridor_walk(tsta_psa_plan* p, int64_t i, int64_t j, int state, int64_t nops)
+{
+    NvtxRange range("tsta_psa corridor");
+    const int K = (int)psa_tile_rows(p->m);
+    int k_low = K, width = 0;
+    p->slots = build_corridor(p, i, j, p->h_rows, &k_low, &width);
+    if (p->slots <= 0) return set_error(TSTA_ECUDA, "empty traceback corridor at (%lld, %lld)", (long long)i, (long long)j);
+    if ((size_t)p->slots * (size_t)psa_tile_bytes(p->C) > p->d_dirs.cap) {
+        TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        if (int rc = p->d_dirs.reserve((size_t)(p->slots + p->slots / 4) * (size_t)psa_tile_bytes(p->C))) return rc;
+    }
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_tilerows.p, p->h_rows, (size_t)K * sizeof(PsaTileRow), cudaMemcpyHostToDevice, p->stream));
+    PsaRetraceArgs ra{};
+    ra.sc = p->sc;
+    ra.s0 = p->d_s0.as<uint8_t>(); ra.s1 = p->d_s1.as<uint8_t>();
+    ra.n = (int)p->n; ra.m = (int)p->m; ra.nbands = p->nbands;
+    ra.bnd = p->d_bnd.as<unsigned long long>(); ra.bnd_stride = p->m;
+    ra.epoch = p->epoch;
+    ra.ckpt = p->d_ckpt.as<uint32_t>(); ra.ckpt_band_words = psa_ckpt_band_words(p->m, p->C);
+    ra.rows = p->d_tilerows.as<PsaTileRow>(); ra.nrows = K;
+    ra.dirs = p->d_dirs.as<uint8_t>();
+    ra.abort_flag = p->d_ctl.as<int>() + 6;
+    ra.timeout_ns = 2000000000ull;
+    const int nranges = K - k_low;
+    if (p->C == 2) launch_retrace<2>(ra, width, nranges, p->stream);
+    else if (p->C == 3) launch_retrace<3>(ra, width, nranges, p->stream);
+    else if (p->C == 4) launch_retrace<4>(ra, width, nranges, p->stream);
+    else if (p->C == 6) launch_retrace<6>(ra, width, nranges, p->stream);
+    else launch_retrace<8>(ra, width, nranges, p->stream);
+    TSTA_CUDA_TRY(cudaGetLastError());
+    p->launches++;
+    p->rounds++;
+    p->tiles_run += p->slots;
+    if (int rc = launch_walk(p, i, j, state, nops)) return rc;
+    p->launches++;
+    return TSTA_OK;
+}
+
+// Traceback kernel of a plan (whole pair or one column slice).
+static int launch_walk(tsta_psa_plan* p, int64_t start_i, int64_t start_j, int start_state, int64_t start_nops)
 {
     NvtxRange range("tsta_psa traceback");
     int* ctl = p->d_ctl.as<int>();
@@ -210,12 +302,17 @@ static int launch_walk(tsta_psa_plan* p, int64_t start_i, int start_state)
     ta.ops = p->d_ops.as<uint8_t>();
     ta.out = ctl + 2;
     ta.enc = p->packed ? 1 : 0;
-    ta.start_i = (int)start_i; ta.start_j = (int)p->n - 1; ta.start_forced = start_state;
+    ta.start_i = (int)start_i; ta.start_j = (int)start_j; ta.start_forced = start_state;
+    ta.start_nops = (int)start_nops;
     if (getenv("TSTA_TRACE_DEBUG")) { if (!tsta::g_trace_dbg) cudaMalloc(&tsta::g_trace_dbg, 64); ta.dbg = tsta::g_trace_dbg; }
     if (p->skew) {
         ta.skew_band_bytes = psa_skew_band_bytes(p->m, p->C);
         ta.skew_steps = psa_skew_steps(p->m);
         ta.skew_bands = p->nbands;
+        if (p->ckpt) {
+            ta.tile_rows = p->d_tilerows.as<PsaTileRow>();
+            ta.tile_bytes = psa_tile_bytes(p->C);
+        }
         cudaError_t e;
         if (p->C == 2) e = launch_trace_skew<2>(ta, p->stream);
         else if (p->C == 3) e = launch_trace_skew<3>(ta, p->stream);
@@ -425,8 +522,14 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
             p->C = c16;
         }
     }
-    p->scale = p->packed && p->want_trace ? 4 : S;
     p->skew = p->packed && p->want_trace;
+    {
+        // TSTA_PSA_TRACE_MODE=full keeps the direction words of the WHOLE matrix (what column slices do)
+        const char* tm = getenv("TSTA_PSA_TRACE_MODE");
+        p->ckpt = p->skew && !(has_left || has_right) && !(tm && strcmp(tm, "full") == 0);
+    }
+    p->scale = p->ckpt ? 1 : (p->skew ? 4 : S);
+    if (p->ckpt) p->CH = 32;
     const int band_cols = (p->packed ? 64 : 32) * p->C;
     p->nbands = (int)((n + band_cols - 1) / band_cols);
     p->n_pad = p->nbands * band_cols;
@@ -451,7 +554,29 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
         }
     }
     if (int rc = p->d_lastrow.reserve((size_t)p->n_pad * sizeof(int))) return rc;
-    if (p->want_trace) {
+    if (p->ckpt) {
+        const size_t K = (size_t)psa_tile_rows(m);
+        if (int rc = p->d_ckpt.reserve((size_t)p->nbands * (size_t)psa_ckpt_band_words(m, p->C) * sizeof(uint32_t))) return rc;
+        if (int rc = p->d_tilerows.reserve(K * sizeof(PsaTileRow))) return rc;
+        if (K > p->rows_cap) {
+            if (p->h_rows) cudaFreeHost(p->h_rows);
+            p->h_rows = nullptr;
+            p->rows_cap = 0;
+            TSTA_CUDA_TRY(cudaMallocHost((void**)&p->h_rows, (K + K / 4) * sizeof(PsaTileRow)));
+            p->rows_cap = K + K / 4;
+        }
+        p->corridor_w = 2048;
+        if (const char* e = getenv("TSTA_PSA_CORRIDOR")) p->corridor_w = atoll(e);
+        p->corridor_w = std::max<int64_t>(p->corridor_w, 1024);      // (a window of the walk is 512 columns wide: progress per corridor)
+        long long budget_mb = 8192;
+        if (const char* e = getenv("TSTA_PSA_TILE_BUDGET_MB")) budget_mb = atoll(e);
+        budget_mb = std::max<long long>(budget_mb, 16);
+        p->max_slots = std::max<long long>((budget_mb << 20) / psa_tile_bytes(p->C), 2 * (p->nbands + 1));
+        int k_low = 0, width = 0;
+        const long long first = build_corridor(p, m - 1, n - 1, p->h_rows, &k_low, &width);
+        if (int rc = p->d_dirs.reserve((size_t)first * (size_t)psa_tile_bytes(p->C))) return rc;
+        if (int rc = p->d_ops.reserve((size_t)(n + m) + 64)) return rc;
+    } else if (p->want_trace) {
         const size_t dir_bytes = p->skew ? (size_t)p->nbands * (size_t)psa_skew_band_bytes(m, p->C)
                                          : (size_t)m * (size_t)(p->n_pad / 2);
         if (int rc = p->d_dirs.reserve(dir_bytes)) return rc;
@@ -474,11 +599,20 @@ int tsta_psa_plan_wait(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
     if (trace_ms) *trace_ms = 0.f;
     if (p->n == 0 || p->m == 0) { p->ran = true; return TSTA_OK; }
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small + 6, p->d_ctl.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
-    if (p->h_small[6] != 0)
-        return set_error(TSTA_ECUDA, "boundary hand-off timed out: a band (or column slice) waited for its left neighbour in vain "
-                                     "(slices of one pair must be launched together and run the same number of times)");
+    for (;;) {
+        TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small, p->d_ctl.as<int>(), 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        if (p->h_small[6] != 0)
+            return set_error(TSTA_ECUDA, "boundary hand-off timed out: a band (or column slice) waited for its left neighbour in vain "
+                                         "(slices of one pair must be launched together and run the same number of times)");
+        if (!p->want_trace || p->h_small[7] == 0) break;
+        if (!p->ckpt) return set_error(TSTA_ECUDA, "traceback ran into cells without a direction code at (%d, %d)", p->h_small[3], p->h_small[4]);
+        // the walk left the corridor (or the corridor's tile budget ended): a new one around the point it got to
+        if (p->rounds > 100000) return set_error(TSTA_ECUDA, "traceback does not advance at (%d, %d)", p->h_small[3], p->h_small[4]);
+        TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.as<int>() + 7, 0, sizeof(int), p->stream));
+        if (int rc = launch_corridor_walk(p, p->h_small[3], p->h_small[4], p->h_small[5], p->h_small[2])) return rc;
+        TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
+    }
     if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
         long long h[4] = {0, 0, 0, 0};
         using tsta::g_trace_dbg;
@@ -529,6 +663,10 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
         TSTA_CUDA_TRY(cudaMemsetAsync(p->d_timeline.p, 0, (size_t)p->nbands * 128, p->stream));
         fa.timeline = p->d_timeline.as<unsigned long long>();
     }
+    fa.ckpt = p->ckpt ? p->d_ckpt.as<uint32_t>() : nullptr;
+    fa.ckpt_band_words = p->ckpt ? psa_ckpt_band_words(p->m, p->C) : 0;
+    p->rounds = 0;
+    p->tiles_run = 0;
     fa.out_max = ctl + 1;
     fa.lastrow = p->d_lastrow.as<int>();
     fa.col_off = (int)p->col0;
@@ -538,13 +676,13 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
 
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     nvtxRangePushA("tsta_psa fill");
-    if (p->want_trace && p->packed) {
+    if (p->want_trace && p->packed && !p->ckpt) {
         if (p->C == 2) launch_pair16<2, 2>(p, fa);
         else if (p->C == 3) launch_pair16<3, 2>(p, fa);
         else if (p->C == 4) launch_pair16<4, 2>(p, fa);
         else if (p->C == 6) launch_pair16<6, 2>(p, fa);
         else launch_pair16<8, 2>(p, fa);
-    } else if (p->want_trace) {
+    } else if (p->want_trace && !p->ckpt) {
         if (p->C == 4) launch_pair<4, true>(p, fa);
         else if (p->C == 8) launch_pair<8, true>(p, fa);
         else launch_pair<16, true>(p, fa);
@@ -564,8 +702,10 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
     TSTA_CUDA_TRY(cudaGetLastError());
     p->launches++;
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
-    if (p->want_trace && !(p->has_left || p->has_right)) {   // (slices are walked later, right to left: tsta_psa_plan_trace_from)
-        if (int rc = launch_walk(p, fa.m - 1, 0)) return rc;
+    if (p->ckpt) {
+        if (int rc = launch_corridor_walk(p, fa.m - 1, fa.n - 1, 0, 0)) return rc;
+    } else if (p->want_trace && !(p->has_left || p->has_right)) {   // (slices are walked later, right to left: tsta_psa_plan_trace_from)
+        if (int rc = launch_walk(p, fa.m - 1, fa.n - 1, 0, 0)) return rc;
         p->launches++;
     }
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
@@ -643,11 +783,33 @@ int tsta_psa_plan_dirs(tsta_psa_plan* p, uint8_t* out)
         const int C = p->C, W = C > 4 ? 2 : 1;
         const size_t band_bytes = (size_t)psa_skew_band_bytes(m, C);
         const int64_t T = psa_skew_steps(m);
-        std::vector<uint32_t> raw((size_t)p->nbands * band_bytes / 4);
+        if (p->ckpt) {
+            // checkpointed traceback keeps tiles around the path only: for this export EVERY tile is re-run
+            // (a corridor as wide as the matrix; the walk that follows finds the same path again)
+            const long long saved_budget = p->max_slots, saved_w = p->corridor_w;
+            p->max_slots = psa_tile_rows(m) * p->nbands;
+            p->corridor_w = 8000000;
+            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.as<int>() + 2, 0, 6 * sizeof(int), p->stream));
+            const int rc = launch_corridor_walk(p, m - 1, n - 1, 0, 0);
+            p->max_slots = saved_budget;
+            p->corridor_w = saved_w;
+            if (rc) return rc;
+            TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        std::vector<uint32_t> raw(p->ckpt ? (size_t)p->slots * (size_t)psa_tile_bytes(C) / 4 : (size_t)p->nbands * band_bytes / 4);
         TSTA_CUDA_TRY(cudaMemcpy(raw.data(), p->d_dirs.p, raw.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<PsaTileRow> rows;
+        if (p->ckpt) rows.assign(p->h_rows, p->h_rows + psa_tile_rows(m));
         auto cell = [&](int64_t i, int64_t j) -> unsigned {
             const int64_t b = j / (64 * C), v = (j % (64 * C)) / C, c = j % C;
-            const size_t w = ((size_t)b * (size_t)T + (size_t)(i + v)) * 32 * W + (size_t)(v & 31) * W + (W == 2 ? (size_t)(v >> 5) : 0);
+            size_t w;
+            if (p->ckpt) {
+                const int64_t t = i + v;
+                const PsaTileRow& r = rows[(size_t)(t / kTileSteps)];
+                if (b < r.bmin || b > r.bmax) return 0u;
+                w = ((size_t)(r.slot0 + (b - r.bmin)) * kTileSteps + (size_t)(t % kTileSteps)) * 32 * W + (size_t)(v & 31) * W + (W == 2 ? (size_t)(v >> 5) : 0);
+            } else
+            w = ((size_t)b * (size_t)T + (size_t)(i + v)) * 32 * W + (size_t)(v & 31) * W + (W == 2 ? (size_t)(v >> 5) : 0);
             const unsigned sh = (unsigned)(4 * c + (W == 1 ? 16 * (v >> 5) : 0));
             return (raw[w] >> sh) & 15u;
         };
@@ -685,6 +847,15 @@ int tsta_psa_plan_info(tsta_psa_plan* p, int* launches, int* cols_per_lane, int*
 
 int tsta_psa_plan_packed(tsta_psa_plan* p) { return p && p->packed ? 1 : 0; }
 
+int tsta_psa_plan_trace_stats(tsta_psa_plan* p, int* corridors, long long* tiles, long long* tiles_of_matrix)
+{
+    if (!p) return set_error(TSTA_EINVAL, "plan is NULL");
+    if (corridors) *corridors = p->ckpt ? p->rounds : 0;
+    if (tiles) *tiles = p->ckpt ? p->tiles_run : 0;
+    if (tiles_of_matrix) *tiles_of_matrix = p->ckpt ? psa_tile_rows(p->m) * p->nbands : 0;
+    return TSTA_OK;
+}
+
 int tsta_psa_plan_timeline(tsta_psa_plan* p, unsigned long long* out)   // [bands][16]: 8 globaltimer stamps (ns), then import statistics (TSTA_PSA_TIMELINE=1)
 {
     if (!p || !out || !p->d_timeline.p) return set_error(TSTA_EINVAL, "no timeline recorded (set TSTA_PSA_TIMELINE=1)");
@@ -703,7 +874,7 @@ int tsta_psa_plan_trace_from(tsta_psa_plan* p, int64_t start_i, int start_forced
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     int* ctl = p->d_ctl.as<int>();
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
-    if (int rc = launch_walk(p, start_i, start_forced)) return rc;
+    if (int rc = launch_walk(p, start_i, p->n - 1, start_forced, 0)) return rc;
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->h_small, ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
