@@ -146,7 +146,7 @@ def test_dual_pair_mode_with_traceback(gpu, env, lens):
 
 @pytest.fixture
 def trace_env():
-    keys = ("TSTA_PSA_TRACE_MODE", "TSTA_PSA_CORRIDOR", "TSTA_PSA_TILE_BUDGET_MB", "TSTA_PSA_C16")
+    keys = ("TSTA_PSA_TRACE_MODE", "TSTA_PSA_CORRIDOR", "TSTA_PSA_TILE_BUDGET_MB", "TSTA_PSA_C16", "TSTA_PSA_WALK")
     saved = {k: os.environ.get(k) for k in keys}
     yield os.environ
     for k, v in saved.items():
@@ -166,10 +166,12 @@ def _traced(gpu, x, y, prm=(2, -5, -2, -4)):
     return r, st
 
 
-def test_checkpointed_traceback_leaves_and_reenters_corridor(gpu, trace_env):
+@pytest.mark.parametrize("walk", ["chase", "serial"])
+def test_checkpointed_traceback_leaves_and_reenters_corridor(gpu, trace_env, walk):
     """A 3000-base deletion moves the path 3000 columns sideways: the walk leaves the first corridor
     (margin 1024) and is resumed in new ones; the alignment is the oracle's byte for byte."""
     trace_env["TSTA_PSA_CORRIDOR"] = "1024"
+    trace_env["TSTA_PSA_WALK"] = walk
     x = synth.random_read(20_000, 71)
     y = x[:8_000] + x[11_000:]
     o = ob.psa(x, y)
@@ -196,12 +198,15 @@ def test_checkpointed_traceback_tile_budget(gpu, trace_env):
         assert st["corridors"] >= 2
 
 
-@pytest.mark.parametrize("mode", ["full", "ckpt"])
+@pytest.mark.parametrize("mode", ["full", "ckpt", "ckpt_serial"])
 def test_trace_modes_agree_with_oracle(gpu, trace_env, mode):
-    """Both traceback modes of the packed kernels (direction words of the whole matrix / checkpoints +
-    corridor) against the oracle, every strip width, linear and affine gaps, ragged shapes."""
+    """The traceback modes of the packed kernels (direction words of the whole matrix / checkpoints +
+    corridor with the parallel tile chase / the same with the serial window walker) against the oracle,
+    every strip width, linear and affine gaps, ragged shapes."""
     if mode == "full":
         trace_env["TSTA_PSA_TRACE_MODE"] = "full"
+    if mode == "ckpt_serial":
+        trace_env["TSTA_PSA_WALK"] = "serial"
     rnd = random.Random(7)
     for c16 in (2, 3, 4, 6, 8):
         trace_env["TSTA_PSA_C16"] = str(c16)
@@ -214,4 +219,4 @@ def test_trace_modes_agree_with_oracle(gpu, trace_env, mode):
                 r, st = _traced(gpu, x, y, prm)
                 assert (r.maxsorce, r.corner) == (o.maxsorce, o.corner), (mode, c16, la, lb, prm)
                 assert r.output_bytes() == o.output_bytes(), (mode, c16, la, lb, prm)
-                assert (st["corridors"] >= 1) == (mode == "ckpt")
+                assert (st["corridors"] >= 1) == (mode != "full")

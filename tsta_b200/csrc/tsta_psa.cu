@@ -11,6 +11,7 @@
 #include "psa_fill.cuh"
 #include "psa_fill16.cuh"
 #include "psa_trace.cuh"
+#include "psa_chase.cuh"
 
 namespace tsta {
 
@@ -113,7 +114,9 @@ struct tsta_psa_plan {
     long long slots = 0;           // tiles of the current corridor
     int rounds = 0;                // corridors the last run needed (1 = the walk never left the first one)
     long long tiles_run = 0;       // tiles re-run by the last run, all corridors
-    DevBuf d_ckpt, d_tilerows;
+    bool chase = true;             // parallel traceback over the tiles (psa_chase.cuh); false: the serial window walker
+    DevBuf d_ckpt, d_tilerows, d_summary, d_visits, d_counts, d_vslots;
+    int max_visits = 0;
     PsaTileRow* h_rows = nullptr;  // pinned, [rows_cap]
     size_t rows_cap = 0;
     // column slice of a pair spread over several GPUs (tsta_psa_plan_upload_slice)
@@ -140,6 +143,7 @@ static void plan_free(tsta_psa_plan* p)
     p->d_s0.release(); p->d_s1.release(); p->d_bnd.release(); p->d_ctl.release();
     p->d_dirs.release(); p->d_ops.release(); p->d_lastrow.release(); p->d_inbox.release(); p->d_timeline.release();
     p->d_ckpt.release(); p->d_tilerows.release();
+    p->d_summary.release(); p->d_visits.release(); p->d_counts.release(); p->d_vslots.release();
     if (p->h_rows) cudaFreeHost(p->h_rows);
     if (p->outbox_open) cudaIpcCloseMemHandle(p->outbox);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -249,6 +253,18 @@ static void launch_retrace(const PsaRetraceArgs& ra, int width, int nranges, cud
     psa_retrace16_kernel<C><<<dim3((unsigned)width, (unsigned)nranges), 32, 0, st>>>(ra);
 }
 
+// Parallel traceback over the corridor's tiles: summaries, chase, per-visit walks, compaction (psa_chase.cuh).
+template <int C>
+static void launch_chase(const PsaChaseArgs& ca, int width, int nranges, cudaStream_t st)
+{
+    psa_tile_summary_kernel<C><<<dim3((unsigned)width, (unsigned)nranges), 32, 0, st>>>(ca);
+    psa_chase_kernel<C><<<1, 32, 0, st>>>(ca);
+    psa_visit_walk_kernel<C><<<(unsigned)((ca.max_visits + 63) / 64), 64, 0, st>>>(ca);
+    psa_visit_compact_kernel<C><<<1, 1024, 0, st>>>(ca);
+}
+static size_t chase_sum_words(int C) { return (size_t)2 * 3 * C * 64 + (size_t)kTileSteps * 3; }
+static size_t chase_visit_moves(int C) { return (size_t)kTileSteps + 64 * (size_t)C; }
+
 static int launch_walk(tsta_psa_plan* p, int64_t start_i, int64_t start_j, int start_state, int64_t start_nops);
 
 // Checkpointed traceback: the traced form of the corridor's tiles, then the walk from (i, j).
@@ -285,8 +301,38 @@ static int launch_corridor_walk(tsta_psa_plan* p, int64_t i, int64_t j, int stat
     p->launches++;
     p->rounds++;
     p->tiles_run += p->slots;
-    if (int rc = launch_walk(p, i, j, state, nops)) return rc;
-    p->launches++;
+    if (!p->chase) {
+        if (int rc = launch_walk(p, i, j, state, nops)) return rc;
+        p->launches++;
+        return TSTA_OK;
+    }
+    if (p->slots * chase_sum_words(p->C) * sizeof(uint32_t) > p->d_summary.cap) {
+        TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        if (int rc = p->d_summary.reserve((size_t)(p->slots + p->slots / 4) * chase_sum_words(p->C) * sizeof(uint32_t))) return rc;
+    }
+    PsaChaseArgs ca{};
+    ca.dirs = p->d_dirs.as<uint8_t>(); ca.tile_bytes = psa_tile_bytes(p->C);
+    ca.summary = p->d_summary.as<uint32_t>();
+    ca.rows = p->d_tilerows.as<PsaTileRow>(); ca.nrows = K;
+    ca.n = (int)p->n; ca.m = (int)p->m;
+    ca.start_i = (int)i; ca.start_j = (int)j; ca.start_arr = state; ca.start_nops = (int)nops;
+    ca.visits = p->d_visits.as<int4>(); ca.max_visits = p->max_visits;
+    ca.nvisits = p->d_counts.as<int>();                       // [0] number of visits, then counts, then offsets
+    ca.counts = p->d_counts.as<int>() + 4;
+    ca.offsets = p->d_counts.as<int>() + 4 + p->max_visits;
+    ca.slots = p->d_vslots.as<uint8_t>();
+    ca.ops = p->d_ops.as<uint8_t>();
+    ca.out = p->d_ctl.as<int>() + 2;
+    {
+        NvtxRange r2("tsta_psa traceback");
+        if (p->C == 2) launch_chase<2>(ca, width, nranges, p->stream);
+        else if (p->C == 3) launch_chase<3>(ca, width, nranges, p->stream);
+        else if (p->C == 4) launch_chase<4>(ca, width, nranges, p->stream);
+        else if (p->C == 6) launch_chase<6>(ca, width, nranges, p->stream);
+        else launch_chase<8>(ca, width, nranges, p->stream);
+    }
+    TSTA_CUDA_TRY(cudaGetLastError());
+    p->launches += 4;
     return TSTA_OK;
 }
 
@@ -575,6 +621,17 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
         int k_low = 0, width = 0;
         const long long first = build_corridor(p, m - 1, n - 1, p->h_rows, &k_low, &width);
         if (int rc = p->d_dirs.reserve((size_t)first * (size_t)psa_tile_bytes(p->C))) return rc;
+        {
+            const char* w = getenv("TSTA_PSA_WALK");           // "serial": the one-thread window walker instead of the tile chase
+            p->chase = !(w && strcmp(w, "serial") == 0);
+        }
+        if (p->chase) {
+            p->max_visits = 4 * ((int)K + p->nbands) + 64;
+            if (int rc = p->d_summary.reserve((size_t)first * chase_sum_words(p->C) * sizeof(uint32_t))) return rc;
+            if (int rc = p->d_visits.reserve((size_t)p->max_visits * sizeof(int4))) return rc;
+            if (int rc = p->d_counts.reserve((size_t)(2 * p->max_visits + 4) * sizeof(int))) return rc;
+            if (int rc = p->d_vslots.reserve((size_t)p->max_visits * chase_visit_moves(p->C))) return rc;
+        }
         if (int rc = p->d_ops.reserve((size_t)(n + m) + 64)) return rc;
     } else if (p->want_trace) {
         const size_t dir_bytes = p->skew ? (size_t)p->nbands * (size_t)psa_skew_band_bytes(m, p->C)
@@ -606,7 +663,8 @@ int tsta_psa_plan_wait(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
             return set_error(TSTA_ECUDA, "boundary hand-off timed out: a band (or column slice) waited for its left neighbour in vain "
                                          "(slices of one pair must be launched together and run the same number of times)");
         if (!p->want_trace || p->h_small[7] == 0) break;
-        if (!p->ckpt) return set_error(TSTA_ECUDA, "traceback ran into cells without a direction code at (%d, %d)", p->h_small[3], p->h_small[4]);
+        if (!p->ckpt || p->h_small[7] == 3)
+            return set_error(TSTA_ECUDA, "traceback ran into cells without a direction code at (%d, %d)", p->h_small[3], p->h_small[4]);
         // the walk left the corridor (or the corridor's tile budget ended): a new one around the point it got to
         if (p->rounds > 100000) return set_error(TSTA_ECUDA, "traceback does not advance at (%d, %d)", p->h_small[3], p->h_small[4]);
         TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.as<int>() + 7, 0, sizeof(int), p->stream));
