@@ -5,6 +5,12 @@ import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 os.environ["TSTA_PSA_TIMELINE"] = "1"
+if not os.environ.get("TSTA_LIB"):      # the stamps are compiled in only with -DTSTA_TIMELINE=1 (build it where nvcc is: python tools/timeline.py --build)
+    os.environ["TSTA_LIB"] = str(Path(__file__).resolve().parents[1] / "tsta_b200" / "_build" / "libtsta_cuda_timeline.so")
+if "--build" in sys.argv:
+    from tsta_b200 import build
+    print(build.build_variant("timeline", ["TSTA_TIMELINE=1"]))
+    sys.exit(0)
 import numpy as np
 from tsta_b200 import api, synth
 

@@ -457,6 +457,11 @@ __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint
 #define TSTA_FAST_RAMP 1
 #endif
 constexpr int kImportGroup = TSTA_IMPORT_GROUP;
+// Per-band time stamps (tools/timeline.py): compiled in only for the experiment build (-DTSTA_TIMELINE=1).
+#ifndef TSTA_TIMELINE
+#define TSTA_TIMELINE 0
+#endif
+constexpr bool kTimeline = TSTA_TIMELINE != 0;
 template <int C, int TM, bool PIPE, int CH>
 __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScoring& sc, const uint32_t* tab4,
                                                 PsaWarpSmem16<C, TM == 1>& sm, const int lane)
@@ -586,7 +591,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         const bool mine = lane < G && row < m;
         unsigned spins = 0;
         unsigned long long t_wait = 0;
-        const long long dbg_c0 = b.timeline ? clock64() : 0;
+        const long long dbg_c0 = (kTimeline && b.timeline) ? clock64() : 0;
         while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
             __nanosleep(20);
             if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
@@ -610,7 +615,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         } else if (mine) sm.in[slot0 + lane] = vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE));
         __syncwarp();
         if (lane < G && row + G < m) bnd_next = ld_relaxed_u64(b.bnd_in + row + G);
-        if (b.timeline && lane == 0) {   // diagnostics: polls that found stale rows, cycles spent importing, imports
+        if (kTimeline && b.timeline && lane == 0) {   // diagnostics: polls that found stale rows, cycles spent importing, imports
             b.timeline[b.band * 16 + 8] += spins;
             b.timeline[b.band * 16 + 9] += (unsigned long long)(clock64() - dbg_c0);
             b.timeline[b.band * 16 + 10] += 1;
@@ -618,13 +623,18 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     };
 
     auto stamp = [&](int slot) {
-        if (PIPE && b.timeline && lane == 0) {
+        if (kTimeline && PIPE && b.timeline && lane == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             b.timeline[b.band * 16 + slot] = now;
         }
     };
     stamp(0);
+    if (kTimeline && PIPE && b.timeline && lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        b.timeline[b.band * 16 + 11] = smid;
+    }
     const int ch_last = min(nchunks, b.ch_end);
     for (int ch = b.ch_begin; ch < ch_last; ch++) {
         const int t0 = ch * CH;
