@@ -127,6 +127,19 @@ __device__ __forceinline__ void ring16_put(SM& sm, int row, uint2 v)
     if (k < kMaxChunkRows) sm.rowring[kRing16 + k] = v;
 }
 
+// Slow path of the hand-off poll (every 65536th stale poll): true when the run was aborted or this warp has
+// waited longer than timeout_ns, in which case the abort flag is raised for everybody else.
+static __device__ __noinline__ bool psa_handoff_expired(int* abort_flag, unsigned long long timeout_ns, unsigned long long& t_wait, int lane)
+{
+    if (!abort_flag) return false;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t_wait == 0) t_wait = now;
+    int stop = *reinterpret_cast<volatile int*>(abort_flag);
+    if (now - t_wait > timeout_ns) { stop = 1; if (lane == 0) atomicExch(abort_flag, 1); }
+    return __any_sync(kFullMask, stop != 0);
+}
+
 // Per-warp shared-memory workspace of the packed sweep.
 template <int C, bool RING>
 struct __align__(16) PsaWarpSmem16 {
@@ -456,6 +469,9 @@ __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint
 #ifndef TSTA_FAST_RAMP
 #define TSTA_FAST_RAMP 1
 #endif
+#ifndef TSTA_WATCHDOG
+#define TSTA_WATCHDOG 1
+#endif
 constexpr int kImportGroup = TSTA_IMPORT_GROUP;
 // Per-band time stamps (tools/timeline.py): compiled in only for the experiment build (-DTSTA_TIMELINE=1).
 #ifndef TSTA_TIMELINE
@@ -592,16 +608,20 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         unsigned spins = 0;
         unsigned long long t_wait = 0;
         const long long dbg_c0 = (kTimeline && b.timeline) ? clock64() : 0;
-        while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
-            __nanosleep(20);
-            if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
-            if ((++spins & 0xfffu) == 0 && b.abort_flag) {       // watchdog: never hang the GPU on a neighbour that does not come
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t_wait == 0) t_wait = now;
-                int stop = *reinterpret_cast<volatile int*>(b.abort_flag);
-                if (now - t_wait > b.timeout_ns) { stop = 1; if (lane == 0) atomicExch(b.abort_flag, 1); }
-                if (__any_sync(kFullMask, stop != 0)) break;
+        if (TSTA_WATCHDOG && b.has_left && b.band == 0) {
+            // the producer is ANOTHER GPU (column slices): never hang on a neighbour that does not come
+            while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
+                __nanosleep(20);
+                if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
+                if ((++spins & 0xfffu) == 0 && psa_handoff_expired(b.abort_flag, b.timeout_ns, t_wait, lane)) break;
+            }
+        } else {
+            // the producer is a band of this launch that took its ticket earlier: it runs, or has run, whatever this
+            // warp does -- the wait always ends.  No watchdog here: any code inside this loop delays every band
+            // behind this one (measured on the 100 kbp pair: 6.6 ms with a check every 4096 polls, 6.2 ms without)
+            while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
+                __nanosleep(20);
+                if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
             }
         }
         // absolute modulo 2^16 -> relative to this warp's base (score-only: Ft = Fg - (O+E))
