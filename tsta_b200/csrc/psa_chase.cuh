@@ -31,8 +31,10 @@ template <int C>
 struct PsaChaseGeom {
     static constexpr int kWords = C > 4 ? 2 : 1;            // direction words per lane and step
     static constexpr int kBandCols = 64 * C;
-    static constexpr int kRowWords = 3 * C * 64;            // entries of one step: [arrival][column of the lane][virtual lane]
-    static constexpr int kSumWords = 2 * kRowWords + kTileSteps * 3;   // steps 126, 127; then the last column [step][arrival]
+    static constexpr int kRowWords = 3 * C * 64;            // entries of the last step: [arrival][column of the lane][virtual lane]
+    // a walk enters a tile through its last step (from the tile below), through the last column of every lane in
+    // the step before (a diagonal move out of the next lane's first row below), or through the band's last column
+    static constexpr int kSumWords = kRowWords + 64 + kTileSteps * 3;   // step 127; step 126: [virtual lane]; last column [step][arrival]
     static constexpr int kVisitMoves = kTileSteps + kBandCols;         // most moves one visit can make
 };
 
@@ -52,6 +54,7 @@ struct PsaChaseArgs {
     uint8_t* slots;              // [max_visits][kVisitMoves]
     uint8_t* ops;                // all moves, walk order (tags: 3 diagonal, 2 left, 1 up)
     int* out;                    // [0] moves so far, [1] i, [2] j, [3] arrival (0 = free), [5] status
+    uint32_t* start_exit;        // [3] where a walk from the START cell leaves its tile, per arrival (written by the summary kernel)
 };
 
 // The cell a walk leaves a tile to: offsets from the tile's corner, so that 32 bits are plenty.
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(32) psa_tile_summary_kernel(const PsaChaseArgs
 {
     using G = PsaChaseGeom<C>;
     const int lane = threadIdx.x;
-    const int k = a.nrows - 1 - (int)blockIdx.y;
+    const int k = a.nrows - (int)gridDim.y + (int)blockIdx.y;    // top ranges first: the chase starts at the bottom, whose lines are then the freshest in L2
     const PsaTileRow row = a.rows[k];
     const int band = row.bmin + (int)blockIdx.x;
     if (band > row.bmax) return;
@@ -140,15 +143,17 @@ __global__ void __launch_bounds__(32) psa_tile_summary_kernel(const PsaChaseArgs
                 Dp[h][c] = E3;
                 U[h][c] = E1;
                 Lc = E2;
-                if (s >= kTileSteps - 2) {
-                    uint32_t* e = sum + (s - (kTileSteps - 2)) * G::kRowWords + c * 64 + v;
+                if (s == kTileSteps - 1) {
+                    uint32_t* e = sum + c * 64 + v;
                     e[0] = E1; e[C * 64] = E2; e[2 * C * 64] = E3;
                 }
+                if (s == kTileSteps - 2 && c == C - 1) sum[G::kRowWords + v] = E3;
+                if (i == a.start_i && j0 + c == a.start_j) { a.start_exit[0] = E1; a.start_exit[1] = E2; a.start_exit[2] = E3; }
                 if (c == C - 1) {
                     out2[h] = E2;
                     out3[h] = E3;
                     if (h == 1 && lane == 31) {
-                        uint32_t* e = sum + 2 * G::kRowWords + s * 3;
+                        uint32_t* e = sum + G::kRowWords + 64 + s * 3;
                         e[0] = E1; e[1] = E2; e[2] = E3;
                     }
                 }
@@ -215,13 +220,24 @@ __device__ __forceinline__ int psa_tile_walk(const PsaChaseArgs& a, long long sl
 // ---------------------------------------------------------------------------------------
 // 2. the chase: one lookup per tile
 // ---------------------------------------------------------------------------------------
+constexpr int kChaseRowsSmem = 2560;       // tile-table rows kept in shared memory (40 KB): pairs of up to ~320 kbp rows
+
 template <int C>
-__global__ void __launch_bounds__(32) psa_chase_kernel(const PsaChaseArgs a)
+__global__ void __launch_bounds__(32) psa_chase_kernel(const PsaChaseArgs a0)
 {
     using G = PsaChaseGeom<C>;
+    // every visit is a chain of dependent loads (table row -> summary word): the table row comes from shared memory
+    __shared__ PsaTileRow s_rows[kChaseRowsSmem];
+    PsaChaseArgs a = a0;
+    if (a.nrows <= kChaseRowsSmem) {
+        for (int q = threadIdx.x; q < a.nrows; q += 32) s_rows[q] = a0.rows[q];
+        __syncwarp();
+        a.rows = s_rows;
+    }
     if (threadIdx.x != 0) return;
     PsaCell x{a.start_i, a.start_j, a.start_arr ? a.start_arr : 3};
     int nv = 0, status = 0;
+    bool first = true;
     while (x.i >= 0 && x.j >= 0) {
         int band, k, s, v, c;
         long long slot;
@@ -230,8 +246,10 @@ __global__ void __launch_bounds__(32) psa_chase_kernel(const PsaChaseArgs a)
         a.visits[nv++] = make_int4(x.i, x.j, x.arr, 0);
         const uint32_t* sum = a.summary + slot * G::kSumWords;
         uint32_t e;
-        if (s >= kTileSteps - 2) e = __ldcg(sum + (s - (kTileSteps - 2)) * G::kRowWords + (x.arr - 1) * (C * 64) + c * 64 + v);
-        else if (v == 63 && c == C - 1) e = __ldcg(sum + 2 * G::kRowWords + s * 3 + (x.arr - 1));
+        if (first) { e = __ldcg(a.start_exit + (x.arr - 1)); first = false; }     // the start cell: kept by the summary kernel
+        else if (s == kTileSteps - 1) e = __ldcg(sum + (x.arr - 1) * (C * 64) + c * 64 + v);
+        else if (v == 63 && c == C - 1) e = __ldcg(sum + G::kRowWords + 64 + s * 3 + (x.arr - 1));
+        else if (s == kTileSteps - 2 && c == C - 1 && x.arr == 3) e = __ldcg(sum + G::kRowWords + v);
         else {
             // not a cell whose exit was kept (the start of the alignment): walk this tile step by step
             bool bad = false;

@@ -4,6 +4,7 @@
 // (psa/psa.c:588-666): state set-up (blockmatrix_init, 219-232, happens inside the fill
 // kernel), the fill, the traceback and the '-'-padded strings of trace() (467-515).
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -222,7 +223,8 @@ static thread_local AlignCache g_align_cache;
 static long long build_corridor(const tsta_psa_plan* p, int64_t i, int64_t j, PsaTileRow* rows, int* k_low, int* width)
 {
     const int K = (int)psa_tile_rows(p->m);
-    const int64_t band_cols = 64 * p->C, W = p->corridor_w;
+    // (every corridor after the first doubles the margin: the path has shown that it wanders further than expected)
+    const int64_t band_cols = 64 * p->C, W = p->corridor_w << std::min(p->rounds, 6);
     long long slots = 0;
     bool full = false;
     *k_low = K;
@@ -254,15 +256,24 @@ static void launch_retrace(const PsaRetraceArgs& ra, int width, int nranges, cud
 }
 
 // Parallel traceback over the corridor's tiles: summaries, chase, per-visit walks, compaction (psa_chase.cuh).
+static cudaEvent_t g_chase_ev[6];      // TSTA_TRACE_DEBUG=1: time stamps around the kernels of the last corridor
+static bool g_chase_dbg = false;
+
 template <int C>
 static void launch_chase(const PsaChaseArgs& ca, int width, int nranges, cudaStream_t st)
 {
+    auto stamp = [&](int k) { if (g_chase_dbg) cudaEventRecord(g_chase_ev[k], st); };
+    stamp(1);
     psa_tile_summary_kernel<C><<<dim3((unsigned)width, (unsigned)nranges), 32, 0, st>>>(ca);
+    stamp(2);
     psa_chase_kernel<C><<<1, 32, 0, st>>>(ca);
+    stamp(3);
     psa_visit_walk_kernel<C><<<(unsigned)((ca.max_visits + 63) / 64), 64, 0, st>>>(ca);
+    stamp(4);
     psa_visit_compact_kernel<C><<<1, 1024, 0, st>>>(ca);
+    stamp(5);
 }
-static size_t chase_sum_words(int C) { return (size_t)2 * 3 * C * 64 + (size_t)kTileSteps * 3; }
+static size_t chase_sum_words(int C) { return (size_t)3 * C * 64 + 64 + (size_t)kTileSteps * 3; }
 static size_t chase_visit_moves(int C) { return (size_t)kTileSteps + 64 * (size_t)C; }
 
 static int launch_walk(tsta_psa_plan* p, int64_t start_i, int64_t start_j, int start_state, int64_t start_nops);
@@ -292,6 +303,11 @@ static int launch_corridor_walk(tsta_psa_plan* p, int64_t i, int64_t j, int stat
     ra.abort_flag = p->d_ctl.as<int>() + 6;
     ra.timeout_ns = 2000000000ull;
     const int nranges = K - k_low;
+    if (getenv("TSTA_TRACE_DEBUG") && !g_chase_dbg) {
+        for (auto& e : g_chase_ev) cudaEventCreate(&e);
+        g_chase_dbg = true;
+    }
+    if (g_chase_dbg) cudaEventRecord(g_chase_ev[0], p->stream);
     if (p->C == 2) launch_retrace<2>(ra, width, nranges, p->stream);
     else if (p->C == 3) launch_retrace<3>(ra, width, nranges, p->stream);
     else if (p->C == 4) launch_retrace<4>(ra, width, nranges, p->stream);
@@ -317,9 +333,10 @@ static int launch_corridor_walk(tsta_psa_plan* p, int64_t i, int64_t j, int stat
     ca.n = (int)p->n; ca.m = (int)p->m;
     ca.start_i = (int)i; ca.start_j = (int)j; ca.start_arr = state; ca.start_nops = (int)nops;
     ca.visits = p->d_visits.as<int4>(); ca.max_visits = p->max_visits;
-    ca.nvisits = p->d_counts.as<int>();                       // [0] number of visits, then counts, then offsets
-    ca.counts = p->d_counts.as<int>() + 4;
-    ca.offsets = p->d_counts.as<int>() + 4 + p->max_visits;
+    ca.nvisits = p->d_counts.as<int>();                       // [0] number of visits, [4..6] exits of the start cell, then counts, then offsets
+    ca.start_exit = p->d_counts.as<uint32_t>() + 4;
+    ca.counts = p->d_counts.as<int>() + 8;
+    ca.offsets = p->d_counts.as<int>() + 8 + p->max_visits;
     ca.slots = p->d_vslots.as<uint8_t>();
     ca.ops = p->d_ops.as<uint8_t>();
     ca.out = p->d_ctl.as<int>() + 2;
@@ -611,7 +628,10 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
             TSTA_CUDA_TRY(cudaMallocHost((void**)&p->h_rows, (K + K / 4) * sizeof(PsaTileRow)));
             p->rows_cap = K + K / 4;
         }
+        // margin: the optimal path of two unrelated reads wanders ~ length^(2/3) away from the straight line
+        // (measured: +-1000 columns at 100 kbp); 2048 columns at 100 kbp, scaled by that law for longer reads
         p->corridor_w = 2048;
+        if (n > 100000) p->corridor_w = (int64_t)(2048.0 * pow((double)n / 100000.0, 2.0 / 3.0));
         if (const char* e = getenv("TSTA_PSA_CORRIDOR")) p->corridor_w = atoll(e);
         p->corridor_w = std::max<int64_t>(p->corridor_w, 1024);      // (a window of the walk is 512 columns wide: progress per corridor)
         long long budget_mb = 8192;
@@ -619,6 +639,7 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
         budget_mb = std::max<long long>(budget_mb, 16);
         p->max_slots = std::max<long long>((budget_mb << 20) / psa_tile_bytes(p->C), 2 * (p->nbands + 1));
         int k_low = 0, width = 0;
+        p->rounds = 0;
         const long long first = build_corridor(p, m - 1, n - 1, p->h_rows, &k_low, &width);
         if (int rc = p->d_dirs.reserve((size_t)first * (size_t)psa_tile_bytes(p->C))) return rc;
         {
@@ -629,7 +650,7 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
             p->max_visits = 4 * ((int)K + p->nbands) + 64;
             if (int rc = p->d_summary.reserve((size_t)first * chase_sum_words(p->C) * sizeof(uint32_t))) return rc;
             if (int rc = p->d_visits.reserve((size_t)p->max_visits * sizeof(int4))) return rc;
-            if (int rc = p->d_counts.reserve((size_t)(2 * p->max_visits + 4) * sizeof(int))) return rc;
+            if (int rc = p->d_counts.reserve((size_t)(2 * p->max_visits + 8) * sizeof(int))) return rc;
             if (int rc = p->d_vslots.reserve((size_t)p->max_visits * chase_visit_moves(p->C))) return rc;
         }
         if (int rc = p->d_ops.reserve((size_t)(n + m) + 64)) return rc;
@@ -671,7 +692,14 @@ int tsta_psa_plan_wait(tsta_psa_plan* p, float* fill_ms, float* trace_ms)
         if (int rc = launch_corridor_walk(p, p->h_small[3], p->h_small[4], p->h_small[5], p->h_small[2])) return rc;
         TSTA_CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
     }
-    if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
+    if (p->ckpt && p->chase && g_chase_dbg) {
+        float t[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t[k], g_chase_ev[k], g_chase_ev[k + 1]);
+        int nv = 0;
+        cudaMemcpy(&nv, p->d_counts.p, sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "trace dbg: last corridor of %d: %lld tiles; retrace %.3f summary %.3f chase %.3f (%d visits) walks %.3f compact %.3f ms\n",
+                p->rounds, p->slots, t[0], t[1], t[2], nv, t[3], t[4]);
+    } else if (p->want_trace && getenv("TSTA_TRACE_DEBUG")) {
         long long h[4] = {0, 0, 0, 0};
         using tsta::g_trace_dbg;
         if (g_trace_dbg) { cudaMemcpy(h, g_trace_dbg, 32, cudaMemcpyDeviceToHost);
