@@ -97,9 +97,10 @@ WORKLOADS = {
                   "TSTA_msa: partial-order alignment of 16 synthetic 50 kbp reads (5 % divergence), one job per GPU"),
     "msa16x10k": ("msa", (16, 10_000), True, AFFINE, "TSTA_msa: 16 x 10 kbp (debug)"),
 }
-SUITE_1GPU = ["pair100k_trace", "pair200k_trace", "batch250", "batch250_linear", "batch10k", "batch10k_linear",
-              "batch250_trace", "batch10k_trace", "msa16x50k"]
 SUITE_NGPU = ["batch10k_strong", "batch250_strong", "pair100k_bands", "pair400k_bands"]
+# (the fixed jobs of the N-GPU suite also run on one GPU: the first point of their strong-scaling curves)
+SUITE_1GPU = ["pair100k_trace", "pair200k_trace", "batch250", "batch250_linear", "batch10k", "batch10k_linear",
+              "batch250_trace", "batch10k_trace", "msa16x50k"] + SUITE_NGPU
 
 
 def peaks():
@@ -878,10 +879,14 @@ def pair_parity(name, res):
 
 
 def summarize(res):
+    rf = res["roofline"]
+    step_frac = None
+    if rf.get("frac") and rf.get("kernel_ms") and res["ms_per_step"]:
+        step_frac = rf["frac"] * rf["kernel_ms"] / res["ms_per_step"]        # all kernels of the step (fill + traceback) against the same peak
     return {"value": res["value"], "unit": "GCUPS", "ms_per_step": res["ms_per_step"], "steps": res["steps"],
             "scaling": res["scaling"], "kernel_ms": res["roofline"].get("kernel_ms"),
             "e2e": res["e2e"]["value"], "e2e_ms_per_step": res["e2e"]["ms_per_step"],
-            "roofline_frac": res["roofline"]["frac"], "gpu_launches": res["gpu_launches"],
+            "roofline_frac": res["roofline"]["frac"], "roofline_frac_whole_step": step_frac, "gpu_launches": res["gpu_launches"],
             "result": res["result"], "parity": res["parity"],
             "parity_checked": bool(res["parity"] and res["parity"].get("checked", "equals_one_gpu_run" in res["parity"])),
             "config": res["config"], "impl": res["impl"], "extra": res["extra"]}

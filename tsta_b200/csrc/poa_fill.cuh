@@ -40,7 +40,7 @@
 
 namespace tsta {
 
-constexpr int kPoaC = 4;            // columns per lane
+constexpr int kPoaC = 4;            // columns per lane (widest variant; the kernel is a template: 2 or 4)
 constexpr int kPoaHist = 32;        // history ring depth in rows (power of two)
 constexpr int kPoaNear = kPoaHist - 2;   // predecessors at most this many rows back are read from the ring
 constexpr int kPoaSlotNone = 32;    // extra history slots: "no predecessor" (keys of -infinity),
@@ -53,7 +53,9 @@ constexpr int kPoaBndRing = 64;     // boundary ring (rows)
 constexpr int kPoaTrRing = 64;      // trace ring (rows)
 constexpr int kPoaDescRing = 64;
 constexpr int kPoaKeyMin = INT_MIN / 2;
-constexpr int kPoaSlotBytes = 33 * kPoaC * 8 + 16;   // 1072
+template <int C> constexpr int kPoaSlotBytesC = 33 * C * 8 + 16;   // 1072 / 544: lanes sit one slot apart, and (entry - slot) / 16 is odd,
+                                                                     // so the 16-byte loads of a quarter warp fall on eight different bank groups
+constexpr int kPoaSlotBytes = kPoaSlotBytesC<kPoaC>;
 
 // Row descriptor, built on the host from the CSR graph and staged through shared memory a chunk
 // ahead of the wavefront, so that the inner loop never waits for a dependent global load:
@@ -86,18 +88,20 @@ struct PoaFillArgs {
     int* lastsorce;           // [nrows] H(r, len-1)
 };
 
-struct PoaSmem {
+template <int C>
+struct PoaSmemC {
     // keys of the last kPoaHist rows (+ the three constant slots): entry [slot][lane + 1] holds the
     // lane's C columns as (H*256, Eout*256 + 64); entry [slot][0] is the band's left edge, so that
     // "the previous lane's last column" is one uniform load for every lane
     // (slot stride 1072 B = 67 x 16: lanes sit one row apart, i.e. lane k reads slot t-k, and an odd
     // multiple of 16 bytes spreads the eight 16-byte loads of a quarter warp over all banks)
-    unsigned char hist[kPoaSlots * kPoaSlotBytes];
-    uint16_t tr[kPoaTrRing][32 * kPoaC];     // trace ring
+    unsigned char hist[kPoaSlots * kPoaSlotBytesC<C>];
+    uint16_t tr[kPoaTrRing][32 * C];         // trace ring
     int2 bring[kPoaBndRing];                 // left boundary keys (H(r, j0-1)*256, Fg(r, j0)*256 + 64) by row
     uint4 desc[kPoaDescRing];                // row descriptors
     int kconst[8];                           // scoring constants, read back once (see the kernel)
 };
+using PoaSmem = PoaSmemC<kPoaC>;
 
 // boundary element: low word = key of H (H*256); high word: bits 0-15 Fg-H, bits 17-31 epoch.
 // Fk - Hk = (Fg-H)*256 + 64, so its bytes 1-2 are the 16-bit difference; ep16 = epoch << 1.
@@ -128,6 +132,26 @@ __device__ __forceinline__ void sts_s4(uint32_t addr, int x, int y, int z, int w
 {
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w));
 }
+
+// The (H, Eout) keys of one lane's C columns in a history slot: C == 4: two 16-byte loads, C == 2: one.
+template <int C>
+__device__ __forceinline__ void poa_lds_keys(uint32_t A, int (&h)[C], int (&e)[C])
+{
+    if constexpr (C == 4) {
+        const int4 v01 = lds_s4(A), v23 = lds_s4(A + 16);
+        h[0] = v01.x; e[0] = v01.y; h[1] = v01.z; e[1] = v01.w; h[2] = v23.x; e[2] = v23.y; h[3] = v23.z; e[3] = v23.w;
+    } else {
+        const int4 v01 = lds_s4(A);
+        h[0] = v01.x; e[0] = v01.y; h[1] = v01.z; e[1] = v01.w;
+    }
+}
+template <int C>
+__device__ __forceinline__ void poa_sts_keys(uint32_t A, const int (&ko)[2 * C])
+{
+    sts_s4(A, ko[0], ko[1], ko[2], ko[3]);
+    if constexpr (C == 4) sts_s4(A + 16, ko[4], ko[5], ko[6], ko[7]);
+}
+
 
 // One row of one lane's strip (C columns, serial in F).  In: the reduced predecessor keys kd/ke, the
 // Fg key of the strip's first column and (quirks only) the H key of the left neighbour; out: the
@@ -174,12 +198,14 @@ __device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], 
         tw[c / 2] = __byte_perm(__byte_perm(lo8[c], lo8[c + 1], 0x0040), __byte_perm(hi8[c], hi8[c + 1], 0x0040), 0x5140);
 }
 
+template <int C>
 __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ PoaFillArgs a)
 {
-    constexpr int C = kPoaC;
-    constexpr int kSlotBytes = kPoaSlotBytes;
+    static_assert(C == 2 || C == 4, "strip widths of the POA fill");
+    constexpr int kSlotBytes = kPoaSlotBytesC<C>;
+    constexpr int kEnt = C * 8;                                 // bytes of one lane's entry in a history slot
     extern __shared__ __align__(16) unsigned char poa_smem_raw[];
-    PoaSmem& sm = *reinterpret_cast<PoaSmem*>(poa_smem_raw);
+    PoaSmemC<C>& sm = *reinterpret_cast<PoaSmemC<C>*>(poa_smem_raw);
     const int lane = threadIdx.x;
     int band = 0;
     if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
@@ -217,16 +243,17 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
     unsigned long long* bnd_out = a.bnd + (long long)band * R;
     const bool store_right = (band + 1 < a.nbands) && lane == 31;
     const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(&sm.hist[0]);
-    const uint32_t my_hist = hist_addr + lane * (C * 8);        // this lane's view: +24 previous lane's last H key, +32.. own columns
+    const uint32_t my_hist = hist_addr + lane * kEnt;           // this lane's view: +kEnt-8 previous lane's last H key, +kEnt.. own columns
 
     // ---- constant history slots -------------------------------------------------------------------
     {
         // "no predecessor": keys of -infinity everywhere (also the left edge)
-        sts_s4(hist_addr + kPoaSlotNone * kSlotBytes + (lane + 1) * 32, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
-        sts_s4(hist_addr + kPoaSlotNone * kSlotBytes + (lane + 1) * 32 + 16, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
-        if (lane == 0) {
-            sts_s4(hist_addr + kPoaSlotNone * kSlotBytes, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
-            sts_s4(hist_addr + kPoaSlotNone * kSlotBytes + 16, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
+        {
+            int kmin[2 * C];
+#pragma unroll
+            for (int q = 0; q < 2 * C; q++) kmin[q] = kPoaKeyMin;
+            poa_sts_keys<C>(hist_addr + kPoaSlotNone * kSlotBytes + (lane + 1) * kEnt, kmin);
+            if (lane == 0) poa_sts_keys<C>(hist_addr + kPoaSlotNone * kSlotBytes, kmin);
         }
         // virtual rows above a head (c-t-simd.c:176-188): the H key of column c is only ever read
         // as the DIAGONAL input of column c+1, the E key is Eout_v(c) = Hv(c) + O + E (opened)
@@ -243,11 +270,10 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 k[2 * c + 1] = (Hp + OE) * 256 + 64;
             }
             const uint32_t slot = hist_addr + (kPoaSlotHead + v) * kSlotBytes;
-            sts_s4(slot + (lane + 1) * 32, k[0], k[1], k[2], k[3]);
-            sts_s4(slot + (lane + 1) * 32 + 16, k[4], k[5], k[6], k[7]);
+            poa_sts_keys<C>(slot + (lane + 1) * kEnt, k);
             if (lane == 0) {   // left edge: diagonal input of column j0
                 const int Hd0 = (late && j0 <= L - 1) ? j0 * E : (j0 == 0 ? 0 : O + j0 * E);
-                sts_s4(slot + 16, 0, 0, Hd0 * 256, 0);
+                sts_s4(slot + kEnt - 16, 0, 0, Hd0 * 256, 0);
             }
         }
     }
@@ -260,7 +286,7 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
     const unsigned ep16 = a.epoch << 1;
     // "no predecessor" is the same -infinity for every lane: all lanes read ONE address (a broadcast,
     // one wavefront) instead of their own copy 32 bytes apart (two-way bank conflicts on every load)
-    const uint32_t none_addr = hist_addr + kPoaSlotNone * kSlotBytes + 32;
+    const uint32_t none_addr = hist_addr + kPoaSlotNone * kSlotBytes + kEnt;
     // flags (descriptor bits 16..) that take a lane out of the PLAIN step: slow / spilled rows always,
     // late heads only in the lanes that own column L-1 or L; every row when the strip has an 'N'
     const unsigned unplain = hasN ? 0xffffffffu : (((kPoaSlow | kPoaKeep) | (hasL ? kPoaLate : 0u)) << 16);
@@ -335,27 +361,29 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 int kd[C], ke[C];
                 {
                     const uint32_t A = my_hist + (dsc.y & 0xffu) * kSlotBytes;
-                    const int Hd0 = lds_s32(A + 24);
-                    const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
-                    kd[0] = Hd0 + 255; kd[1] = v01.x + 255; kd[2] = v01.z + 255; kd[3] = v23.x + 255;
-                    ke[0] = v01.y + 127; ke[1] = v01.w + 127; ke[2] = v23.y + 127; ke[3] = v23.w + 127;
+                    const int Hd0 = lds_s32(A + kEnt - 8);
+                    int ph[C], pe[C];
+                    poa_lds_keys<C>(A + kEnt, ph, pe);
+                    kd[0] = Hd0 + 255;
+#pragma unroll
+                    for (int c = 1; c < C; c++) kd[c] = ph[c - 1] + 255;
+#pragma unroll
+                    for (int c = 0; c < C; c++) ke[c] = pe[c] + 127;
                 }
 #pragma unroll
                 for (int j = 1; j < kPoaFast; j++) {
                     if (j >= 3 && j >= maxnp) break;
                     const uint32_t slot = ((j < 4 ? dsc.y : dsc.z) >> (8 * (j & 3))) & 0xffu;
                     const uint32_t A = slot == kPoaSlotNone ? none_addr : my_hist + slot * kSlotBytes;
-                    const int Hd0 = lds_s32(A + 24);
-                    const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
+                    const int Hd0 = lds_s32(A + kEnt - 8);
+                    int ph[C], pe[C];
+                    poa_lds_keys<C>(A + kEnt, ph, pe);
                     const int wd = 192 + 63 - j, we = 64 + 63 - j;
                     kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
-                    kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
-                    kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
-                    kd[3] = __viaddmax_s32(v23.x, wd, kd[3]);
-                    ke[0] = __viaddmax_s32(v01.y, we, ke[0]);
-                    ke[1] = __viaddmax_s32(v01.w, we, ke[1]);
-                    ke[2] = __viaddmax_s32(v23.y, we, ke[2]);
-                    ke[3] = __viaddmax_s32(v23.w, we, ke[3]);
+#pragma unroll
+                    for (int c = 1; c < C; c++) kd[c] = __viaddmax_s32(ph[c - 1], wd, kd[c]);
+#pragma unroll
+                    for (int c = 0; c < C; c++) ke[c] = __viaddmax_s32(pe[c], we, ke[c]);
                 }
                 int ko[2 * C];
                 uint32_t tw[C / 2];
@@ -363,10 +391,10 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 poa_row<C, false>(kd, ke, rc, isL, isLm1, b, MS, XS, ES, ES64, ES128, OES, 0, Fk, Hl, ko, tw);
                 Hout = Hl; Fout = Fk;
                 const uint32_t own = my_hist + ((uint32_t)r & (kPoaHist - 1)) * kSlotBytes;
-                sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
-                sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
-                if (lane == 0) sts_u32(own + 24, (uint32_t)Hleft_in);
-                sts_u2(tr_addr + rm * (32 * C * 2), tw[0], tw[1]);
+                poa_sts_keys<C>(own + kEnt, ko);
+                if (lane == 0) sts_u32(own + kEnt - 8, (uint32_t)Hleft_in);
+                if constexpr (C == 4) sts_u2(tr_addr + rm * (32 * C * 2), tw[0], tw[1]);
+                else sts_u32(tr_addr + rm * (32 * C * 2), tw[0]);
                 if (owns_last) {
                     int hk = ko[0];
 #pragma unroll
@@ -388,27 +416,29 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     // ---- fast path: up to eight predecessors, all inside the history ring ----------
                     {   // predecessor 0: every row has one (heads: the virtual row's slot)
                         const uint32_t A = my_hist + (dsc.y & 0xffu) * kSlotBytes;
-                        const int Hd0 = lds_s32(A + 24);
-                        const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
-                        kd[0] = Hd0 + 255; kd[1] = v01.x + 255; kd[2] = v01.z + 255; kd[3] = v23.x + 255;
-                        ke[0] = v01.y + 127; ke[1] = v01.w + 127; ke[2] = v23.y + 127; ke[3] = v23.w + 127;
+                        const int Hd0 = lds_s32(A + kEnt - 8);
+                        int ph[C], pe[C];
+                        poa_lds_keys<C>(A + kEnt, ph, pe);
+                        kd[0] = Hd0 + 255;
+#pragma unroll
+                        for (int c = 1; c < C; c++) kd[c] = ph[c - 1] + 255;
+#pragma unroll
+                        for (int c = 0; c < C; c++) ke[c] = pe[c] + 127;
                     }
 #pragma unroll
                     for (int j = 1; j < kPoaFast; j++) {
                         if (j >= 2 && j >= maxnp) break;
                         const uint32_t slot = ((j < 4 ? dsc.y : dsc.z) >> (8 * (j & 3))) & 0xffu;
                         const uint32_t A = slot == kPoaSlotNone ? none_addr : my_hist + slot * kSlotBytes;
-                        const int Hd0 = lds_s32(A + 24);
-                        const int4 v01 = lds_s4(A + 32), v23 = lds_s4(A + 48);
+                        const int Hd0 = lds_s32(A + kEnt - 8);
+                        int ph[C], pe[C];
+                        poa_lds_keys<C>(A + kEnt, ph, pe);
                         const int wd = 192 + 63 - j, we = 64 + 63 - j;
                         kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
-                        kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
-                        kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
-                        kd[3] = __viaddmax_s32(v23.x, wd, kd[3]);
-                        ke[0] = __viaddmax_s32(v01.y, we, ke[0]);
-                        ke[1] = __viaddmax_s32(v01.w, we, ke[1]);
-                        ke[2] = __viaddmax_s32(v23.y, we, ke[2]);
-                        ke[3] = __viaddmax_s32(v23.w, we, ke[3]);
+#pragma unroll
+                        for (int c = 1; c < C; c++) kd[c] = __viaddmax_s32(ph[c - 1], wd, kd[c]);
+#pragma unroll
+                        for (int c = 0; c < C; c++) ke[c] = __viaddmax_s32(pe[c], we, ke[c]);
                     }
                 } else {
                     // ---- slow path: any in-degree, predecessors further back than the ring ----------
@@ -418,31 +448,31 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                     const int e0 = (int)dsc.z;
                     for (int j = 0; j < npre; j++) {
                         const int p = __ldg(a.pred_row + e0 + j);
-                        int4 v01, v23;
+                        int ph[C], pe[C];
                         int Hd0;
                         if (p < 0 || r - p <= kPoaNear) {
                             const int slot = p < 0 ? ((flags & kPoaLate) ? kPoaSlotLate : kPoaSlotHead) : (p & (kPoaHist - 1));
                             const uint32_t A = my_hist + slot * kSlotBytes;
-                            Hd0 = lds_s32(A + 24);
-                            v01 = lds_s4(A + 32);
-                            v23 = lds_s4(A + 48);
+                            Hd0 = lds_s32(A + kEnt - 8);
+                            poa_lds_keys<C>(A + kEnt, ph, pe);
                         } else {
                             const int2* src = a.HE + (long long)__ldg(&a.desc[p].w) * a.stride + j0;
-                            v01 = __ldcg(reinterpret_cast<const int4*>(src));
-                            v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
+                            const int4 v01 = __ldcg(reinterpret_cast<const int4*>(src));
+                            ph[0] = v01.x; pe[0] = v01.y; ph[1] = v01.z; pe[1] = v01.w;
+                            if constexpr (C == 4) {
+                                const int4 v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
+                                ph[2] = v23.x; pe[2] = v23.y; ph[3] = v23.z; pe[3] = v23.w;
+                            }
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
                             else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p);
                             else Hd0 = __ldg(a.hneg1 + p) * 256;
                         }
                         const int wd = 192 + 63 - j, we = 64 + 63 - j;
                         kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
-                        kd[1] = __viaddmax_s32(v01.x, wd, kd[1]);
-                        kd[2] = __viaddmax_s32(v01.z, wd, kd[2]);
-                        kd[3] = __viaddmax_s32(v23.x, wd, kd[3]);
-                        ke[0] = __viaddmax_s32(v01.y, we, ke[0]);
-                        ke[1] = __viaddmax_s32(v01.w, we, ke[1]);
-                        ke[2] = __viaddmax_s32(v23.y, we, ke[2]);
-                        ke[3] = __viaddmax_s32(v23.w, we, ke[3]);
+#pragma unroll
+                        for (int c = 1; c < C; c++) kd[c] = __viaddmax_s32(ph[c - 1], wd, kd[c]);
+#pragma unroll
+                        for (int c = 0; c < C; c++) ke[c] = __viaddmax_s32(pe[c], we, ke[c]);
                     }
                 }
 
@@ -461,15 +491,15 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
                 // history ring (own columns + the band's left edge), HBM spill for far successors, trace ring
                 {
                     const uint32_t own = my_hist + ((uint32_t)r & (kPoaHist - 1)) * kSlotBytes;
-                    sts_s4(own + 32, ko[0], ko[1], ko[2], ko[3]);
-                    sts_s4(own + 48, ko[4], ko[5], ko[6], ko[7]);
-                    if (lane == 0) sts_u32(own + 24, (uint32_t)Hleft_in);
+                    poa_sts_keys<C>(own + kEnt, ko);
+                    if (lane == 0) sts_u32(own + kEnt - 8, (uint32_t)Hleft_in);
                     if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
                         int2* g = a.HE + (long long)dsc.w * a.stride + j0;
                         *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
-                        *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
+                        if constexpr (C == 4) *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
                     }
-                    sts_u2(tr_addr + rm * (32 * C * 2), tw[0], tw[1]);
+                    if constexpr (C == 4) sts_u2(tr_addr + rm * (32 * C * 2), tw[0], tw[1]);
+                    else sts_u32(tr_addr + rm * (32 * C * 2), tw[0]);
                 }
                 if (last_band) {
                     if (owns_last) {
@@ -488,19 +518,20 @@ __global__ void __launch_bounds__(32) poa_fill_kernel(const __grid_constant__ Po
         {
             const int hi = min(R, max(0, t0 + kPoaChunk - 31));
             const int lo = min(R, max(0, t0 - 31));
-            constexpr int kUnits = 32 * C * 2 / 16;    // 16 units per row
+            constexpr int kUnits = 32 * C * 2 / 16;    // 16-byte units per row: 16 (C == 4) or 8 (C == 2)
+            constexpr int kRowsPerPass = 32 / kUnits;  // rows the warp covers with one load per lane
             const int units = (hi - lo) * kUnits;
             if (hi - lo == kPoaChunk) {
-                // a whole chunk: lane u handles part u%16 of rows lo + u/16 + 2k -- eight independent load/store pairs
+                // a whole chunk: lane u handles part u % kUnits of rows lo + u / kUnits + kRowsPerPass * k -- independent load/store pairs
                 const int part = lane % kUnits;
                 uint16_t* dst = a.trace + (long long)(lo + lane / kUnits) * a.stride + (long long)band * 32 * C + part * 8;
-                uint4 v[kPoaChunk / 2];
+                uint4 v[kPoaChunk / kRowsPerPass];
 #pragma unroll
-                for (int k = 0; k < kPoaChunk / 2; k++)
-                    v[k] = *reinterpret_cast<const uint4*>(&sm.tr[(lo + lane / kUnits + 2 * k) & (kPoaTrRing - 1)][part * 8]);
+                for (int k = 0; k < kPoaChunk / kRowsPerPass; k++)
+                    v[k] = *reinterpret_cast<const uint4*>(&sm.tr[(lo + lane / kUnits + kRowsPerPass * k) & (kPoaTrRing - 1)][part * 8]);
 #pragma unroll
-                for (int k = 0; k < kPoaChunk / 2; k++)
-                    __stcs(reinterpret_cast<uint4*>(dst + (long long)(2 * k) * a.stride), v[k]);
+                for (int k = 0; k < kPoaChunk / kRowsPerPass; k++)
+                    __stcs(reinterpret_cast<uint4*>(dst + (long long)(kRowsPerPass * k) * a.stride), v[k]);
             } else
             for (int u = lane; u < units; u += 32) {
                 const int row = lo + u / kUnits, part = u % kUnits;

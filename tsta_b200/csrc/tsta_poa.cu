@@ -23,7 +23,7 @@ struct tsta_poa {
     DevBuf d_rowptr, d_pred, d_base, d_hneg1, d_read, d_HE, d_trace, d_bnd, d_ctl, d_last, d_path, d_desc;
     std::vector<uint4> h_desc;
     unsigned epoch = 0;
-    int nrows = 0, len = 0, nbands = 0;
+    int nrows = 0, len = 0, nbands = 0, C = kPoaC;
     long long stride = 0;
     bool filled = false;
     int launches = 0;
@@ -61,7 +61,9 @@ int tsta_poa_create(tsta_poa** out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreate(&p->ev[k]);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(poa_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaSmem));
+        e = cudaFuncSetAttribute(poa_fill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaSmemC<4>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(poa_fill_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaSmemC<2>));
     if (e != cudaSuccess) {
         poa_free(p);
         return set_error(TSTA_ECUDA, "POA context creation failed: %s", cudaGetErrorString(e));
@@ -144,7 +146,12 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
         q.w = ((q.x >> 16) & kPoaKeep) ? (unsigned)nkeep++ : 0u;
     }
     p->n_keep += (long long)nkeep;
-    const int band_cols = 32 * kPoaC;
+    // Strip width.  The kernel is a template (2 or 4 columns per lane).  Measured on 16 x 50 kbp: 4 columns (391 bands)
+    // fill in 398 ms, 2 columns (782 bands, two per SM sub-partition) in 445 ms -- the fixed cost of a step (shuffle,
+    // history round trip, descriptor) does not shrink with the strip, and twice the bands double the start-up.
+    p->C = 4;
+    if (const char* e = getenv("TSTA_POA_C")) { const int c = atoi(e); if (c == 2 || c == 4) p->C = c; }
+    const int band_cols = 32 * p->C;
     p->nbands = (len + band_cols - 1) / band_cols;
     p->stride = (long long)p->nbands * band_cols;
     p->nrows = nrows;
@@ -171,7 +178,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     if (int rc = grow(p->d_path, (size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
     {   // grow generously: the graph gains rows every round
         const size_t cells = (size_t)nrows * (size_t)p->stride;
-        const size_t spill = std::max<size_t>(nkeep, 1) * (size_t)(((len + 32 * kPoaC - 1) / (32 * kPoaC)) * 32 * kPoaC) * sizeof(int2);
+        const size_t spill = std::max<size_t>(nkeep, 1) * (size_t)p->stride * sizeof(int2);
         if (int rc = grow(p->d_HE, spill)) return rc;
         if (int rc = grow(p->d_trace, cells * 2)) return rc;
         const size_t need = (size_t)p->nbands * (size_t)nrows * 8;
@@ -207,7 +214,11 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     a.ticket = p->d_ctl.as<unsigned>();
     a.lastsorce = p->d_last.as<int>();
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
-    { NvtxRange range("tsta_poa fill"); poa_fill_kernel<<<p->nbands, 32, sizeof(PoaSmem), p->stream>>>(a); }
+    {
+        NvtxRange range("tsta_poa fill");
+        if (p->C == 2) poa_fill_kernel<2><<<p->nbands, 32, sizeof(PoaSmemC<2>), p->stream>>>(a);
+        else poa_fill_kernel<4><<<p->nbands, 32, sizeof(PoaSmemC<4>), p->stream>>>(a);
+    }
     TSTA_CUDA_TRY(cudaGetLastError());
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(lastsorce, p->d_last.p, (size_t)nrows * 4, cudaMemcpyDeviceToHost, p->stream));
