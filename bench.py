@@ -665,15 +665,17 @@ def wl_batch(ctx, name, steps):
     s0, o0, l0, s1, o1, l1 = [p.array for p in pins]
     outs = [api.PinnedArray(npairs, np.int32), api.PinnedArray(npairs, np.int32)]
     if trace:
-        ops_off = np.arange(npairs, dtype=np.int64) * (2 * ln)
-        outs += [api.PinnedArray(npairs * 2 * ln, np.uint8), api.pinned_copy(ops_off), api.PinnedArray(npairs, np.int32)]
+        # moves come back packed four to a byte (tsta_psa_batch_packed): 2 bits are all a move needs
+        slot = (2 * ln + 3) & ~3
+        ops_off = np.arange(npairs, dtype=np.int64) * slot
+        outs += [api.PinnedArray(npairs * slot // 4, np.uint8), api.pinned_copy(ops_off), api.PinnedArray(npairs, np.int32)]
     out = tuple(p.array for p in outs)
     torch = ctx.torch
     gathered = None
 
     def one_step():
         nonlocal gathered
-        r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, out=out, **prm)
+        r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, out=out, packed=trace, **prm)
         if strong and world > 1:
             # the job ends when rank 0 holds every pair's result: ONE all_gather of (maxsorce, corner) per step
             mine = torch.from_numpy(np.stack([r.maxsorce, r.corner])).cuda()
@@ -761,9 +763,8 @@ def batch_parity(a, b, r, prm, trace, ln, samples=6):
         ms, out = ref_one_pair(x, y, prm, trace, 4 if ln <= 1000 else 10, 2.0 if ln <= 1000 else 6.0)
         ok = ok and ms == int(r.maxsorce[k])
         if trace:
-            cap = 2 * ln
             nal = int(r._alen[k])
-            ops = r._ops[r._ops_off[k] + cap - nal: r._ops_off[k] + cap]
+            ops = r.moves(k, 2 * ln)
             A = np.full(nal, ord("-"), dtype=np.uint8)
             B = np.full(nal, ord("-"), dtype=np.uint8)
             A[ops != 2] = a[k]

@@ -154,6 +154,18 @@ int  tsta_psa_batch(const tsta_params* p, int64_t npairs,
                     uint8_t* ops, const int64_t* ops_off, int32_t* alen,
                     float* kernel_ms);
 
+/* The same with the moves PACKED four to a byte (always with traceback): a quarter of the bytes that
+ * travel back over PCIe.  ops_off[k] still counts MOVES and must be a multiple of 4; move p of pair k's
+ * slot (the alignment again occupies the last alen[k] of its len0+len1 positions) is bits 2(p & 3) .. +1 of
+ * byte (ops_off[k] + p) >> 2 of ops2, same codes (1 / 0 / 2).  ops2 holds at least max(ops_off+len0+len1)/4
+ * rounded up bytes. */
+int  tsta_psa_batch_packed(const tsta_params* p, int64_t npairs,
+                           const char* seqs0, const int64_t* off0, const int32_t* len0,
+                           const char* seqs1, const int64_t* off1, const int32_t* len1,
+                           int32_t* maxsorce, int32_t* corner,
+                           uint8_t* ops2, const int64_t* ops_off, int32_t* alen,
+                           float* kernel_ms);
+
 /* ------------------------------------------------------------------------------------ */
 /* Sequence-to-graph alignment (TSTA_msa)                                                */
 /* ------------------------------------------------------------------------------------ */

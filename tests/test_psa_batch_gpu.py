@@ -93,3 +93,19 @@ def test_batch_equals_single_pair_path_at_scale(gpu):
         o = ob.psa(*pairs[k])
         assert (r0.maxsorce[k], r0.corner[k]) == (o.maxsorce, o.corner)
         assert r1.output_bytes(k) == o.output_bytes()
+
+
+@pytest.mark.parametrize("chunks", [1, 4])
+def test_packed_moves_equal_byte_moves(gpu, chunks, monkeypatch):
+    """tsta_psa_batch_packed (four moves per byte, what travels back over PCIe in bench.py) decodes to the
+    alignments of the byte form and of the oracle, for ragged lengths and chunked downloads."""
+    monkeypatch.setenv("TSTA_BATCH_CHUNKS", str(chunks))
+    pairs = _mixed_pairs(400, 11, [1, 2, 3, 5, 30, 100, 127, 128, 129, 250, 255, 256, 257, 300, 700])
+    rb = gpu.psa_batch(pairs, trace=True)
+    rp = gpu.psa_batch(pairs, trace=True, packed=True)
+    assert (rb.maxsorce == rp.maxsorce).all() and (rb.corner == rp.corner).all() and (rb._alen == rp._alen).all()
+    assert rp._ops.nbytes * 3 < rb._ops.nbytes
+    for k, (x, y) in enumerate(pairs):
+        assert rp.output_bytes(k) == rb.output_bytes(k), k
+        if k % 7 == 0:
+            assert rp.output_bytes(k) == ob.psa(x, y).output_bytes(), k

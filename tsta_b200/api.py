@@ -308,13 +308,27 @@ class BatchResult:
     _ops_off: np.ndarray | None = None
     _alen: np.ndarray | None = None
     _pairs: list | None = None
+    _packed: bool = False           # moves packed four to a byte (tsta_psa_batch_packed)
+
+    def moves(self, k: int, cap: int) -> np.ndarray:
+        """The alen[k] moves of pair k in reading order (1 both bases, 0 s0 base against a gap, 2 gap against an s1 base);
+        cap = len0 + len1 of the pair (the size of its slot)."""
+        n = int(self._alen[k])
+        o = int(self._ops_off[k])
+        if not self._packed:
+            return self._ops[o + cap - n: o + cap]
+        b0 = (o + cap - n) >> 2
+        raw = self._ops[b0: ((o + cap + 3) >> 2)]
+        two = ((raw[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(-1)
+        first = (o + cap - n) - 4 * b0
+        return two[first: first + n]
 
     def alignment(self, k: int):
         """(a, b) strings of pair k exactly as TSTA_psa would write them (">1" = longer read)."""
         s0, s1 = self._pairs[k]
         cap = len(s0) + len(s1)
         n = int(self._alen[k])
-        ops = self._ops[self._ops_off[k] + cap - n: self._ops_off[k] + cap]
+        ops = self.moves(k, cap)
         A = np.full(n, ord("-"), dtype=np.uint8)
         B = np.full(n, ord("-"), dtype=np.uint8)
         A[ops != 2] = np.frombuffer(s0, dtype=np.uint8)
@@ -326,7 +340,7 @@ class BatchResult:
         return b">1\n" + a + b"\n>2\n" + b
 
 
-def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False) -> BatchResult:
+def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False, packed=False) -> BatchResult:
     """Many independent pairs through tsta_psa_batch.  `pairs` is a list of (x, y) byte strings
     in any order; each pair is swapped like psa/psa.c:194-199."""
     ordered = [order_pair(x, y) for x, y in pairs]
@@ -342,11 +356,11 @@ def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False) -> BatchResult:
     seqs0 = b"".join(a for a, _ in ordered) or b"\0"
     seqs1 = b"".join(b for _, b in ordered) or b"\0"
     return psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M, X, E, O, trace,
-                            pairs=ordered, swapped=swapped)
+                            pairs=ordered, swapped=swapped, packed=packed)
 
 
 def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4, trace=False,
-                     pairs=None, swapped=None, out=None) -> BatchResult:
+                     pairs=None, swapped=None, out=None, packed=False) -> BatchResult:
     """Array form of tsta_psa_batch (what bench.py uses; no per-pair Python objects).
     `out` = (maxsorce, corner[, ops, ops_off, alen]) preallocated arrays (e.g. pinned) to write into."""
     npairs = len(len0)
@@ -359,23 +373,35 @@ def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4
         ops, ops_off, alen = out[2], out[3], out[4]
     elif trace:
         cap = len0.astype(np.int64) + len1.astype(np.int64)
+        if packed:
+            cap = (cap + 3) & ~3                    # packed slots start at multiples of four moves
         ops_off = np.zeros(npairs, dtype=np.int64)
         if npairs:
             ops_off[1:] = np.cumsum(cap[:-1])
-        ops = np.zeros(max(int(cap.sum()), 1), dtype=np.uint8)
+        ops = np.zeros(max(int(cap.sum()) // (4 if packed else 1), 1), dtype=np.uint8)
         alen = np.zeros(npairs, dtype=np.int32)
     b0 = seqs0 if isinstance(seqs0, bytes) else seqs0.ctypes.data
     b1 = seqs1 if isinstance(seqs1, bytes) else seqs1.ctypes.data
-    _check(load().tsta_psa_batch(
-        C.byref(p), npairs,
-        C.cast(b0, C.c_void_p), off0.ctypes.data, len0.ctypes.data,
-        C.cast(b1, C.c_void_p), off1.ctypes.data, len1.ctypes.data,
-        int(trace), ms.ctypes.data, corner.ctypes.data,
-        ops.ctypes.data if trace else None, ops_off.ctypes.data if trace else None,
-        alen.ctypes.data if trace else None, C.byref(kms)))
+    if trace and packed:
+        L = load()
+        L.tsta_psa_batch_packed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.tsta_psa_batch_packed(
+            C.byref(p), npairs,
+            C.cast(b0, C.c_void_p), off0.ctypes.data, len0.ctypes.data,
+            C.cast(b1, C.c_void_p), off1.ctypes.data, len1.ctypes.data,
+            ms.ctypes.data, corner.ctypes.data, ops.ctypes.data, ops_off.ctypes.data, alen.ctypes.data, C.byref(kms)))
+    else:
+        _check(load().tsta_psa_batch(
+            C.byref(p), npairs,
+            C.cast(b0, C.c_void_p), off0.ctypes.data, len0.ctypes.data,
+            C.cast(b1, C.c_void_p), off1.ctypes.data, len1.ctypes.data,
+            int(trace), ms.ctypes.data, corner.ctypes.data,
+            ops.ctypes.data if trace else None, ops_off.ctypes.data if trace else None,
+            alen.ctypes.data if trace else None, C.byref(kms)))
     return BatchResult(ms, corner, kms.value,
                        swapped if swapped is not None else np.zeros(npairs, dtype=bool),
-                       ops, ops_off, alen, pairs)
+                       ops, ops_off, alen, pairs, bool(trace and packed))
 
 
 # ------------------------------------------------------------------------------------------

@@ -504,6 +504,9 @@ struct PsaBatchTraceArgs {
     int enc;                     // see PsaTraceArgs
 };
 
+// PACK: four moves per byte (move p of the slot in bits 2(p & 3) of byte (ops_off + p) >> 2; ops_off is a
+// multiple of four): a quarter of the bytes that cross PCIe afterwards.
+template <bool PACK>
 static __global__ void __launch_bounds__(128) psa_batch_trace_kernel(const PsaBatchTraceArgs a)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,18 +515,32 @@ static __global__ void __launch_bounds__(128) psa_batch_trace_kernel(const PsaBa
     const long long stride = (long long)((n + a.cols_per_band - 1) / a.cols_per_band) * (a.cols_per_band / 2);
     const uint8_t* d = a.dirs + a.dirs_off[k];
     uint8_t* ops = a.ops + a.ops_off[k] + (n + m - 1);   // written backwards
+    uint8_t* packed = a.ops + (a.ops_off[k] >> 2);
     int i = m - 1, j = n - 1, forced = -1, nops = 0;
+    unsigned acc = 0;
+    auto put = [&](int mv) {
+        if (PACK) {
+            const int p = n + m - 1 - nops;               // position in the slot, descending
+            acc |= (unsigned)mv << (2 * (p & 3));
+            if ((p & 3) == 0) { packed[p >> 2] = (uint8_t)acc; acc = 0; }
+        } else ops[-nops] = (uint8_t)mv;
+        nops++;
+    };
     while (i >= 0 && j >= 0) {
         const uint8_t byte = __ldcs(d + (long long)i * stride + (j >> 1));
         const int c = (j & 1) ? (byte >> 4) : (byte & 15);
         const int mv = forced >= 0 ? forced : psa_back_move(c, a.enc);
-        ops[-(nops++)] = (uint8_t)mv;
+        put(mv);
         if (mv == 1) { i--; j--; forced = -1; }
         else if (mv == 0) { forced = (c & 4) ? 0 : -1; j--; }
         else { forced = (c & 8) ? 2 : -1; i--; }
     }
-    while (j >= 0) { ops[-(nops++)] = 0; j--; }
-    while (i >= 0) { ops[-(nops++)] = 2; i--; }
+    while (j >= 0) { put(0); j--; }
+    while (i >= 0) { put(2); i--; }
+    if (PACK) {
+        const int p = n + m - 1 - nops;                   // next (unwritten) position: flush a partly filled byte
+        if ((p & 3) != 3) packed[p >> 2] = (uint8_t)acc;
+    }
     a.alen[k] = nops;
 }
 

@@ -85,12 +85,39 @@ struct Guard {   // shim over the persistent context: same call sites as a scope
 constexpr int kBatchWarps = 4;
 }  // namespace
 
+static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
+                          const char* seqs0, const int64_t* off0, const int32_t* len0,
+                          const char* seqs1, const int64_t* off1, const int32_t* len1,
+                          int want_trace, int32_t* maxsorce, int32_t* corner,
+                          uint8_t* ops, const int64_t* ops_off, int32_t* alen,
+                          float* kernel_ms, const bool pack2);
+
 extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                               const char* seqs0, const int64_t* off0, const int32_t* len0,
                               const char* seqs1, const int64_t* off1, const int32_t* len1,
                               int want_trace, int32_t* maxsorce, int32_t* corner,
                               uint8_t* ops, const int64_t* ops_off, int32_t* alen,
                               float* kernel_ms)
+{
+    return psa_batch_impl(prm, npairs, seqs0, off0, len0, seqs1, off1, len1, want_trace, maxsorce, corner, ops, ops_off, alen, kernel_ms, false);
+}
+
+extern "C" int tsta_psa_batch_packed(const tsta_params* prm, int64_t npairs,
+                                     const char* seqs0, const int64_t* off0, const int32_t* len0,
+                                     const char* seqs1, const int64_t* off1, const int32_t* len1,
+                                     int32_t* maxsorce, int32_t* corner,
+                                     uint8_t* ops2, const int64_t* ops_off, int32_t* alen,
+                                     float* kernel_ms)
+{
+    return psa_batch_impl(prm, npairs, seqs0, off0, len0, seqs1, off1, len1, 1, maxsorce, corner, ops2, ops_off, alen, kernel_ms, true);
+}
+
+static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
+                          const char* seqs0, const int64_t* off0, const int32_t* len0,
+                          const char* seqs1, const int64_t* off1, const int32_t* len1,
+                          int want_trace, int32_t* maxsorce, int32_t* corner,
+                          uint8_t* ops, const int64_t* ops_off, int32_t* alen,
+                          float* kernel_ms, const bool pack2)
 {
     if (kernel_ms) *kernel_ms = 0.f;
     if (int rc = check_params(prm)) return rc;
@@ -113,6 +140,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
         cells += (double)len0[k] * (double)len1[k];
         if (want_trace) {
             if (ops_off[k] < 0) return set_error(TSTA_EINVAL, "pair %lld: negative ops_off", (long long)k);
+            if (pack2 && (ops_off[k] & 3)) return set_error(TSTA_EINVAL, "pair %lld: packed moves need ops_off to be a multiple of 4", (long long)k);
             ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
         }
     }
@@ -213,7 +241,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     size_t dirs_budget = 0;
     if (want_trace) {
         size_t free_b = 0, total_b = 0;
-        if (int rc = g.alloc(&d_ops, (size_t)ops_total, g_ctx.ops)) return rc;
+        if (int rc = g.alloc(&d_ops, (size_t)(pack2 ? (ops_total + 3) / 4 + 4 : ops_total), g_ctx.ops)) return rc;
         if (int rc = g.alloc(&d_ops_off, (size_t)npairs, g_ctx.ops_off)) return rc;
         if (int rc = g.alloc(&d_alen, (size_t)npairs, g_ctx.alen)) return rc;
         if (int rc = g.alloc(&d_dirs_off, (size_t)npairs, g_ctx.dirs_off)) return rc;
@@ -314,7 +342,8 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                 t.len0 = d_len0 + k0; t.len1 = d_len1 + k0; t.npairs = k1 - k0;
                 t.cols_per_band = band_cols;
                 t.ops = d_ops; t.ops_off = d_ops_off + k0; t.alen = d_alen + k0;
-                psa_batch_trace_kernel<<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
+                if (pack2) psa_batch_trace_kernel<true><<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
+                else psa_batch_trace_kernel<false><<<(unsigned)((k1 - k0 + 127) / 128), 128, 0, g.st>>>(t);
             } else if (packed && dual) {
                 // short reads: two pairs per warp (psa_sweep_dual16), 32*Cd columns each
                 if (Cd == 4) psa_batch16_dual_kernel<4, false, kBatchWarps><<<blocks, 32 * kBatchWarps, 0, g.st>>>(a);
@@ -341,6 +370,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                 hi = std::max<int64_t>(hi, ops_off[k] + len0[k] + len1[k]);
             }
             if (last_done) TSTA_CUDA_TRY(cudaStreamWaitEvent(g_ctx.dh, last_done, 0));
+            if (pack2) { lo >>= 2; hi = (hi + 3) >> 2; }      // (slots start at multiples of four moves: chunks do not share a byte)
             if (hi > lo) TSTA_CUDA_TRY(cudaMemcpyAsync(ops + lo, d_ops + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, g_ctx.dh));
         }
     }
@@ -348,7 +378,7 @@ extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
     TSTA_CUDA_TRY(cudaMemcpyAsync(corner, d_corner, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
     if (want_trace) {
         TSTA_CUDA_TRY(cudaMemcpyAsync(alen, d_alen, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
-        if (nch == 1) TSTA_CUDA_TRY(cudaMemcpyAsync(ops, d_ops, (size_t)ops_total, cudaMemcpyDeviceToHost, g.st));
+        if (nch == 1) TSTA_CUDA_TRY(cudaMemcpyAsync(ops, d_ops, (size_t)(pack2 ? (ops_total + 3) / 4 : ops_total), cudaMemcpyDeviceToHost, g.st));
     }
     TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
     TSTA_CUDA_TRY(cudaStreamSynchronize(g_ctx.dh));
