@@ -196,6 +196,23 @@ static int choose_strip16(int64_t n, int sms)
     return 8;
 }
 
+// Column slices over several GPUs: the strip width that minimises the time model of DESIGN.md 5,
+//     T(C) = tau(C) * (rows + bands of the WHOLE pair * lag),   tau(C) = 39 + 11 C cycles,   lag = 118 steps,
+// among the widths that give this GPU at most one band per sub-partition.  (The slice's own length alone would pick
+// narrow strips -- fewer columns per GPU -- and with them more bands in the chain: 0.86 x at two GPUs on 100 kbp.)
+static int choose_strip16_slice(int64_t n_slice, int64_t n_total, int64_t m, int sms)
+{
+    const int64_t slots = (int64_t)sms * 4;
+    int best = 8;
+    double best_t = 1e300;
+    for (int c : {2, 3, 4, 6, 8}) {
+        if ((n_slice + 64 * c - 1) / (64 * c) > slots && c != 8) continue;
+        const double t = (39.0 + 11.0 * c) * ((double)m + (double)((n_total + 64 * c - 1) / (64 * c)) * 118.0);
+        if (t < best_t) { best_t = t; best = c; }
+    }
+    return best;
+}
+
 // Lane strip width for one long pair: the pipeline runs at the speed of its slowest band,
 // so prefer at most one band (warp) per SM sub-partition (4 per SM) and widen the strips
 // when the read is long enough to need more.
@@ -574,7 +591,7 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
     p->packed = false;
     {
         const bool tr = p->want_trace != 0;
-        int c16 = choose_strip16(n, p->sms);
+        int c16 = (has_left || has_right) ? choose_strip16_slice(n, n_total, m, p->sms) : choose_strip16(n, p->sms);
         if (const char* e = getenv("TSTA_PSA_C16")) {
             const int c = atoi(e);
             if (c == 2 || c == 3 || c == 4 || c == 6 || c == 8) c16 = c;
