@@ -127,6 +127,15 @@ __device__ __forceinline__ void ring16_put(SM& sm, int row, uint2 v)
     if (k < kMaxChunkRows) sm.rowring[kRing16 + k] = v;
 }
 
+// The row-table ring through a 32-bit shared address (the generic form makes the compiler rebuild the shared window
+// base -- S2UR + ULEA -- in front of every access of the chunk-boundary code).
+__device__ __forceinline__ void ring16_put_at(uint32_t ring_addr, int row, uint2 v)
+{
+    const int k = row & (kRing16 - 1);
+    sts_u2(ring_addr + 8u * k, v.x, v.y);
+    if (k < kMaxChunkRows) sts_u2(ring_addr + 8u * (kRing16 + k), v.x, v.y);
+}
+
 // Slow path of the hand-off poll (every 65536th stale poll): true when the run was aborted or this warp has
 // waited longer than timeout_ns, in which case the abort flag is raised for everybody else.
 static __device__ __noinline__ bool psa_handoff_expired(int* abort_flag, unsigned long long timeout_ns, unsigned long long& t_wait, int lane)
@@ -469,6 +478,12 @@ __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint
 #ifndef TSTA_FAST_RAMP
 #define TSTA_FAST_RAMP 1
 #endif
+#ifndef TSTA_DEBUG_ASSERTS
+#define TSTA_DEBUG_ASSERTS 0
+#endif
+#if TSTA_DEBUG_ASSERTS
+#include <assert.h>
+#endif
 #ifndef TSTA_WATCHDOG
 #define TSTA_WATCHDOG 1
 #endif
@@ -566,10 +581,16 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     const int nchunks = (nsteps + CH - 1) / CH;
     const bool export_right = (b.band + 1 < b.nbands || b.has_right) && b.bnd_out != nullptr;
     const bool import_left = b.band > 0 || b.has_left;
-    const unsigned epoch = PIPE ? b.epoch : 1u;
+    // Debug build (-DTSTA_DEBUG_ASSERTS=1; compute-sanitizer is not available on the pool): the batched sweep parks a
+    // band's right boundary IN PLACE in the column the next band reads (row r is prefetched one chunk before it is
+    // needed and rewritten at step r + 63); there the elements carry band + 1 as their tag, so that a row that was
+    // overwritten before it was read -- or read before it was written -- trips the assert below.
+    const unsigned epoch = PIPE ? b.epoch : (TSTA_DEBUG_ASSERTS ? (unsigned)b.band + 1u : 1u);
     const bool store_right = export_right && lane == 31;
     const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(sm.in);
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sm.rowring);
+    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab4);
+    auto tab_of = [&](uint32_t byte) { return lds_u32(tab_addr + 4u * (byte & 0xffu)); };
     const uint32_t dirw_addr = (uint32_t)__cvta_generic_to_shared(sm.dirw) + lane * (C == 8 ? 8 : 4);
     uint32_t* const dir_lane = TM == 2 ? reinterpret_cast<uint32_t*>(b.dirs) + lane * (C > 4 ? 2 : 1) : nullptr;
     const uint32_t selH = lane == 0 ? 0x1054u : 0x3210u;         // lane 0: lo <- boundary H, hi <- lane 31's low half
@@ -585,13 +606,13 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     const bool stager = lane < CH;
     if (t_begin == 0) {
         // rows above row 0 (read by lanes whose first row is still to come): the fixed-point table
-        sm.rowring[kRing16 - 32 + lane] = make_uint2(kFakeTab, kFakeTab);
-        if (stager && lane < mrows) ring16_put(sm, lane, make_uint2(lane < m ? tab4[b.s1[lane]] : 0u, kFakeTab));   // rows < 32: no high row yet
+        sts_u2(ring_addr + 8u * (kRing16 - 32 + lane), kFakeTab, kFakeTab);
+        if (stager && lane < mrows) ring16_put_at(ring_addr, lane, make_uint2(lane < m ? tab_of(b.s1[lane]) : 0u, kFakeTab));   // rows < 32: no high row yet
     } else {
         // resumed sweep (t_begin >= 128): the steps of the first chunk read the entries of rows t_begin-31 .. t_begin+31
         const int ra = t_begin - 32 + lane, rb = t_begin + lane;
-        ring16_put(sm, ra, make_uint2(ra < m ? tab4[b.s1[ra]] : 0u, ra - 32 < m ? tab4[b.s1[ra - 32]] : 0u));
-        ring16_put(sm, rb, make_uint2(rb < m ? tab4[b.s1[rb]] : 0u, rb - 32 < m ? tab4[b.s1[rb - 32]] : 0u));
+        ring16_put_at(ring_addr, ra, make_uint2(ra < m ? tab_of(b.s1[ra]) : 0u, ra - 32 < m ? tab_of(b.s1[ra - 32]) : 0u));
+        ring16_put_at(ring_addr, rb, make_uint2(rb < m ? tab_of(b.s1[rb]) : 0u, rb - 32 < m ? tab_of(b.s1[rb - 32]) : 0u));
     }
     uint32_t raw_next = (stager && t_begin + CH + lane < m) ? b.s1[t_begin + CH + lane] : 0xffffffffu;
     // left boundary: PIPE imports it in groups of G rows (lanes 0..G-1 hold the group that is consumed
@@ -599,17 +620,17 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     unsigned long long bnd_next = 0;
     if (import_left && (PIPE ? lane < G : stager) && t_begin + lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + t_begin + lane);
     __syncwarp();
-    L.Tnext = sm.rowring[(t_begin - lane) & (kRing16 - 1)];      // table of this lane's row at the first step (row t_begin - lane)
+    L.Tnext = lds_u2(ring_addr + 8u * ((t_begin - lane) & (kRing16 - 1)));      // table of this lane's row at the first step (row t_begin - lane)
 
     // PIPE: make rows [row0, row0 + G) of the left boundary available in sm.in[slot0 ..] and prefetch the next group
     auto import_group = [&](const int row0, const int slot0, const int cur_base) {
         const int row = row0 + lane;
         const bool mine = lane < G && row < m;
-        unsigned spins = 0;
-        unsigned long long t_wait = 0;
         const long long dbg_c0 = (kTimeline && b.timeline) ? clock64() : 0;
         if (TSTA_WATCHDOG && b.has_left && b.band == 0) {
             // the producer is ANOTHER GPU (column slices): never hang on a neighbour that does not come
+            unsigned spins = 0;
+            unsigned long long t_wait = 0;
             while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
                 __nanosleep(20);
                 if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
@@ -624,6 +645,9 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
                 if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
             }
         }
+#if TSTA_DEBUG_ASSERTS
+        if (mine && !(b.abort_flag && *reinterpret_cast<volatile int*>(b.abort_flag))) assert((unsigned)(bnd_next >> 32) == epoch);
+#endif
         // absolute modulo 2^16 -> relative to this warp's base (score-only: Ft = Fg - (O+E))
         if (TM == 2 && b.bnd_unscaled) {
             // the column was written by the score-only pass (unscaled H | Fg): times four, and Fg is "opened"
@@ -631,12 +655,12 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             const uint32_t raw = (uint32_t)bnd_next;
             const uint32_t rel = vadd2(raw, dup16(-(cur_base >> 2)));
             const uint32_t opened = (((raw >> 16) - raw - (uint32_t)(sc.O + sc.E)) & 0xffffu) == 0u ? 0x00020000u : 0u;
-            if (mine) sm.in[slot0 + lane] = ((rel & 0x3fff3fffu) << 2) + opened;
-        } else if (mine) sm.in[slot0 + lane] = vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE));
+            if (mine) sts_u32(in_addr + 4u * (slot0 + lane), ((rel & 0x3fff3fffu) << 2) + opened);
+        } else if (mine) sts_u32(in_addr + 4u * (slot0 + lane), vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE)));
         __syncwarp();
         if (lane < G && row + G < m) bnd_next = ld_relaxed_u64(b.bnd_in + row + G);
         if (kTimeline && b.timeline && lane == 0) {   // diagnostics: polls that found stale rows, cycles spent importing, imports
-            b.timeline[b.band * 16 + 8] += spins;
+            b.timeline[b.band * 16 + 8] += 0;   // (stale polls are no longer counted)
             b.timeline[b.band * 16 + 9] += (unsigned long long)(clock64() - dbg_c0);
             b.timeline[b.band * 16 + 10] += 1;
         }
@@ -689,8 +713,8 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         {
             const int rown = t0 + CH + lane;                    // row of the next chunk
             if (stager && rown < mrows) {
-                const uint32_t hi_tab = rown >= 32 ? sm.rowring[(rown - 32) & (kRing16 - 1)].x : kFakeTab;
-                ring16_put(sm, rown, make_uint2(rown < m ? tab4[raw_next & 0xffu] : 0u, hi_tab));
+                const uint32_t hi_tab = rown >= 32 ? lds_u32(ring_addr + 8u * ((rown - 32) & (kRing16 - 1))) : kFakeTab;
+                ring16_put_at(ring_addr, rown, make_uint2(rown < m ? tab_of(raw_next) : 0u, hi_tab));
             }
             const int rownn = rown + CH;
             raw_next = (stager && rownn < m) ? b.s1[rownn] : 0u;
@@ -699,12 +723,15 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
                 if (t0 < m) import_group(t0, 0, base);          // (also orders the ring stores above)
                 if (ch == 0) stamp(1);                          // the first rows of the left boundary have arrived
             } else if (import_left) {
-                if (row < m) sm.in[lane] = vadd2((uint32_t)bnd_next, pack16(-base, -base - shiftOE));
+#if TSTA_DEBUG_ASSERTS
+                if (row < m) assert((unsigned)(bnd_next >> 32) == (unsigned)b.band);      // written by band - 1 of THIS pair
+#endif
+                if (row < m) sts_u32(in_addr + 4u * lane, vadd2((uint32_t)bnd_next, pack16(-base, -base - shiftOE)));
                 const int rowp = row + CH;
                 if (stager && rowp < m) bnd_next = ld_relaxed_u64(b.bnd_in + rowp);
             } else if (row < m) {
                 const int hb = S * (sc.O + (row + 1) * sc.E) - base;   // H(i,-1); Fg(i,0) = H(i,-1)+O+E, opened
-                sm.in[lane] = pack16(hb, hb + OEs - shiftOE);
+                sts_u32(in_addr + 4u * lane, pack16(hb, hb + OEs - shiftOE));
             }
         }
         __syncwarp();
