@@ -1,19 +1,9 @@
 """POA fill kernel time against rows and bands on chain graphs: slope = cycles per step, intercept = ramp."""
 import sys
-sys.path.insert(0, '/root/repo')
-import numpy as np
+sys.path.insert(0, "/root/repo")
+sys.path.insert(0, "/root/repo/tools")
+from poa_model_lib import chain
 from tsta_b200 import api, synth
-
-def chain(nrows, read, two=0.0):
-    rp, pr = [0], []
-    rng = np.random.default_rng(1)
-    for r in range(nrows):
-        ps = [-1] if r == 0 else [r - 1]
-        if r > 3 and rng.random() < two: ps.append(r - 3)
-        pr += ps; rp.append(len(pr))
-    base = np.frombuffer((read * (nrows // len(read) + 1))[:nrows], dtype=np.uint8)
-    hneg1 = (-6 - 2 * np.arange(nrows)).astype(np.int32)
-    return np.array(rp, np.int32), np.array(pr, np.int32), base, hneg1
 
 poa = api.Poa()
 for ln in (128, 2560, 20000, 50000):

@@ -6,10 +6,12 @@
 // node_fuse() (751-785) a second kernel that returns the compact path.
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
 #include "poa_fill.cuh"
+#include "poa_rows.cuh"
 
 namespace tsta {
 int check_params(const tsta_params* p);
@@ -24,10 +26,12 @@ struct tsta_poa {
     std::vector<uint4> h_desc;
     unsigned epoch = 0;
     int nrows = 0, len = 0, nbands = 0, C = kPoaC;
+    bool rows_kernel = true;       // last fill ran poa_rows_kernel (row-synchronous) rather than poa_fill_kernel (skewed)
     long long stride = 0;
     bool filled = false;
     int launches = 0;
     double t_desc = 0, t_alloc = 0, t_run = 0;   // host seconds per phase (TSTA_POA_TIMING=1 prints them)
+    long long n_fill_rows = 0, n_fill_skew = 0;   // fills by kernel
     long long n_rows = 0, n_wide = 0, n_far = 0, n_keep = 0, n_deg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -64,6 +68,10 @@ int tsta_poa_create(tsta_poa** out)
         e = cudaFuncSetAttribute(poa_fill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaSmemC<4>));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(poa_fill_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaSmemC<2>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(poa_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaRowsSmem<4>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(poa_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaRowsSmem<2>));
     if (e != cudaSuccess) {
         poa_free(p);
         return set_error(TSTA_ECUDA, "POA context creation failed: %s", cudaGetErrorString(e));
@@ -75,8 +83,8 @@ int tsta_poa_create(tsta_poa** out)
 void tsta_poa_destroy(tsta_poa* p)
 {
     if (p && getenv("TSTA_POA_TIMING"))
-        fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s\n",
-                p->t_desc, p->t_alloc, p->t_run);
+        fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s; fills: %lld poa_rows_kernel, %lld poa_fill_kernel\n",
+                p->t_desc, p->t_alloc, p->t_run, p->n_fill_rows, p->n_fill_skew);
     if (p && getenv("TSTA_POA_TIMING"))
         fprintf(stderr, "tsta_poa rows %lld: in-degree>8 %lld, with a far predecessor %lld, spilled %lld; in-degree histogram 1:%lld 2:%lld 3:%lld 4:%lld 5:%lld 6:%lld 7+:%lld\n",
                 p->n_rows, p->n_wide, p->n_far, p->n_keep, p->n_deg[1], p->n_deg[2], p->n_deg[3], p->n_deg[4], p->n_deg[5], p->n_deg[6], p->n_deg[7]);
@@ -108,7 +116,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     p->h_desc.assign((size_t)nrows, make_uint4(0, 0, 0, 0));
     for (int r = 0; r < nrows; r++) {
         const int e0 = row_ptr[r], np = row_ptr[r + 1] - e0;
-        unsigned flags = 0, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone,
+        unsigned flags = 0, jf = kPoaNoFwd, slot[kPoaFast] = {kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone,
                                               kPoaSlotNone, kPoaSlotNone, kPoaSlotNone, kPoaSlotNone};
         static_assert(kPoaFast == 8, "descriptor words y and z hold eight slot bytes");
         if (pred_row[e0] < 0) {
@@ -129,13 +137,14 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
                     far = true;
                 }
                 if (j < kPoaFast) slot[j] = (unsigned)(pr & (kPoaHist - 1));
+                if (j < kPoaFast && pr == r - 1) jf = (unsigned)j;     // poa_rows_kernel takes this one from registers
             }
             if (far) p->n_far++;
         }
         p->n_deg[np < 7 ? np : 7]++;
         p->n_rows++;
         uint4& q = p->h_desc[(size_t)r];
-        q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16);
+        q.x |= (unsigned)base[r] | ((unsigned)np << 8) | (flags << 16) | (jf << 28);
         q.y = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
         q.z = (flags & kPoaSlow) ? (unsigned)e0 : (slot[4] | (slot[5] << 8) | (slot[6] << 16) | (slot[7] << 24));
     }
@@ -144,6 +153,9 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     for (int r = 0; r < nrows; r++) {
         uint4& q = p->h_desc[(size_t)r];
         q.w = ((q.x >> 16) & kPoaKeep) ? (unsigned)nkeep++ : 0u;
+        // poa_rows_kernel: the only predecessor is row r-1 and nothing else is special -> register-only row
+        if (((q.x >> 8) & 0xffu) == 1u && (q.x >> 28) == 0u && !((q.x >> 16) & (kPoaHead | kPoaKeep | kPoaSlow | kPoaLate)))
+            q.x |= kPoaPlainRow << 16;
     }
     p->n_keep += (long long)nkeep;
     // Strip width.  The kernel is a template (2 or 4 columns per lane).  Measured on 16 x 50 kbp: 4 columns (391 bands)
@@ -151,6 +163,11 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     // history round trip, descriptor) does not shrink with the strip, and twice the bands double the start-up.
     p->C = 4;
     if (const char* e = getenv("TSTA_POA_C")) { const int c = atoi(e); if (c == 2 || c == 4) p->C = c; }
+    // Kernel.  poa_rows_kernel (row-synchronous, F by a max-plus scan; poa_rows.cuh) is the default; the skewed
+    // poa_fill_kernel keeps the reads with 'N' columns (quirk Q3 is a second horizontal chain) and strip widths
+    // that do not divide L (the late-head re-base must fall on a lane's first column).  TSTA_POA_KERNEL=skew forces it.
+    p->rows_kernel = (L % p->C == 0) && memchr(read, 'N', (size_t)len) == nullptr;
+    if (const char* e = getenv("TSTA_POA_KERNEL")) { if (!strcmp(e, "skew")) p->rows_kernel = false; }
     const int band_cols = 32 * p->C;
     p->nbands = (len + band_cols - 1) / band_cols;
     p->stride = (long long)p->nbands * band_cols;
@@ -216,7 +233,11 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
     TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     {
         NvtxRange range("tsta_poa fill");
-        if (p->C == 2) poa_fill_kernel<2><<<p->nbands, 32, sizeof(PoaSmemC<2>), p->stream>>>(a);
+        (p->rows_kernel ? p->n_fill_rows : p->n_fill_skew)++;
+        if (p->rows_kernel) {
+            if (p->C == 2) poa_rows_kernel<2><<<p->nbands, 32, sizeof(PoaRowsSmem<2>), p->stream>>>(a);
+            else poa_rows_kernel<4><<<p->nbands, 32, sizeof(PoaRowsSmem<4>), p->stream>>>(a);
+        } else if (p->C == 2) poa_fill_kernel<2><<<p->nbands, 32, sizeof(PoaSmemC<2>), p->stream>>>(a);
         else poa_fill_kernel<4><<<p->nbands, 32, sizeof(PoaSmemC<4>), p->stream>>>(a);
     }
     TSTA_CUDA_TRY(cudaGetLastError());
