@@ -33,6 +33,7 @@
 namespace tsta {
 
 constexpr int kPoaGroup = 8;                 // rows per boundary import group
+constexpr int kPoaRowsDescRing = 128;
 constexpr int kPoaPlane = 33 * 16;           // one 16-byte unit per lane (+ the band's left edge in unit 0)
 template <int C> constexpr int kPoaRowsSlotBytes = (C / 2) * kPoaPlane;
 
@@ -44,13 +45,21 @@ template <int C>
 struct PoaRowsSmem {
     unsigned char hist[kPoaSlots * kPoaRowsSlotBytes<C>];
     int2 bring[kPoaBndRing];                 // left boundary keys (H(r, j0-1)*256, Fg(r, j0)*256 + 64) by row
-    uint4 desc[kPoaDescRing];                // row descriptors
-    int kconst[16];
+    uint4 desc[kPoaRowsDescRing];            // row descriptors, copied in by cp.async two 32-row chunks ahead
+    int kconst[20];
 };
 
 constexpr unsigned kPoaNoFwd = 15u;          // descriptor bits 28..31: index of the predecessor that is row r-1 (15: none)
 constexpr unsigned kPoaPlainRow = 16u;       // flag: the row's ONLY predecessor is row r-1, no spill, not a head: inputs come from registers
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
 __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool doit)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((unsigned)doit) : "memory");
@@ -104,14 +113,18 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
         k[0] = 256 * a.M; k[1] = 256 * a.X; k[2] = 256 * E; k[3] = 256 * OE + 64; k[4] = 256 * E + 64; k[5] = 256 * E + 128;
         k[6] = 256 * a.M + 255; k[7] = 256 * a.X + 255; k[8] = 512 * E; k[9] = 768 * E;
         k[10] = ESC0; k[11] = 2 * ESC0; k[12] = 4 * ESC0; k[13] = 8 * ESC0; k[14] = 16 * ESC0;
+        k[18] = 3 * ESC0; k[19] = 12 * ESC0;
         k[15] = (int)(uint32_t)__cvta_generic_to_shared(&sm.hist[0]);
+        const long long sb = a.stride * 2;                        // bytes between two trace rows
+        k[16] = (int)(unsigned)(sb & 0xffffffffll); k[17] = (int)(sb >> 32);
     }
     __syncwarp();
     const volatile int* kc = sm.kconst;
     const int MS = kc[0], XS = kc[1], ES = kc[2], OES = kc[3], ES64 = kc[4], ES128 = kc[5];
     const int MS255 = kc[6], XS255 = kc[7], ES2 = kc[8], ES3 = kc[9];
-    const int D1 = kc[10], D2 = kc[11], D4 = kc[12], D8 = kc[13], D16 = kc[14];
+    const int D1 = kc[10], D2 = kc[11], D4 = kc[12], D8 = kc[13], D16 = kc[14], D3 = kc[18], D12 = kc[19];
     const uint32_t base = (uint32_t)kc[15];
+    const long long stride_bytes = (long long)(((unsigned long long)(unsigned)kc[17] << 32) | (unsigned)kc[16]);
     constexpr uint32_t kDescOff = (uint32_t)offsetof(PoaRowsSmem<C>, desc);
     constexpr uint32_t kBringOff = (uint32_t)offsetof(PoaRowsSmem<C>, bring);
     const uint32_t lane16 = (uint32_t)lane * 16u;
@@ -146,16 +159,16 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
         }
     }
 
-    // ---- prologue: descriptors of rows [0, 32) staged, [32, 64) in flight; first boundary group in flight ----
-    if (lane < R) sm.desc[lane] = __ldg(a.desc + lane);
-    uint4 pre_d = make_uint4(0, 0, 0, 0);
-    if (lane + 32 < R) pre_d = __ldg(a.desc + lane + 32);
+    // ---- prologue: descriptors of rows [0, 64) copied in; first boundary group in flight ----
+    if (lane < R) cp_async16(base + kDescOff + lane * 16, a.desc + lane);
+    if (lane + 32 < R) cp_async16(base + kDescOff + (lane + 32) * 16, a.desc + lane + 32);
     unsigned long long pre_b = 0;
     int pre_h = 0;
     if (lane < kPoaGroup && lane < R) {
         if (band > 0) pre_b = ld_relaxed_u64(bnd_in + lane);
         else pre_h = __ldg(a.hneg1 + lane);
     }
+    cp_async_wait_all();
     __syncwarp();
 
     int ko[2 * C];                       // keys of the row just finished (forwarded to the next row)
@@ -163,7 +176,8 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
     for (int q = 0; q < 2 * C; q++) ko[q] = kPoaKeyMin;
     int fwdH = kPoaKeyMin;               // H(r-1, j0-1): the previous lane's last H of the row just finished
     uint4 dsc_next = lds_u4(base + kDescOff);
-    uint16_t* trow = a.trace + j0;       // this lane's cells of row r
+    char* trow = reinterpret_cast<char*>(a.trace + j0);   // this lane's cells of row r
+    uint32_t desc_off = 16, bring_off = 0;   // ring offsets of row r+1's descriptor / row r's boundary element
     int* lastp = a.lastsorce;
 
     // The row proper, from the reduced predecessor keys: hk = best diagonal key + substitution score, ke = best
@@ -172,6 +186,12 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                           const unsigned flags, const unsigned spill_row) {
         uint32_t tw[C / 2];
         int Fout;                                               // Fg key entering the next lane's first column
+        // this row's output addresses; the running pointers move on NOW, a row away from the stores that use them
+        // (an increment right behind its store waits ~16 cycles for the store to release the address registers)
+        char* const tcur = trow;
+        unsigned long long* const bcur = bout;
+        trow += stride_bytes;
+        bout++;
         if ((flags & kPoaLate) && band_has_L) {
             // ---- serial row (late head in the band that re-bases F): the carry moves one lane per pass.
             //      poa_row adds the substitution score itself: hand it hk minus that score ----
@@ -197,13 +217,21 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
 #pragma unroll
             for (int c = 1; c < C; c++) P[c] = c == 1 ? T[0] : __viaddmax_s32(P[c - 1], ES, T[c - 1]);
             const int G = __viaddmax_s32(P[C - 1], ES, T[C - 1]);
-            // ---- exclusive max-plus scan over the lanes (E <= 0: a lane that shuffles its own value back keeps it) ----
-            const int g1 = __shfl_up_sync(kFullMask, G, 1);
-            int S = lane == 0 ? kPoaKeyMin : g1;
-            S = __viaddmax_s32(__shfl_up_sync(kFullMask, S, 1), D1, S);
-            S = __viaddmax_s32(__shfl_up_sync(kFullMask, S, 2), D2, S);
-            S = __viaddmax_s32(__shfl_up_sync(kFullMask, S, 4), D4, S);
-            S = __viaddmax_s32(__shfl_up_sync(kFullMask, S, 8), D8, S);
+            // ---- exclusive max-plus scan over the lanes, radix 4: three dependent shuffle stages (1..4, then 4/8/12,
+            //      then 16).  Stage 1 forms the EXCLUSIVE prefix over four lanes, so lanes 0..3 must not take the value
+            //      shfl_up hands back to them; in the later stages a lane that gets its own value back keeps it (E <= 0) ----
+            const int g1 = __shfl_up_sync(kFullMask, G, 1), g2 = __shfl_up_sync(kFullMask, G, 2);
+            const int g3 = __shfl_up_sync(kFullMask, G, 3), g4 = __shfl_up_sync(kFullMask, G, 4);
+            int S = lane >= 1 ? g1 : kPoaKeyMin;                  // (selects, not branches: the lanes diverge here)
+            S = __viaddmax_s32(lane >= 2 ? g2 : kPoaKeyMin, D1, S);
+            S = __viaddmax_s32(lane >= 3 ? g3 : kPoaKeyMin, D2, S);
+            S = __viaddmax_s32(lane >= 4 ? g4 : kPoaKeyMin, D3, S);
+            {
+                const int s4 = __shfl_up_sync(kFullMask, S, 4), s8 = __shfl_up_sync(kFullMask, S, 8), s12 = __shfl_up_sync(kFullMask, S, 12);
+                S = __viaddmax_s32(s4, D4, S);
+                S = __viaddmax_s32(s8, D8, S);
+                S = __viaddmax_s32(s12, D12, S);
+            }
             S = __viaddmax_s32(__shfl_up_sync(kFullMask, S, 16), D16, S);
             const int Cin = __viaddmax_s32(Fin, cin_dec, S);      // lane 0: S = -inf, cin_dec = 0
             // ---- pass 2: every column from its exact F ----
@@ -238,9 +266,8 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
             *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
             if constexpr (C == 4) *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
         }
-        if constexpr (C == 4) __stcs(reinterpret_cast<uint2*>(trow), make_uint2(tw[0], tw[1]));
-        else __stcs(reinterpret_cast<uint32_t*>(trow), tw[0]);
-        trow += a.stride;
+        if constexpr (C == 4) __stcs(reinterpret_cast<uint2*>(tcur), make_uint2(tw[0], tw[1]));
+        else __stcs(reinterpret_cast<uint32_t*>(tcur), tw[0]);
         if constexpr (LAST) {
             if (owns_last) {
                 int hl = ko[0];
@@ -249,18 +276,17 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                 lastp[r] = hl >> 8;
             }
         }
-        st_relaxed_u64_if(bout, poa_bnd_pack(ko[2 * (C - 1)], Fout, ep16), store_right);
-        bout++;
+        st_relaxed_u64_if(bcur, poa_bnd_pack(ko[2 * (C - 1)], Fout, ep16), store_right);
         const int upH = __shfl_up_sync(kFullMask, ko[2 * (C - 1)], 1);
         fwdH = lane == 0 ? Hedge : upH;
         __syncwarp();                                           // this row's history stores before the next row's loads
     };
 
     for (int r0 = 0; r0 < R; r0 += 32) {
-        {   // stage the descriptors of rows [r0+32, r0+64), fetch those of [r0+64, r0+96)
-            const int rown = r0 + 32 + lane;
-            if (rown < R) sm.desc[rown & (kPoaDescRing - 1)] = pre_d;
-            if (rown + 32 < R) pre_d = __ldg(a.desc + rown + 32);
+        {   // the descriptors of rows [r0+32, r0+64) have arrived (copy issued one chunk ago); start [r0+64, r0+96)
+            cp_async_wait_all();
+            const int rown = r0 + 64 + lane;
+            if (rown < R) cp_async16(base + kDescOff + ((uint32_t)rown & (kPoaRowsDescRing - 1)) * 16, a.desc + rown);
         }
 #pragma unroll 1
         for (int t0 = r0; t0 < min(R, r0 + 32); t0 += kPoaGroup) {
@@ -287,8 +313,10 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
 #pragma unroll 1
             for (int r = t0; r < rend; r++) {
                 const uint4 dsc = dsc_next;
-                dsc_next = lds_u4(base + kDescOff + ((uint32_t)(r + 1) & (kPoaDescRing - 1)) * 16);
-                const uint2 bv = lds_u2(base + kBringOff + ((uint32_t)r & (kPoaBndRing - 1)) * 8);   // one address: a broadcast
+                dsc_next = lds_u4(base + kDescOff + desc_off);
+                const uint2 bv = lds_u2(base + kBringOff + bring_off);   // one address: a broadcast
+                desc_off = (desc_off + 16) & (kPoaRowsDescRing * 16 - 1);
+                bring_off = (bring_off + 8) & (kPoaBndRing * 8 - 1);
                 const int Hedge = (int)bv.x, Fin = (int)bv.y;
                 const int b = (int)(dsc.x & 0xffu);
                 const unsigned flags = (dsc.x >> 16) & 0xffu;
