@@ -586,47 +586,74 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
         int w0 = ((c0 + 8) & ~7) - kPoaWinCols;
         if (w0 < 0) w0 = 0;
         const int rlo = max(0, r0 - kPoaWinRows + 1);
+        // the window's cells by cp.async (no round trip through registers: all 8 copies of a thread are in flight at once,
+        // next to the graph slice below)
+        const uint32_t win_addr = (uint32_t)__cvta_generic_to_shared(&win[0][0]);
         for (int u = threadIdx.x; u < kPoaWinRows * (kPoaWinCols / 8); u += kPoaWalkThreads) {
             const int rr = u / (kPoaWinCols / 8), q = u % (kPoaWinCols / 8);
             const int row = r0 - rr;
             const long long col = (long long)w0 + q * 8;
             if (row >= 0 && col < a.stride)
-                *reinterpret_cast<uint4*>(&win[rr][q * 8]) =
-                    __ldcs(reinterpret_cast<const uint4*>(a.trace + (long long)row * a.stride + col));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(win_addr + (uint32_t)u * 16u),
+                             "l"(a.trace + (long long)row * a.stride + col) : "memory");
         }
+        const int ebase = __ldg(a.row_ptr + rlo);
+        const int ecount = min(__ldg(a.row_ptr + r0 + 1) - ebase, kPoaWinEdges);
         for (int u = threadIdx.x; u <= r0 - rlo + 1; u += kPoaWalkThreads) s_ptr[u] = a.row_ptr[rlo + u];
         for (int u = threadIdx.x; u < kPoaWinRows; u += kPoaWalkThreads) s_base[u] = r0 - u >= 0 ? a.base[r0 - u] : 0;
         for (int u = threadIdx.x; u < kPoaWinCols; u += kPoaWalkThreads) s_read[u] = w0 + u < a.len ? a.read[w0 + u] : 0;
-        __syncthreads();
-        const int ebase = s_ptr[0];
-        const int ecount = min(s_ptr[r0 - rlo + 1] - ebase, kPoaWinEdges);
         for (int u = threadIdx.x; u < ecount; u += kPoaWalkThreads) s_pred[u] = a.pred_row[ebase + u];
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
             // pend: how this cell was entered (1 = horizontal move, 2 = vertical move, 0 = otherwise);
             // the cell's own bits 14 / 15 then say whether the move is forced to continue.
-            // Written with selects only: one iteration is a chain of two shared-memory loads.
+            // One warp walks: lane k ASSUMES that the k cells before it were diagonal moves into the row right above
+            // (the usual case along a read that mostly matches the graph) and decodes cell (r-k, c-k); the lanes up to
+            // the first cell that says otherwise are on the path, and the walk resumes from that cell's real successor.
+            // 10-30 steps per pass instead of one, for the same chain of two dependent shared-memory loads.
+            const int lane = threadIdx.x;
             int r = r0, c = c0, pend = s_pend, n = s_n;
             while (r >= rlo && c >= w0) {
-                const uint32_t w = win[r0 - r][c - w0];
-                const int e0 = s_ptr[r - rlo] - ebase;
-                const bool match = s_read[c - w0] == s_base[r0 - r];
-                const bool fF = pend == 1 && c > 0 && (w & 0x8000u);
-                const bool fE = pend == 2 && r > 0 && !(w & 0x4000u);
-                const uint32_t type = fF ? 1u : (fE ? 2u : ((w >> 6) & 3u));        // 3 diagonal, 2 vertical, 1 horizontal
-                const int pj = 63 - (int)((fE ? (w >> 8) : w) & 63u);
-                const int kind = type == 3u ? (match ? 1 : 2) : (type == 2u ? 0 : 3);
-                PoaStep st;
-                st.row = r; st.col = c; st.kind = (uint8_t)kind; st.pred = (uint8_t)(type == 1u ? 0 : pj); st.pad = 0;
-                a.path[n++] = st;
-                const int e = e0 + pj;
-                int p = s_pred[min(e, kPoaWinEdges - 1)];
-                if (type != 1u && e >= kPoaWinEdges) p = a.pred_row[ebase + e];   // (a window with > 2048 edges: never seen)
-                r = type == 1u ? r : p;
-                c = type == 2u ? c : c - 1;
-                pend = type == 1u ? 1 : (type == 2u ? 2 : 0);
+                const int rr = r - lane, cc = c - lane;
+                const bool in = rr >= rlo && cc >= w0;
+                uint32_t type = 0;
+                int pj = 0, p = 0, kind = 0;
+                if (in) {
+                    const uint32_t w = win[r0 - rr][cc - w0];
+                    const int e0 = s_ptr[rr - rlo] - ebase;
+                    const bool match = s_read[cc - w0] == s_base[r0 - rr];
+                    const int pd = lane == 0 ? pend : 0;                  // lanes > 0 are entered by a diagonal move
+                    const bool fF = pd == 1 && cc > 0 && (w & 0x8000u);
+                    const bool fE = pd == 2 && rr > 0 && !(w & 0x4000u);
+                    type = fF ? 1u : (fE ? 2u : ((w >> 6) & 3u));        // 3 diagonal, 2 vertical, 1 horizontal
+                    pj = 63 - (int)((fE ? (w >> 8) : w) & 63u);
+                    kind = type == 3u ? (match ? 1 : 2) : (type == 2u ? 0 : 3);
+                    const int e = e0 + pj;
+                    p = s_pred[min(e, kPoaWinEdges - 1)];
+                    if (type != 1u && e >= kPoaWinEdges) p = a.pred_row[ebase + e];   // (a window with > 2048 edges: never seen)
+                }
+                const bool cont = in && type == 3u && p == rr - 1;        // the next cell IS the one lane + 1 looks at
+                const unsigned okmask = __ballot_sync(kFullMask, cont);
+                const int d = okmask == 0xffffffffu ? 32 : __ffs((int)~okmask) - 1;   // first lane whose successor is elsewhere
+                if (lane <= d && in) {
+                    PoaStep st;
+                    st.row = rr; st.col = cc; st.kind = (uint8_t)kind; st.pred = (uint8_t)(type == 1u ? 0 : pj); st.pad = 0;
+                    a.path[n + lane] = st;
+                }
+                if (d == 32) {
+                    r -= 32; c -= 32; pend = 0; n += 32;
+                } else {
+                    const int src = d;
+                    const int d_in = __shfl_sync(kFullMask, (int)in, src);
+                    const int nr = __shfl_sync(kFullMask, type == 1u ? rr : p, src);
+                    const int nc = __shfl_sync(kFullMask, type == 2u ? cc : cc - 1, src);
+                    const int np = __shfl_sync(kFullMask, type == 1u ? 1 : (type == 2u ? 2 : 0), src);
+                    if (d_in) { r = nr; c = nc; pend = np; n += d + 1; }
+                    else { r -= d; c -= d; pend = d == 0 ? pend : 0; n += d; }   // left the window: reload around (r, c)
+                }
             }
-            s_row = r; s_col = c; s_pend = pend; s_n = n;
+            if (lane == 0) { s_row = r; s_col = c; s_pend = pend; s_n = n; }
         }
         __syncthreads();
     }

@@ -137,6 +137,7 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
                     far = true;
                 }
                 if (j < kPoaFast) slot[j] = (unsigned)(pr & (kPoaHist - 1));
+                if (pr == r - 1 && jf != kPoaNoFwd) flags |= kPoaSlow;   // (a duplicated edge: generic loop reads the ring)
                 if (j < kPoaFast && pr == r - 1) jf = (unsigned)j;     // poa_rows_kernel takes this one from registers
             }
             if (far) p->n_far++;
