@@ -804,11 +804,11 @@ def wl_msa(ctx, name, steps):
     # 2 per edge-cell + 5 per node-cell; int32 kernel -> held against the measured VIADDMNMX rate
     ec, nc, fm = MSA_LAST.get("edge_cells"), MSA_LAST.get("node_cells"), MSA_LAST.get("fill_ms")
     ach = (2.0 * ec + 5.0 * nc) / (fm * 1e-3) / 1e12 if ec and nc and fm else None
-    roof = {"bound": "int_alu", "bound_note": "int32 ALU issue; the kernel is latency bound (one warp per SM sub-partition, DESIGN.md 6)",
+    roof = {"bound": "int_alu", "bound_note": "int32 ALU issue; the kernel is bound by one warp's issue rate and the per-row scan latency (one warp per band, DESIGN.md 6)",
             "achieved": ach, "peak": ctx.dpx_peak / 1e12, "unit": "Tlaneop/s", "frac": (ach / (ctx.dpx_peak / 1e12)) if ach else None,
             "peak_source": "measured live: dependency-free VIADDMNMX loop (tsta_measure_dpx_peak)",
             "algorithmic_ops": "2 per edge-cell + 5 per node-cell (SURVEY.md 8d)", "edge_cells": ec, "node_cells": nc,
-            "kernel": "poa_fill_kernel", "kernel_ms": fm, "fill_gcups": cells_rank / (fm * 1e-3) / 1e9 if fm else None, "traffic": None}
+            "kernel": "poa_rows_kernel", "kernel_ms": fm, "fill_gcups": cells_rank / (fm * 1e-3) / 1e9 if fm else None, "traffic": None}
     # parity: OUR driver on the sample the reference arm is timed on (same generator, 10 kbp reads), -o md5 against
     # the reference's (the full 16 x 50 kbp comparison is tests/test_full_size_gpu.py)
     parity = None

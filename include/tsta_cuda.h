@@ -196,6 +196,26 @@ void tsta_poa_destroy(tsta_poa* ctx);
 int  tsta_poa_fill(tsta_poa* ctx, const tsta_params* p, int L, int nrows,
                    const int32_t* row_ptr, const int32_t* pred_row, const uint8_t* base, const int32_t* hneg1,
                    const char* read, int len, int32_t* lastsorce, float* kernel_ms);
+/* Device-resident graph (the reference re-sorts and re-reads the whole graph for every read:
+ * msa/msa.c:132-133, msa/topo.c:243-260; here the graph stays in HBM between reads).  Nodes are
+ * identified by stable ids 0..nnodes-1.  After a read has been fused the caller sends only the
+ * records of the nodes whose base / predecessor list changed (or that are new): base_in = base |
+ * in-degree << 8 (in-degree 0: a head), pre[] = predecessor NODE ids in pre[] order.  Nodes with at
+ * most two predecessors travel as 16-byte records, up to eight as 40-byte records; a node with more
+ * than eight predecessors cannot be resident (use tsta_poa_fill for that job). */
+typedef struct tsta_poa_node2 { int32_t id; uint32_t base_in; int32_t pre[2]; } tsta_poa_node2;
+typedef struct tsta_poa_node8 { int32_t id; uint32_t base_in; int32_t pre[8]; } tsta_poa_node8;
+int  tsta_poa_graph_update(tsta_poa* ctx, int nnodes, int n_narrow, const tsta_poa_node2* narrow,
+                           int n_wide, const tsta_poa_node8* wide);
+/* tsta_poa_fill on the resident graph: sort[r] = id of the node in row r of the current topological
+ * order (4 bytes per row is all that crosses PCIe besides the read).  Row descriptors, the
+ * predecessor table in row indices and the spill slots are built on the device; H(r,-1) is computed
+ * by the fill itself, so hneg1 may be NULL unless the read runs on the skewed kernel (it contains
+ * 'N', or L is not a multiple of the strip width), in which case it is required. */
+int  tsta_poa_fill_resident(tsta_poa* ctx, const tsta_params* p, int L, int nrows, const int32_t* sort,
+                            const int32_t* hneg1, const char* read, int len, int32_t* lastsorce, float* kernel_ms);
+/* Bytes of graph tables and reads this context has copied to the device so far (TSTA_MSA_TIMING). */
+long long tsta_poa_h2d_bytes(const tsta_poa* ctx);
 /* Walk the traceback of the last fill from (start_row, len-1) with the reference's forced
  * continuation rules (c-t-simd.c:767-769, 776-782); path must hold nrows+len steps. */
 int  tsta_poa_walk(tsta_poa* ctx, int start_row, tsta_poa_step* path, int* nsteps, float* kernel_ms);

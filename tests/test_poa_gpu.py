@@ -148,6 +148,33 @@ def test_quirk_rows_n_columns_and_late_heads(gpu, seed):
     poa.close()
 
 
+@pytest.mark.parametrize("kernel,C", [("rows", 4), ("rows", 2), ("skew", 4), ("skew", 2)])
+def test_both_fill_kernels_late_heads_dense_graphs(gpu, monkeypatch, kernel, C):
+    """The row-synchronous kernel (poa_rows.cuh: F by scan, register forwarding, serial pass for late heads in
+    the band that owns column L) and the skewed kernel (poa_fill.cuh), each strip width, on reads WITHOUT 'N'
+    -- the inputs both kernels accept -- with many heads, small L, wide and far predecessors."""
+    monkeypatch.setenv("TSTA_POA_KERNEL", kernel)
+    monkeypatch.setenv("TSTA_POA_C", str(C))
+    rnd = random.Random(4242 + C)
+    poa = gpu.Poa()
+    for k in range(6):
+        M, X, E, O = rnd.choice([(2, -5, -2, -4), (1, -1, -1, 0), (2, -5, -2, 0), (1, -3, -1, -5), (5, -4, 0, -3)])
+        nrows, ln, L = rnd.choice([90, 400, 1100]), rnd.choice([5, 131, 260, 900]), rnd.choice([64, 128, 640])
+        read = synth.random_read(ln, 900 + 13 * k + C)
+        g = random_dag(nrows, rnd, E, O, far=rnd.choice([0.0, 0.2]), heads=rnd.choice([0.0, 0.06]),
+                       maxin=rnd.choice([3, 6, 11]), backbone=read)
+        src, es, fs, last = ob.poa_fill(*g, read, M, X, E, O, L)
+        glast, _ = poa.fill(*g, read, M, X, E, O, L)
+        np.testing.assert_array_equal(glast, last)
+        assert_trace(poa, src, es, fs, g)
+        want = ob.poa_walk(g[0], g[1], src, es, fs, nrows - 1)
+        got, _ = poa.walk(nrows - 1)
+        assert len(got) == len(want)
+        for fld in ("row", "col", "kind", "pred"):
+            np.testing.assert_array_equal(got[fld], want[fld])
+    poa.close()
+
+
 def run_msa(reads, prm, W, tmp_path):
     fa, fo = tmp_path / "r.fa", tmp_path / "o.txt"
     ob.write_fasta(fa, reads)

@@ -75,7 +75,8 @@ struct PoaFillArgs {
     const int* row_ptr;       // [nrows+1]
     const int* pred_row;      // [nedges], -1 = virtual predecessor of a head
     const uint8_t* base;      // [nrows]
-    const int* hneg1;         // [nrows] H(r,-1)
+    const int* hneg1;         // [nrows] H(r,-1); NULL: poa_rows_kernel computes it in band 0 (device-resident graphs)
+    int* edge_spill;          // [nkeep] H(r,-1) keys of the spilled rows (written and read by band 0 when hneg1 is NULL)
     const uint8_t* read;      // [len]
     int len, nrows, nbands, L;
     int M, X, E, O;
@@ -563,9 +564,10 @@ struct PoaWalkArgs {
     long long stride;
     const int* row_ptr;
     const int* pred_row;
-    const uint8_t* base;      // [nrows]  a diagonal move is a match iff read[col] == base[row]
+    const uint4* desc;        // [nrows]  row descriptors: a diagonal move is a match iff read[col] == base of the row (x & 255)
     const uint8_t* read;      // [len]
     int len, nrows, start_row;
+    int fixed8;               // the predecessor table is at stride 8 (device-built graphs): row_ptr[r] = 8 r
     PoaStep* path;
     int* nsteps;
 };
@@ -597,10 +599,10 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(win_addr + (uint32_t)u * 16u),
                              "l"(a.trace + (long long)row * a.stride + col) : "memory");
         }
-        const int ebase = __ldg(a.row_ptr + rlo);
-        const int ecount = min(__ldg(a.row_ptr + r0 + 1) - ebase, kPoaWinEdges);
-        for (int u = threadIdx.x; u <= r0 - rlo + 1; u += kPoaWalkThreads) s_ptr[u] = a.row_ptr[rlo + u];
-        for (int u = threadIdx.x; u < kPoaWinRows; u += kPoaWalkThreads) s_base[u] = r0 - u >= 0 ? a.base[r0 - u] : 0;
+        const int ebase = a.fixed8 ? 8 * rlo : __ldg(a.row_ptr + rlo);
+        const int ecount = min((a.fixed8 ? 8 * (r0 + 1) : __ldg(a.row_ptr + r0 + 1)) - ebase, kPoaWinEdges);
+        for (int u = threadIdx.x; u <= r0 - rlo + 1; u += kPoaWalkThreads) s_ptr[u] = a.fixed8 ? 8 * (rlo + u) : a.row_ptr[rlo + u];
+        for (int u = threadIdx.x; u < kPoaWinRows; u += kPoaWalkThreads) s_base[u] = r0 - u >= 0 ? (uint8_t)(__ldg(&a.desc[r0 - u].x) & 0xffu) : 0;
         for (int u = threadIdx.x; u < kPoaWinCols; u += kPoaWalkThreads) s_read[u] = w0 + u < a.len ? a.read[w0 + u] : 0;
         for (int u = threadIdx.x; u < ecount; u += kPoaWalkThreads) s_pred[u] = a.pred_row[ebase + u];
         asm volatile("cp.async.wait_all;" ::: "memory");

@@ -79,7 +79,10 @@ __device__ __forceinline__ void poa_rows_lds(uint32_t slot_addr, uint32_t lane16
 }
 
 // One band (32*C columns, one warp) over all rows.  LAST: the band that holds column len-1 also writes lastsorce.
-template <int C, bool LAST>
+// EDGE0: band 0 when the caller did not supply hneg1 (device-resident graphs, tsta_poa_fill_resident): the left edge
+// H(r,-1) = max_j H(p_j,-1) + E (c-t-simd.c:196-200; O+E for a head, 187) is the DP's "column -1" and is carried like
+// any other column -- every lane computes it from the edge words the history already holds.
+template <int C, bool LAST, bool EDGE0>
 __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem<C>& sm, const int band, const int lane)
 {
     constexpr int kSlotB = kPoaRowsSlotBytes<C>;
@@ -166,7 +169,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
     int pre_h = 0;
     if (lane < kPoaGroup && lane < R) {
         if (band > 0) pre_b = ld_relaxed_u64(bnd_in + lane);
-        else pre_h = __ldg(a.hneg1 + lane);
+        else if constexpr (!EDGE0) pre_h = __ldg(a.hneg1 + lane);
     }
     cp_async_wait_all();
     __syncwarp();
@@ -175,6 +178,9 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
 #pragma unroll
     for (int q = 0; q < 2 * C; q++) ko[q] = kPoaKeyMin;
     int fwdH = kPoaKeyMin;               // H(r-1, j0-1): the previous lane's last H of the row just finished
+    int edge_prev = kPoaKeyMin;          // EDGE0: H(r-1, -1) as a key
+    constexpr uint32_t kEdgeOff = (C / 2 - 1) * kPoaPlane + 8;   // the left-edge word of a history slot
+    const int OEk = OES - 64;            // (O+E)*256
     uint4 dsc_next = lds_u4(base + kDescOff);
     char* trow = reinterpret_cast<char*>(a.trace + j0);   // this lane's cells of row r
     uint32_t desc_off = 16, bring_off = 0;   // ring offsets of row r+1's descriptor / row r's boundary element
@@ -262,6 +268,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
         if constexpr (C == 4) sts_s4(own + kPoaPlane, ko[4], ko[5], ko[6], ko[7]);
         sts_u32_if(own + (C / 2 - 1) * kPoaPlane - 8, (uint32_t)Hedge, lane == 0);     // lane 0: the band's left edge (unit 0)
         if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
+            if constexpr (EDGE0) a.edge_spill[spill_row] = Hedge;         // (every lane, the same value)
             int2* g = a.HE + (long long)spill_row * a.stride + j0;
             *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
             if constexpr (C == 4) *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
@@ -279,6 +286,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
         st_relaxed_u64_if(bcur, poa_bnd_pack(ko[2 * (C - 1)], Fout, ep16), store_right);
         const int upH = __shfl_up_sync(kFullMask, ko[2 * (C - 1)], 1);
         fwdH = lane == 0 ? Hedge : upH;
+        if constexpr (EDGE0) edge_prev = Hedge;
         __syncwarp();                                           // this row's history stores before the next row's loads
     };
 
@@ -303,7 +311,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                         sm.bring[row & (kPoaBndRing - 1)] = make_int2(Hk, Hk + (int)(short)(hi & 0xffffu) * 256 + 64);
                     }
                     if (row + kPoaGroup < R) pre_b = ld_relaxed_u64(bnd_in + row + kPoaGroup);
-                } else {
+                } else if constexpr (!EDGE0) {
                     if (row < R) sm.bring[row & (kPoaBndRing - 1)] = make_int2(pre_h * 256, (pre_h + OE) * 256 + 64);   // Fg(r,0) = H(r,-1)+O+E
                     if (row + kPoaGroup < R) pre_h = __ldg(a.hneg1 + row + kPoaGroup);
                 }
@@ -317,11 +325,12 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                 const uint2 bv = lds_u2(base + kBringOff + bring_off);   // one address: a broadcast
                 desc_off = (desc_off + 16) & (kPoaRowsDescRing * 16 - 1);
                 bring_off = (bring_off + 8) & (kPoaBndRing * 8 - 1);
-                const int Hedge = (int)bv.x, Fin = (int)bv.y;
+                int Hedge = (int)bv.x, Fin = (int)bv.y;
                 const int b = (int)(dsc.x & 0xffu);
                 const unsigned flags = (dsc.x >> 16) & 0xffu;
                 int hk[C], ke[C];
                 if (flags & kPoaPlainRow) {
+                    if constexpr (EDGE0) { Hedge = edge_prev + ES; Fin = Hedge + OES; }
                     // ---- the only predecessor is the row just finished: registers, weights folded into the score ----
 #pragma unroll
                     for (int c = 0; c < C; c++) {
@@ -335,15 +344,19 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                 const int np = (int)((dsc.x >> 8) & 0xffu);
                 const int jf = (int)(dsc.x >> 28);
                 int kd[C];
+                int emax = kPoaKeyMin;                                  // EDGE0: max_j H(p_j, -1)
                 if (!(flags & kPoaSlow)) {
                     {
                         int Hd0, ph[C], pe[C];
                         if (jf == 0) {
                             Hd0 = fwdH;
+                            if constexpr (EDGE0) emax = edge_prev;
 #pragma unroll
                             for (int c = 0; c < C; c++) { ph[c] = ko[2 * c]; pe[c] = ko[2 * c + 1]; }
-                        } else
+                        } else {
                             poa_rows_lds<C>(base + (dsc.y & 0xffu) * kSlotB, lane16, Hd0, ph, pe);
+                            if constexpr (EDGE0) emax = lds_s32(base + (dsc.y & 0xffu) * kSlotB + kEdgeOff);
+                        }
                         kd[0] = Hd0 + 255;
 #pragma unroll
                         for (int c = 1; c < C; c++) kd[c] = ph[c - 1] + 255;
@@ -355,11 +368,13 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                         int Hd0, ph[C], pe[C];
                         if (j == jf) {
                             Hd0 = fwdH;
+                            if constexpr (EDGE0) emax = max(emax, edge_prev);
 #pragma unroll
                             for (int c = 0; c < C; c++) { ph[c] = ko[2 * c]; pe[c] = ko[2 * c + 1]; }
                         } else {
                             const uint32_t slot = ((j < 4 ? dsc.y : dsc.z) >> (8 * (j & 3))) & 0xffu;
                             poa_rows_lds<C>(base + slot * kSlotB, lane16, Hd0, ph, pe);
+                            if constexpr (EDGE0) emax = max(emax, lds_s32(base + slot * kSlotB + kEdgeOff));
                         }
                         const int wd = 192 + 63 - j, we = 64 + 63 - j;
                         kd[0] = __viaddmax_s32(Hd0, wd, kd[0]);
@@ -379,7 +394,9 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                         if (p < 0 || r - p <= kPoaNear) {
                             const int slot = p < 0 ? ((flags & kPoaLate) ? kPoaSlotLate : kPoaSlotHead) : (p & (kPoaHist - 1));
                             poa_rows_lds<C>(base + slot * kSlotB, lane16, Hd0, ph, pe);
+                            if constexpr (EDGE0) emax = max(emax, lds_s32(base + slot * kSlotB + kEdgeOff));
                         } else {
+                            if constexpr (EDGE0) emax = max(emax, __ldcg(a.edge_spill + __ldg(&a.desc[p].w)));
                             const int2* src = a.HE + (long long)__ldg(&a.desc[p].w) * a.stride + j0;
                             const int4 v01 = __ldcg(reinterpret_cast<const int4*>(src));
                             ph[0] = v01.x; pe[0] = v01.y; ph[1] = v01.z; pe[1] = v01.w;
@@ -389,6 +406,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                             }
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
                             else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p);
+                            else if constexpr (EDGE0) Hd0 = __ldcg(a.edge_spill + __ldg(&a.desc[p].w));
                             else Hd0 = __ldg(a.hneg1 + p) * 256;
                         }
                         const int wd = 192 + 63 - j, we = 64 + 63 - j;
@@ -399,6 +417,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                         for (int c = 0; c < C; c++) ke[c] = __viaddmax_s32(pe[c], we, ke[c]);
                     }
                 }
+                if constexpr (EDGE0) { Hedge = (flags & kPoaHead) ? OEk : emax + ES; Fin = Hedge + OES; }
 #pragma unroll
                 for (int c = 0; c < C; c++) hk[c] = kd[c] + ((int)rc[c] == b ? MS : XS);
                 finish_row(r, hk, ke, Hedge, Fin, flags, dsc.w);
@@ -417,8 +436,12 @@ __global__ void __launch_bounds__(32) poa_rows_kernel(const __grid_constant__ Po
     int band = 0;
     if (lane == 0) band = (int)atomicAdd(a.ticket, 1u);
     band = __shfl_sync(kFullMask, band, 0);
-    if (band + 1 == a.nbands) poa_rows_sweep<C, true>(a, sm, band, lane);
-    else poa_rows_sweep<C, false>(a, sm, band, lane);
+    const bool edge0 = band == 0 && a.hneg1 == nullptr;
+    if (band + 1 == a.nbands) {
+        if (edge0) poa_rows_sweep<C, true, true>(a, sm, band, lane);
+        else poa_rows_sweep<C, true, false>(a, sm, band, lane);
+    } else if (edge0) poa_rows_sweep<C, false, true>(a, sm, band, lane);
+    else poa_rows_sweep<C, false, false>(a, sm, band, lane);
 }
 
 }  // namespace tsta

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "poa_fill.cuh"
 #include "poa_rows.cuh"
+#include "poa_build.cuh"
 
 namespace tsta {
 int check_params(const tsta_params* p);
@@ -23,6 +24,11 @@ struct tsta_poa {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     DevBuf d_rowptr, d_pred, d_base, d_hneg1, d_read, d_HE, d_trace, d_bnd, d_ctl, d_last, d_path, d_desc;
+    // device-resident graph (tsta_poa_graph_update / tsta_poa_fill_resident, poa_build.cuh)
+    DevBuf d_nmeta, d_npre, d_nsub, d_sort, d_keep, d_recs, d_edge;
+    int node_cap = 0;              // nodes the resident table has room for
+    bool fixed8 = false;           // the last fill's predecessor table is at stride 8 (no row_ptr)
+    long long h2d_bytes = 0;       // graph + read bytes uploaded by the fills of this context
     std::vector<uint4> h_desc;
     unsigned epoch = 0;
     int nrows = 0, len = 0, nbands = 0, C = kPoaC;
@@ -45,11 +51,124 @@ static void poa_free(tsta_poa* p)
     if (!p) return;
     cudaSetDevice(p->device);
     DevBuf* bufs[] = {&p->d_rowptr, &p->d_pred, &p->d_base, &p->d_hneg1, &p->d_read, &p->d_HE,
-                      &p->d_trace, &p->d_bnd, &p->d_ctl, &p->d_last, &p->d_path, &p->d_desc};
+                      &p->d_trace, &p->d_bnd, &p->d_ctl, &p->d_last, &p->d_path, &p->d_desc,
+                      &p->d_nmeta, &p->d_npre, &p->d_nsub, &p->d_sort, &p->d_keep, &p->d_recs, &p->d_edge};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
+}
+
+// Buffers grow with 60 % headroom: the graph gains rows every round and a cudaFree + cudaMalloc pair costs
+// milliseconds whatever the size (tools/malloc_time.py), so a 16-read job reallocates once or twice.
+static int poa_grow(DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return (int)TSTA_OK;
+    if (b.reserve(bytes + bytes * 3 / 5 + 4096) == TSTA_OK) return (int)TSTA_OK;
+    return b.reserve(bytes);                                    // no room for headroom: exact size
+}
+
+// Same, keeping the first `used` bytes (the resident node table).
+static int poa_grow_keep(DevBuf& b, size_t bytes, size_t used, cudaStream_t st)
+{
+    if (bytes <= b.cap) return (int)TSTA_OK;
+    DevBuf nb;
+    if (nb.reserve(bytes + bytes * 3 / 5 + 4096) != TSTA_OK) {
+        if (int rc = nb.reserve(bytes)) return rc;
+    }
+    if (used > 0 && b.p) {
+        cudaError_t e = cudaMemcpyAsync(nb.p, b.p, used, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { nb.release(); return set_error(TSTA_ECUDA, "node table copy failed: %s", cudaGetErrorString(e)); }
+    }
+    b.release();
+    b = nb;
+    return TSTA_OK;
+}
+
+// Strip width and kernel for this read (see tsta_poa_fill).
+static void poa_choose(tsta_poa* p, int L, int nrows, const char* read, int len)
+{
+    // Strip width.  The kernels are templates (2 or 4 columns per lane); 4 is the default: the per-row cost barely
+    // shrinks with the strip, so twice the bands only add start-up.
+    p->C = 4;
+    if (const char* e = getenv("TSTA_POA_C")) { const int c = atoi(e); if (c == 2 || c == 4) p->C = c; }
+    // Kernel.  poa_rows_kernel (row-synchronous, F by a max-plus scan; poa_rows.cuh) is the default; the skewed
+    // poa_fill_kernel keeps the reads with 'N' columns (quirk Q3 is a second horizontal chain) and strip widths
+    // that do not divide L (the late-head re-base must fall on a lane's first column).  TSTA_POA_KERNEL=skew forces it.
+    p->rows_kernel = (L % p->C == 0) && memchr(read, 'N', (size_t)len) == nullptr;
+    if (const char* e = getenv("TSTA_POA_KERNEL")) { if (!strcmp(e, "skew")) p->rows_kernel = false; }
+    const int band_cols = 32 * p->C;
+    p->nbands = (len + band_cols - 1) / band_cols;
+    p->stride = (long long)p->nbands * band_cols;
+    p->nrows = nrows;
+    p->len = len;
+}
+
+// Everything after the graph tables are in place: working buffers, the read, the fill launch, lastsorce back.
+// pred_tab / hneg1_dev: the predecessor rows the slow path reads and H(r,-1) (NULL: computed by band 0).
+static int poa_launch(tsta_poa* p, const tsta_params* prm, int L, int nrows, size_t nkeep, const int* pred_tab, const int* hneg1_dev,
+                      const char* read, int len, int32_t* lastsorce, float* kernel_ms)
+{
+    const double t1 = poa_now();
+    if (int rc = poa_grow(p->d_read, (size_t)len)) return rc;
+    if (int rc = poa_grow(p->d_last, (size_t)nrows * 4)) return rc;
+    if (int rc = p->d_ctl.reserve(64)) return rc;
+    if (int rc = poa_grow(p->d_path, (size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
+    {
+        const size_t cells = (size_t)nrows * (size_t)p->stride;
+        const size_t spill = std::max<size_t>(nkeep, 1) * (size_t)p->stride * sizeof(int2);
+        if (int rc = poa_grow(p->d_HE, spill)) return rc;
+        if (int rc = poa_grow(p->d_edge, std::max<size_t>(nkeep, 1) * 4)) return rc;
+        if (int rc = poa_grow(p->d_trace, cells * 2)) return rc;
+        const size_t need = (size_t)p->nbands * (size_t)nrows * 8;
+        if (need > p->d_bnd.cap) {
+            if (int rc = poa_grow(p->d_bnd, need)) return rc;
+            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+            p->epoch = 0;
+        }
+    }
+    if (++p->epoch > 0x7fffu) {
+        TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
+        p->epoch = 1;
+    }
+    const double t2 = poa_now();
+    p->t_alloc += t2 - t1;
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_read.p, read, (size_t)len, cudaMemcpyHostToDevice, p->stream));
+    p->h2d_bytes += len;
+    TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.p, 0, 32, p->stream));
+
+    PoaFillArgs a{};
+    a.desc = p->d_desc.as<uint4>();
+    a.row_ptr = p->d_rowptr.as<int>(); a.pred_row = pred_tab;
+    a.base = p->d_base.as<uint8_t>(); a.hneg1 = hneg1_dev; a.read = p->d_read.as<uint8_t>();
+    a.edge_spill = p->d_edge.as<int>();
+    a.len = len; a.nrows = nrows; a.nbands = p->nbands; a.L = L;
+    a.M = prm->M; a.X = prm->X; a.E = prm->E; a.O = prm->O;
+    a.HE = p->d_HE.as<int2>(); a.stride = p->stride;
+    a.trace = p->d_trace.as<uint16_t>();
+    a.bnd = p->d_bnd.as<unsigned long long>(); a.epoch = p->epoch;
+    a.ticket = p->d_ctl.as<unsigned>();
+    a.lastsorce = p->d_last.as<int>();
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+    {
+        NvtxRange range("tsta_poa fill");
+        (p->rows_kernel ? p->n_fill_rows : p->n_fill_skew)++;
+        if (p->rows_kernel) {
+            if (p->C == 2) poa_rows_kernel<2><<<p->nbands, 32, sizeof(PoaRowsSmem<2>), p->stream>>>(a);
+            else poa_rows_kernel<4><<<p->nbands, 32, sizeof(PoaRowsSmem<4>), p->stream>>>(a);
+        } else if (p->C == 2) poa_fill_kernel<2><<<p->nbands, 32, sizeof(PoaSmemC<2>), p->stream>>>(a);
+        else poa_fill_kernel<4><<<p->nbands, 32, sizeof(PoaSmemC<4>), p->stream>>>(a);
+    }
+    TSTA_CUDA_TRY(cudaGetLastError());
+    TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(lastsorce, p->d_last.p, (size_t)nrows * 4, cudaMemcpyDeviceToHost, p->stream));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (kernel_ms) TSTA_CUDA_TRY(cudaEventElapsedTime(kernel_ms, p->ev[0], p->ev[1]));
+    p->filled = true;
+    p->launches = 1;
+    p->t_run += poa_now() - t2;
+    return TSTA_OK;
 }
 
 extern "C" {
@@ -159,98 +278,121 @@ int tsta_poa_fill(tsta_poa* p, const tsta_params* prm, int L, int nrows,
             q.x |= kPoaPlainRow << 16;
     }
     p->n_keep += (long long)nkeep;
-    // Strip width.  The kernel is a template (2 or 4 columns per lane).  Measured on 16 x 50 kbp: 4 columns (391 bands)
-    // fill in 398 ms, 2 columns (782 bands, two per SM sub-partition) in 445 ms -- the fixed cost of a step (shuffle,
-    // history round trip, descriptor) does not shrink with the strip, and twice the bands double the start-up.
-    p->C = 4;
-    if (const char* e = getenv("TSTA_POA_C")) { const int c = atoi(e); if (c == 2 || c == 4) p->C = c; }
-    // Kernel.  poa_rows_kernel (row-synchronous, F by a max-plus scan; poa_rows.cuh) is the default; the skewed
-    // poa_fill_kernel keeps the reads with 'N' columns (quirk Q3 is a second horizontal chain) and strip widths
-    // that do not divide L (the late-head re-base must fall on a lane's first column).  TSTA_POA_KERNEL=skew forces it.
-    p->rows_kernel = (L % p->C == 0) && memchr(read, 'N', (size_t)len) == nullptr;
-    if (const char* e = getenv("TSTA_POA_KERNEL")) { if (!strcmp(e, "skew")) p->rows_kernel = false; }
-    const int band_cols = 32 * p->C;
-    p->nbands = (len + band_cols - 1) / band_cols;
-    p->stride = (long long)p->nbands * band_cols;
-    p->nrows = nrows;
-    p->len = len;
+    poa_choose(p, L, nrows, read, len);
+    p->fixed8 = false;
     const double t1 = poa_now();
     p->t_desc += t1 - t0;
-
-    // The graph gains rows every round and a cudaFree + cudaMalloc pair costs milliseconds whatever
-    // the size (tools/malloc_time.py), so every buffer grows with 60 % headroom: a 16-read job
-    // reallocates once or twice instead of on every call.
-    auto grow = [](DevBuf& b, size_t bytes) {
-        if (bytes <= b.cap) return (int)TSTA_OK;
-        if (b.reserve(bytes + bytes * 3 / 5 + 4096) == TSTA_OK) return (int)TSTA_OK;
-        return b.reserve(bytes);                                    // no room for headroom: exact size
-    };
-    if (int rc = grow(p->d_desc, (size_t)nrows * sizeof(uint4))) return rc;
-    if (int rc = grow(p->d_rowptr, (size_t)(nrows + 1) * 4)) return rc;
-    if (int rc = grow(p->d_pred, (size_t)nedges * 4)) return rc;
-    if (int rc = grow(p->d_base, (size_t)nrows)) return rc;
-    if (int rc = grow(p->d_hneg1, (size_t)nrows * 4)) return rc;
-    if (int rc = grow(p->d_read, (size_t)len)) return rc;
-    if (int rc = grow(p->d_last, (size_t)nrows * 4)) return rc;
-    if (int rc = p->d_ctl.reserve(64)) return rc;
-    if (int rc = grow(p->d_path, (size_t)(nrows + len + 1) * sizeof(PoaStep))) return rc;
-    {   // grow generously: the graph gains rows every round
-        const size_t cells = (size_t)nrows * (size_t)p->stride;
-        const size_t spill = std::max<size_t>(nkeep, 1) * (size_t)p->stride * sizeof(int2);
-        if (int rc = grow(p->d_HE, spill)) return rc;
-        if (int rc = grow(p->d_trace, cells * 2)) return rc;
-        const size_t need = (size_t)p->nbands * (size_t)nrows * 8;
-        if (need > p->d_bnd.cap) {
-            if (int rc = grow(p->d_bnd, need)) return rc;
-            TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
-            p->epoch = 0;
-        }
-    }
-    if (++p->epoch > 0x7fffu) {
-        TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
-        p->epoch = 1;
-    }
-    const double t2 = poa_now();
-    p->t_alloc += t2 - t1;
+    if (int rc = poa_grow(p->d_desc, (size_t)nrows * sizeof(uint4))) return rc;
+    if (int rc = poa_grow(p->d_rowptr, (size_t)(nrows + 1) * 4)) return rc;
+    if (int rc = poa_grow(p->d_pred, (size_t)nedges * 4)) return rc;
+    if (int rc = poa_grow(p->d_hneg1, (size_t)nrows * 4)) return rc;
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_desc.p, p->h_desc.data(), (size_t)nrows * sizeof(uint4), cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_rowptr.p, row_ptr, (size_t)(nrows + 1) * 4, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_pred.p, pred_row, (size_t)nedges * 4, cudaMemcpyHostToDevice, p->stream));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_base.p, base, (size_t)nrows, cudaMemcpyHostToDevice, p->stream));
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_hneg1.p, hneg1, (size_t)nrows * 4, cudaMemcpyHostToDevice, p->stream));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_read.p, read, (size_t)len, cudaMemcpyHostToDevice, p->stream));
-    TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.p, 0, 64, p->stream));
+    p->h2d_bytes += (long long)nrows * (sizeof(uint4) + 8) + 4 + (long long)nedges * 4;
+    return poa_launch(p, prm, L, nrows, nkeep, p->d_pred.as<int>(), p->d_hneg1.as<int>(), read, len, lastsorce, kernel_ms);
+}
 
-    PoaFillArgs a{};
-    a.desc = p->d_desc.as<uint4>();
-    a.row_ptr = p->d_rowptr.as<int>(); a.pred_row = p->d_pred.as<int>();
-    a.base = p->d_base.as<uint8_t>(); a.hneg1 = p->d_hneg1.as<int>(); a.read = p->d_read.as<uint8_t>();
-    a.len = len; a.nrows = nrows; a.nbands = p->nbands; a.L = L;
-    a.M = prm->M; a.X = prm->X; a.E = prm->E; a.O = prm->O;
-    a.HE = p->d_HE.as<int2>(); a.stride = p->stride;
-    a.trace = p->d_trace.as<uint16_t>();
-    a.bnd = p->d_bnd.as<unsigned long long>(); a.epoch = p->epoch;
-    a.ticket = p->d_ctl.as<unsigned>();
-    a.lastsorce = p->d_last.as<int>();
-    TSTA_CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
-    {
-        NvtxRange range("tsta_poa fill");
-        (p->rows_kernel ? p->n_fill_rows : p->n_fill_skew)++;
-        if (p->rows_kernel) {
-            if (p->C == 2) poa_rows_kernel<2><<<p->nbands, 32, sizeof(PoaRowsSmem<2>), p->stream>>>(a);
-            else poa_rows_kernel<4><<<p->nbands, 32, sizeof(PoaRowsSmem<4>), p->stream>>>(a);
-        } else if (p->C == 2) poa_fill_kernel<2><<<p->nbands, 32, sizeof(PoaSmemC<2>), p->stream>>>(a);
-        else poa_fill_kernel<4><<<p->nbands, 32, sizeof(PoaSmemC<4>), p->stream>>>(a);
+// ---------------------------------------------------------------------------------------
+// device-resident graph: changed node records in, row tables built on the device (poa_build.cuh)
+// ---------------------------------------------------------------------------------------
+int tsta_poa_graph_update(tsta_poa* p, int nnodes, int n_narrow, const tsta_poa_node2* narrow, int n_wide, const tsta_poa_node8* wide)
+{
+    if (!p || nnodes <= 0 || n_narrow < 0 || n_wide < 0 || (n_narrow > 0 && !narrow) || (n_wide > 0 && !wide))
+        return set_error(TSTA_EINVAL, "bad POA graph update");
+    static_assert(sizeof(tsta_poa_node2) == sizeof(PoaNodeNarrow) && sizeof(tsta_poa_node8) == sizeof(PoaNodeWide), "node record layout");
+    for (int i = 0; i < n_narrow; i++)
+        if (narrow[i].id < 0 || narrow[i].id >= nnodes || ((narrow[i].base_in >> 8) & 0xffu) > 2u)
+            return set_error(TSTA_EINVAL, "narrow node record %d: id out of range or more than two predecessors", i);
+    for (int i = 0; i < n_wide; i++)
+        if (wide[i].id < 0 || wide[i].id >= nnodes || ((wide[i].base_in >> 8) & 0xffu) > (unsigned)kPoaNodePreds)
+            return set_error(TSTA_EINVAL, "wide node record %d: id out of range or more than eight predecessors", i);
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    if (nnodes > p->node_cap) {
+        const size_t used = (size_t)p->node_cap;
+        if (int rc = poa_grow_keep(p->d_nmeta, (size_t)nnodes * 4, used * 4, p->stream)) return rc;
+        if (int rc = poa_grow_keep(p->d_npre, (size_t)nnodes * 4 * kPoaNodePreds, used * 4 * kPoaNodePreds, p->stream)) return rc;
+        if (int rc = poa_grow_keep(p->d_nsub, (size_t)nnodes * 4, 0, p->stream)) return rc;
+        p->node_cap = (int)std::min<size_t>(p->d_nmeta.cap / 4, std::min(p->d_npre.cap / (4 * kPoaNodePreds), p->d_nsub.cap / 4));
+    }
+    const size_t bytes = (size_t)n_narrow * sizeof(PoaNodeNarrow) + (size_t)n_wide * sizeof(PoaNodeWide);
+    if (bytes == 0) return TSTA_OK;
+    if (int rc = poa_grow(p->d_recs, bytes)) return rc;
+    PoaNodeTable t{p->d_nmeta.as<unsigned>(), p->d_npre.as<int>(), p->d_nsub.as<int>()};
+    char* d = p->d_recs.as<char>();
+    if (n_narrow > 0) {
+        TSTA_CUDA_TRY(cudaMemcpyAsync(d, narrow, (size_t)n_narrow * sizeof(PoaNodeNarrow), cudaMemcpyHostToDevice, p->stream));
+        poa_apply_narrow_kernel<<<(n_narrow + 255) / 256, 256, 0, p->stream>>>(t, reinterpret_cast<const PoaNodeNarrow*>(d), n_narrow);
+    }
+    if (n_wide > 0) {
+        char* dw = d + (size_t)n_narrow * sizeof(PoaNodeNarrow);
+        TSTA_CUDA_TRY(cudaMemcpyAsync(dw, wide, (size_t)n_wide * sizeof(PoaNodeWide), cudaMemcpyHostToDevice, p->stream));
+        poa_apply_wide_kernel<<<(n_wide + 255) / 256, 256, 0, p->stream>>>(t, reinterpret_cast<const PoaNodeWide*>(dw), n_wide);
     }
     TSTA_CUDA_TRY(cudaGetLastError());
-    TSTA_CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
-    TSTA_CUDA_TRY(cudaMemcpyAsync(lastsorce, p->d_last.p, (size_t)nrows * 4, cudaMemcpyDeviceToHost, p->stream));
+    // (the caller's records may be reused as soon as this returns)
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
-    if (kernel_ms) TSTA_CUDA_TRY(cudaEventElapsedTime(kernel_ms, p->ev[0], p->ev[1]));
-    p->filled = true;
-    p->launches = 1;
-    p->t_run += poa_now() - t2;
+    p->h2d_bytes += (long long)bytes;
     return TSTA_OK;
 }
+
+int tsta_poa_fill_resident(tsta_poa* p, const tsta_params* prm, int L, int nrows, const int32_t* sort, const int32_t* hneg1,
+                           const char* read, int len, int32_t* lastsorce, float* kernel_ms)
+{
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (!p) return set_error(TSTA_EINVAL, "context is NULL");
+    if (int rc = check_params(prm)) return rc;
+    if (nrows <= 0 || len <= 0 || !sort || !read || !lastsorce) return set_error(TSTA_EINVAL, "bad POA arguments");
+    if (p->node_cap <= 0) return set_error(TSTA_EINVAL, "tsta_poa_fill_resident before tsta_poa_graph_update");
+    {
+        const long long amax = std::max(std::max(std::abs(prm->M), std::abs(prm->X)), std::abs(prm->E) + std::abs(prm->O));
+        if (((long long)nrows + len + 2) * amax >= (1LL << 22))
+            return set_error(TSTA_EINVAL, "POA job too large for the int32 key packing: (rows + read length) * max|score| must stay below 2^22");
+    }
+    for (int r = 0; r < nrows; r++)
+        if (sort[r] < 0 || sort[r] >= p->node_cap) return set_error(TSTA_EINVAL, "row %d: node id %d is not in the resident table", r, sort[r]);
+    TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    p->filled = false;
+    const double t0 = poa_now();
+    poa_choose(p, L, nrows, read, len);
+    if (!p->rows_kernel && !hneg1)
+        return set_error(TSTA_EINVAL, "this read runs on the skewed kernel ('N' columns, or L not a multiple of the strip width): it needs hneg1");
+    p->fixed8 = true;
+    if (int rc = poa_grow(p->d_desc, (size_t)nrows * sizeof(uint4))) return rc;
+    if (int rc = poa_grow(p->d_sort, (size_t)nrows * 4)) return rc;
+    if (int rc = poa_grow(p->d_keep, (size_t)nrows * 4)) return rc;
+    if (int rc = poa_grow(p->d_pred, (size_t)nrows * 4 * kPoaNodePreds)) return rc;
+    if (int rc = p->d_ctl.reserve(64)) return rc;
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_sort.p, sort, (size_t)nrows * 4, cudaMemcpyHostToDevice, p->stream));
+    p->h2d_bytes += (long long)nrows * 4;
+    const int* hneg1_dev = nullptr;
+    if (!p->rows_kernel) {
+        if (int rc = poa_grow(p->d_hneg1, (size_t)nrows * 4)) return rc;
+        TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_hneg1.p, hneg1, (size_t)nrows * 4, cudaMemcpyHostToDevice, p->stream));
+        p->h2d_bytes += (long long)nrows * 4;
+        hneg1_dev = p->d_hneg1.as<int>();
+    }
+    TSTA_CUDA_TRY(cudaMemsetAsync(p->d_ctl.as<int>() + 8, 0, 4, p->stream));
+    PoaNodeTable t{p->d_nmeta.as<unsigned>(), p->d_npre.as<int>(), p->d_nsub.as<int>()};
+    const int nb = (nrows + 255) / 256;
+    {
+        NvtxRange range("tsta_poa build rows");
+        poa_rows_of_nodes_kernel<<<nb, 256, 0, p->stream>>>(t, p->d_sort.as<int>(), nrows, p->d_keep.as<int>());
+        poa_build_rows_kernel<<<nb, 256, 0, p->stream>>>(t, p->d_sort.as<int>(), nrows, L, p->d_desc.as<uint4>(), p->d_pred.as<int>(), p->d_keep.as<int>());
+        poa_build_keep_kernel<<<nb, 256, 0, p->stream>>>(nrows, p->d_desc.as<uint4>(), p->d_keep.as<int>(), p->d_ctl.as<int>() + 8);
+    }
+    TSTA_CUDA_TRY(cudaGetLastError());
+    int nkeep = 0;     // sizes the spill: a handful of rows per job
+    TSTA_CUDA_TRY(cudaMemcpyAsync(&nkeep, p->d_ctl.as<int>() + 8, 4, cudaMemcpyDeviceToHost, p->stream));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->n_keep += nkeep;
+    p->n_rows += nrows;
+    p->t_desc += poa_now() - t0;
+    return poa_launch(p, prm, L, nrows, (size_t)nkeep, p->d_pred.as<int>(), hneg1_dev, read, len, lastsorce, kernel_ms);
+}
+
+long long tsta_poa_h2d_bytes(const tsta_poa* p) { return p ? p->h2d_bytes : 0; }
 
 int tsta_poa_walk(tsta_poa* p, int start_row, tsta_poa_step* path, int* nsteps, float* kernel_ms)
 {
@@ -262,7 +404,8 @@ int tsta_poa_walk(tsta_poa* p, int start_row, tsta_poa_step* path, int* nsteps, 
     PoaWalkArgs w{};
     w.trace = p->d_trace.as<uint16_t>(); w.stride = p->stride;
     w.row_ptr = p->d_rowptr.as<int>(); w.pred_row = p->d_pred.as<int>();
-    w.base = p->d_base.as<uint8_t>(); w.read = p->d_read.as<uint8_t>();
+    w.desc = p->d_desc.as<uint4>(); w.read = p->d_read.as<uint8_t>();
+    w.fixed8 = p->fixed8 ? 1 : 0;
     w.len = p->len; w.nrows = p->nrows; w.start_row = start_row;
     w.path = p->d_path.as<PoaStep>();
     w.nsteps = p->d_ctl.as<int>() + 4;
