@@ -816,7 +816,7 @@ def wl_msa(ctx, name, steps):
         parity = msa_parity(nreads, min(ln, 10_000), ctx.local_rank)
     return {"value": cells_total / (step_ms * 1e-3) / 1e9, "ms_per_step": step_ms, "steps": steps, "scaling": "weak",
             "e2e": {"value": cells_total / e2e_s / 1e9, "unit": "GCUPS",
-                    "h2d_bytes_per_step": int(sum(len(r) for r in reads[1:]) + 30 * cells_rank / ln),     # reads + CSR graph + descriptors per round
+                    "h2d_bytes_per_step": export_bytes(MSA_LAST.get("export"), int(sum(len(r) for r in reads[1:]) + 30 * cells_rank / ln)),   # counted by the library (reads + changed node records + the permutation per read)
                     "d2h_bytes_per_step": int(12 * cells_rank / ln),                                      # lastsorce + path steps per round
                     "ms_per_step": e2e_s * 1e3,
                     "is": "driver loop per read: graph export + H2D + fill + walk + D2H path + graph fusion + re-sort "
@@ -844,6 +844,14 @@ def msa_parity(nreads, ln_s, device):
         ref = hashlib.md5(open(os.path.join(d, "ref.txt"), "rb").read()).hexdigest()
     return {"checked": True, "ok": ours == ref, "compared": f"-o md5 of TSTA_msa on {nreads} x {ln_s} bp against the reference binary",
             "out_md5": ours, "reference_out_md5": ref}
+
+
+def export_bytes(line, fallback):
+    """`export: N bytes ...` line of TSTA_msa (TSTA_MSA_TIMING=1): what tsta_poa_* copied to the device."""
+    try:
+        return int(line.split()[1])
+    except Exception:
+        return fallback
 
 
 RUNNERS = {"pair": wl_pair, "bands": wl_bands, "batch": wl_batch, "batch_strong": wl_batch, "msa": wl_msa}

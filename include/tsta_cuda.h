@@ -166,6 +166,18 @@ int  tsta_psa_batch_packed(const tsta_params* p, int64_t npairs,
                            uint8_t* ops2, const int64_t* ops_off, int32_t* alen,
                            float* kernel_ms);
 
+/* The 2-bit wire format for ACGT batches (a store that keeps reads packed, or a caller that packs once and aligns
+ * many times): bases0 / bases1 hold four bases per byte, base i of a stream in bits 2(i & 3) .. +1 of byte i >> 2,
+ * codes 0..3 = A C G T; off*[k] and len*[k] count BASES.  A quarter of the read bytes cross PCIe; the device expands
+ * them.  Results are those of tsta_psa_batch on the expanded reads; with want_trace != 0 the moves come back packed
+ * as in tsta_psa_batch_packed (ops_off multiples of 4). */
+int  tsta_psa_batch_2bit(const tsta_params* p, int64_t npairs,
+                         const uint8_t* bases0, const int64_t* off0, const int32_t* len0,
+                         const uint8_t* bases1, const int64_t* off1, const int32_t* len1,
+                         int want_trace, int32_t* maxsorce, int32_t* corner,
+                         uint8_t* ops2, const int64_t* ops_off, int32_t* alen,
+                         float* kernel_ms);
+
 /* ------------------------------------------------------------------------------------ */
 /* Sequence-to-graph alignment (TSTA_msa)                                                */
 /* ------------------------------------------------------------------------------------ */
@@ -208,7 +220,7 @@ typedef struct tsta_poa_node8 { int32_t id; uint32_t base_in; int32_t pre[8]; } 
 int  tsta_poa_graph_update(tsta_poa* ctx, int nnodes, int n_narrow, const tsta_poa_node2* narrow,
                            int n_wide, const tsta_poa_node8* wide);
 /* tsta_poa_fill on the resident graph: sort[r] = id of the node in row r of the current topological
- * order (4 bytes per row is all that crosses PCIe besides the read).  Row descriptors, the
+ * order (it crosses PCIe as 3 bytes per row; that, the changed records and the read are all that is copied).  Row descriptors, the
  * predecessor table in row indices and the spill slots are built on the device; H(r,-1) is computed
  * by the fill itself, so hneg1 may be NULL unless the read runs on the skewed kernel (it contains
  * 'N', or L is not a multiple of the strip width), in which case it is required. */

@@ -156,3 +156,16 @@ def test_msa16x50k_vs_reference(gpu, tmp_path):
     assert p.stderr == q.stderr                      # seq_num: 16
     assert p.stdout == q.stdout                      # progress line
     assert hashlib.md5(ours.read_bytes()).hexdigest() == hashlib.md5(ref.read_bytes()).hexdigest()
+    # the graph stays on the device between reads: against a full export per read, at least five
+    # times fewer bytes cross PCIe -- and the file is the same
+    nbytes = {}
+    for mode in ("resident", "full"):
+        env = dict(os.environ, TSTA_MSA_TIMING="1")
+        if mode == "full":
+            env["TSTA_MSA_FULL_EXPORT"] = "1"
+        out = tmp_path / (mode + ".txt")
+        r = subprocess.run([str(BIN / "TSTA_msa"), "-i", str(fa), "-o", str(out)], capture_output=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr
+        assert out.read_bytes() == ours.read_bytes()
+        nbytes[mode] = int([l for l in r.stderr.decode().splitlines() if l.startswith("export:")][0].split()[1])
+    assert nbytes["full"] >= 5 * nbytes["resident"], nbytes

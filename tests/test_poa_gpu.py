@@ -2,6 +2,7 @@
 through the TSTA_msa driver, with the real reference's outputs."""
 import hashlib
 import json
+import os
 import random
 import subprocess
 from pathlib import Path
@@ -173,6 +174,84 @@ def test_both_fill_kernels_late_heads_dense_graphs(gpu, monkeypatch, kernel, C):
         for fld in ("row", "col", "kind", "pred"):
             np.testing.assert_array_equal(got[fld], want[fld])
     poa.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_resident_graph_tables_built_on_the_device(gpu, seed):
+    """tsta_poa_graph_update + tsta_poa_fill_resident (node records in NODE-id space, only the permutation per read;
+    descriptors, predecessor table, spill slots and H(r,-1) made on the device) against the oracle, across several
+    "rounds" in which nodes are added, predecessor lists change and the order is reshuffled -- including a read
+    with 'N' (skewed kernel, hneg1 supplied) and rows with far predecessors."""
+    rnd = random.Random(3100 + seed)
+    poa = gpu.Poa()
+    M, X, E, O = rnd.choice([(2, -5, -2, -4), (1, -1, -1, 0), (1, -3, -1, -5)])
+    L = rnd.choice([64, 128, 640])
+    ids = {}                                   # row of the first round -> stable node id (shuffled)
+    sent = {}
+    for rnd_no in range(3):
+        nrows = [150, 420, 900][rnd_no] + 37 * seed
+        ln = rnd.choice([90, 260, 700])
+        read = bytearray(synth.random_read(ln, 40 * seed + rnd_no))
+        if rnd_no == 2 and seed % 2 == 0:
+            for i in range(0, ln, 11):
+                read[i] = ord("N")
+        read = bytes(read)
+        g = random_dag(nrows, rnd, E, O, far=0.1, heads=0.03, maxin=8, backbone=read.replace(b"N", b"A"))
+        row_ptr, pred, base, hneg1 = g
+        # stable ids: rows seen before keep theirs, new rows draw fresh ones; rows are "re-sorted" simply by being
+        # a different graph over a superset of the ids -- all the device sees is (records, permutation)
+        fresh = [i for i in range(2 * nrows + 50) if i not in ids.values()]
+        rnd.shuffle(fresh)
+        for r in range(nrows):
+            if r not in ids:
+                ids[r] = fresh.pop()
+        nnodes = max(ids.values()) + 1
+        changed = []
+        for r in range(nrows):
+            ps = [ids[p] for p in pred[row_ptr[r]:row_ptr[r + 1]] if p >= 0]
+            rec = (int(base[r]), ps)
+            if sent.get(ids[r]) != rec:
+                sent[ids[r]] = rec
+                changed.append((ids[r], rec[0], rec[1]))
+        before = poa.h2d_bytes()
+        poa.graph_update(nnodes, changed)
+        sort = np.array([ids[r] for r in range(nrows)], np.int32)
+        has_n = b"N" in read
+        glast, _ = poa.fill_resident(sort, read, M, X, E, O, L, hneg1=hneg1 if has_n else None)
+        assert poa.h2d_bytes() - before <= 16 * len([c for c in changed if len(c[2]) <= 2]) + 40 * len(changed) + 8 * nrows + ln
+        src, es, fs, last = ob.poa_fill(*g, read, M, X, E, O, L)
+        np.testing.assert_array_equal(glast, last)
+        assert_trace(poa, src, es, fs, g)
+        for start in {nrows - 1, rnd.randrange(nrows)}:
+            want = ob.poa_walk(g[0], g[1], src, es, fs, start)
+            got, _ = poa.walk(start)
+            assert len(got) == len(want)
+            for fld in ("row", "col", "kind", "pred"):
+                np.testing.assert_array_equal(got[fld], want[fld])
+    poa.close()
+
+
+def test_msa_full_export_and_resident_graph_agree(gpu, tmp_path, monkeypatch):
+    """The driver's two export modes write the same file; the resident mode copies a fraction of the bytes (a short job:
+    the one-off upload of the first read's nodes weighs more than at 16 x 50 kbp, where tests/test_full_size_gpu.py
+    asks for a factor of five)."""
+    reads = [synth.random_read(6000, 77)]
+    reads += [synth.mutate(reads[0], 0.06, 500 + k)[:6000] for k in range(7)]
+    fa = tmp_path / "r.fa"
+    ob.write_fasta(fa, reads)
+    out, nbytes = {}, {}
+    for mode in ("resident", "full"):
+        env = dict(os.environ, TSTA_MSA_TIMING="1")
+        if mode == "full":
+            env["TSTA_MSA_FULL_EXPORT"] = "1"
+        fo = tmp_path / (mode + ".txt")
+        p = subprocess.run([str(BIN / "TSTA_msa"), "-i", str(fa), "-o", str(fo)], capture_output=True, timeout=900, env=env)
+        assert p.returncode == 0, p.stderr
+        out[mode] = fo.read_bytes()
+        line = [l for l in p.stderr.decode().splitlines() if l.startswith("export:")][0]
+        nbytes[mode] = int(line.split()[1])
+    assert out["resident"] == out["full"]
+    assert nbytes["full"] >= 3 * nbytes["resident"], nbytes
 
 
 def run_msa(reads, prm, W, tmp_path):

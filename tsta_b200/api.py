@@ -360,9 +360,13 @@ def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False, packed=False) -> BatchR
 
 
 def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4, trace=False,
-                     pairs=None, swapped=None, out=None, packed=False) -> BatchResult:
+                     pairs=None, swapped=None, out=None, packed=False, bits2=False) -> BatchResult:
     """Array form of tsta_psa_batch (what bench.py uses; no per-pair Python objects).
-    `out` = (maxsorce, corner[, ops, ops_off, alen]) preallocated arrays (e.g. pinned) to write into."""
+    `out` = (maxsorce, corner[, ops, ops_off, alen]) preallocated arrays (e.g. pinned) to write into.
+    bits2: seqs0 / seqs1 are in the 2-bit wire format (pack_2bit), offsets and lengths in bases (tsta_psa_batch_2bit;
+    traced results then come back packed)."""
+    if bits2:
+        packed = True
     npairs = len(len0)
     ms = out[0] if out else np.zeros(npairs, dtype=np.int32)
     corner = out[1] if out else np.zeros(npairs, dtype=np.int32)
@@ -382,7 +386,18 @@ def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4
         alen = np.zeros(npairs, dtype=np.int32)
     b0 = seqs0 if isinstance(seqs0, bytes) else seqs0.ctypes.data
     b1 = seqs1 if isinstance(seqs1, bytes) else seqs1.ctypes.data
-    if trace and packed:
+    if bits2:
+        L = load()
+        L.tsta_psa_batch_2bit.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.tsta_psa_batch_2bit(
+            C.byref(p), npairs,
+            C.cast(b0, C.c_void_p), off0.ctypes.data, len0.ctypes.data,
+            C.cast(b1, C.c_void_p), off1.ctypes.data, len1.ctypes.data,
+            int(trace), ms.ctypes.data, corner.ctypes.data,
+            ops.ctypes.data if trace else None, ops_off.ctypes.data if trace else None,
+            alen.ctypes.data if trace else None, C.byref(kms)))
+    elif trace and packed:
         L = load()
         L.tsta_psa_batch_packed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -402,6 +417,19 @@ def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4
     return BatchResult(ms, corner, kms.value,
                        swapped if swapped is not None else np.zeros(npairs, dtype=bool),
                        ops, ops_off, alen, pairs, bool(trace and packed))
+
+
+def pack_2bit(seq) -> np.ndarray:
+    """ACGT bytes -> the 2-bit wire format of tsta_psa_batch_2bit (base i in bits 2(i & 3).. of byte i >> 2)."""
+    a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.asarray(seq, dtype=np.uint8)
+    code = np.zeros(256, dtype=np.uint8)
+    code[ord("C")], code[ord("G")], code[ord("T")] = 1, 2, 3
+    c = code[a]
+    pad = (-len(c)) % 4
+    if pad:
+        c = np.concatenate([c, np.zeros(pad, dtype=np.uint8)])
+    c = c.reshape(-1, 4)
+    return (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8)
 
 
 # ------------------------------------------------------------------------------------------
@@ -441,6 +469,51 @@ class Poa:
                                     base.ctypes.data, hneg1.ctypes.data, read, self.len, last.ctypes.data,
                                     C.byref(ms)))
         return last, ms.value
+
+    NODE2 = np.dtype([("id", "<i4"), ("base_in", "<u4"), ("pre", "<i4", (2,))])
+    NODE8 = np.dtype([("id", "<i4"), ("base_in", "<u4"), ("pre", "<i4", (8,))])
+
+    def graph_update(self, nnodes: int, nodes) -> None:
+        """tsta_poa_graph_update: `nodes` = iterable of (id, base, [predecessor node ids]) (a head: empty list)."""
+        L = load()
+        L.tsta_poa_graph_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        nodes = list(nodes)
+        narrow = np.zeros(sum(1 for n in nodes if len(n[2]) <= 2), dtype=self.NODE2)
+        wide = np.zeros(len(nodes) - len(narrow), dtype=self.NODE8)
+        i2 = i8 = 0
+        for nid, base, pre in nodes:
+            rec = narrow if len(pre) <= 2 else wide
+            k = i2 if len(pre) <= 2 else i8
+            rec[k]["id"], rec[k]["base_in"] = nid, base | (len(pre) << 8)
+            rec[k]["pre"][:] = -1
+            rec[k]["pre"][:len(pre)] = pre
+            if len(pre) <= 2:
+                i2 += 1
+            else:
+                i8 += 1
+        _check(L.tsta_poa_graph_update(self._h, nnodes, len(narrow), narrow.ctypes.data if len(narrow) else None,
+                                       len(wide), wide.ctypes.data if len(wide) else None))
+
+    def fill_resident(self, sort, read: bytes, M=2, X=-5, E=-2, O=-4, L=640, hneg1=None):
+        """tsta_poa_fill_resident: sort[r] = node id of row r.  Returns (lastsorce[nrows] int32, kernel_ms)."""
+        Lb = load()
+        Lb.tsta_poa_fill_resident.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_float)]
+        sort = np.ascontiguousarray(sort, dtype=np.int32)
+        h = None if hneg1 is None else np.ascontiguousarray(hneg1, dtype=np.int32)
+        self.nrows, self.len = len(sort), len(read)
+        last = np.zeros(self.nrows, dtype=np.int32)
+        ms = C.c_float()
+        p = Params(M, X, E, O)
+        _check(Lb.tsta_poa_fill_resident(self._h, C.byref(p), L, self.nrows, sort.ctypes.data,
+                                         None if h is None else h.ctypes.data, read, self.len, last.ctypes.data, C.byref(ms)))
+        return last, ms.value
+
+    def h2d_bytes(self) -> int:
+        L = load()
+        L.tsta_poa_h2d_bytes.argtypes = [C.c_void_p]
+        L.tsta_poa_h2d_bytes.restype = C.c_longlong
+        return int(L.tsta_poa_h2d_bytes(self._h))
 
     def walk(self, start_row: int):
         """Returns (steps as a structured numpy array, kernel_ms)."""

@@ -3,7 +3,7 @@
 // Reference: every read re-sorts the graph and the DP re-reads all of it (msa/msa.c:132-133, msa/topo.c:243-260).
 // The per-read host export + re-upload of round 1 (CSR, base, hneg1, 16-byte descriptors: ~30 bytes per row)
 // becomes: the node table (base, in-degree, up to eight predecessor NODE IDS) lives on the device; after a read is
-// fused the host sends only the records of the nodes that changed and the permutation t_sort produced (4 bytes per
+// fused the host sends only the records of the nodes that changed and the permutation t_sort produced (3 bytes per
 // row); these kernels turn that into what the fill and the walker read -- row descriptors (poa_fill.cuh), a
 // fixed-stride predecessor table in row indices, spill slots.  H(r,-1) is computed by the fill itself
 // (poa_rows.cuh, EDGE0).
@@ -25,31 +25,40 @@ struct PoaNodeTable {
     int* sub;                // [nodes] row of the node in the current order
 };
 
-__global__ void __launch_bounds__(256) poa_apply_narrow_kernel(PoaNodeTable t, const PoaNodeNarrow* recs, int n)
+// Changed node records as they cross PCIe: n1 records of 12 bytes (in-degree <= 1: id, base_in, pre0), then n2 of
+// 16 bytes (in-degree 2), then n8 of 40 bytes (up to eight predecessors), back to back.
+__global__ void __launch_bounds__(256) poa_apply_records_kernel(PoaNodeTable t, const int* buf, int n1, int n2, int n8)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const PoaNodeNarrow r = recs[i];
-    t.meta[r.id] = r.base_in;
-    t.pre[(size_t)r.id * kPoaNodePreds] = r.pre[0];
-    t.pre[(size_t)r.id * kPoaNodePreds + 1] = r.pre[1];
-}
-
-__global__ void __launch_bounds__(256) poa_apply_wide_kernel(PoaNodeTable t, const PoaNodeWide* recs, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const PoaNodeWide& r = recs[i];
-    t.meta[r.id] = r.base_in;
+    if (i < n1) {
+        const int* r = buf + (size_t)i * 3;
+        t.meta[r[0]] = (unsigned)r[1];
+        t.pre[(size_t)r[0] * kPoaNodePreds] = r[2];
+    } else if (i < n1 + n2) {
+        const int* r = buf + (size_t)n1 * 3 + (size_t)(i - n1) * 4;
+        t.meta[r[0]] = (unsigned)r[1];
+        t.pre[(size_t)r[0] * kPoaNodePreds] = r[2];
+        t.pre[(size_t)r[0] * kPoaNodePreds + 1] = r[3];
+    } else if (i < n1 + n2 + n8) {
+        const int* r = buf + (size_t)n1 * 3 + (size_t)n2 * 4 + (size_t)(i - n1 - n2) * 10;
+        t.meta[r[0]] = (unsigned)r[1];
 #pragma unroll
-    for (int j = 0; j < kPoaNodePreds; j++) t.pre[(size_t)r.id * kPoaNodePreds + j] = r.pre[j];
+        for (int j = 0; j < kPoaNodePreds; j++) t.pre[(size_t)r[0] * kPoaNodePreds + j] = r[2 + j];
+    }
 }
 
-__global__ void __launch_bounds__(256) poa_rows_of_nodes_kernel(PoaNodeTable t, const int* sort, int nrows, int* keep)
+// The permutation arrives as 3-byte node ids (4-byte when the graph has 2^24 nodes or more): unpack it, note the row
+// of every node, clear the spill marks.
+__global__ void __launch_bounds__(256) poa_rows_of_nodes_kernel(PoaNodeTable t, const uint8_t* packed, int id_bytes, int* sort,
+                                                                int nrows, int* keep)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
-    t.sub[sort[r]] = r;
+    const uint8_t* q = packed + (size_t)r * id_bytes;
+    int id = (int)q[0] | ((int)q[1] << 8) | ((int)q[2] << 16);
+    if (id_bytes == 4) id |= (int)q[3] << 24;
+    sort[r] = id;
+    t.sub[id] = r;
     keep[r] = 0;
 }
 

@@ -30,6 +30,7 @@ struct tsta_poa {
     bool fixed8 = false;           // the last fill's predecessor table is at stride 8 (no row_ptr)
     long long h2d_bytes = 0;       // graph + read bytes uploaded by the fills of this context
     std::vector<uint4> h_desc;
+    std::vector<int> h_stage;      // transport form of changed node records / the packed permutation
     unsigned epoch = 0;
     int nrows = 0, len = 0, nbands = 0, C = kPoaC;
     bool rows_kernel = true;       // last fill ran poa_rows_kernel (row-synchronous) rather than poa_fill_kernel (skewed)
@@ -316,20 +317,27 @@ int tsta_poa_graph_update(tsta_poa* p, int nnodes, int n_narrow, const tsta_poa_
         if (int rc = poa_grow_keep(p->d_nsub, (size_t)nnodes * 4, 0, p->stream)) return rc;
         p->node_cap = (int)std::min<size_t>(p->d_nmeta.cap / 4, std::min(p->d_npre.cap / (4 * kPoaNodePreds), p->d_nsub.cap / 4));
     }
-    const size_t bytes = (size_t)n_narrow * sizeof(PoaNodeNarrow) + (size_t)n_wide * sizeof(PoaNodeWide);
+    // transport form (poa_build.cuh): 12-byte records for in-degree <= 1, 16 bytes for 2, 40 bytes up to 8
+    std::vector<int>& st = p->h_stage;
+    st.clear();
+    int n1 = 0, n2 = 0;
+    for (int i = 0; i < n_narrow; i++)
+        if (((narrow[i].base_in >> 8) & 0xffu) <= 1u) { st.push_back(narrow[i].id); st.push_back((int)narrow[i].base_in); st.push_back(narrow[i].pre[0]); n1++; }
+    for (int i = 0; i < n_narrow; i++)
+        if (((narrow[i].base_in >> 8) & 0xffu) == 2u) {
+            st.push_back(narrow[i].id); st.push_back((int)narrow[i].base_in); st.push_back(narrow[i].pre[0]); st.push_back(narrow[i].pre[1]); n2++;
+        }
+    for (int i = 0; i < n_wide; i++) {
+        st.push_back(wide[i].id); st.push_back((int)wide[i].base_in);
+        for (int j = 0; j < kPoaNodePreds; j++) st.push_back(wide[i].pre[j]);
+    }
+    const size_t bytes = st.size() * sizeof(int);
     if (bytes == 0) return TSTA_OK;
     if (int rc = poa_grow(p->d_recs, bytes)) return rc;
     PoaNodeTable t{p->d_nmeta.as<unsigned>(), p->d_npre.as<int>(), p->d_nsub.as<int>()};
-    char* d = p->d_recs.as<char>();
-    if (n_narrow > 0) {
-        TSTA_CUDA_TRY(cudaMemcpyAsync(d, narrow, (size_t)n_narrow * sizeof(PoaNodeNarrow), cudaMemcpyHostToDevice, p->stream));
-        poa_apply_narrow_kernel<<<(n_narrow + 255) / 256, 256, 0, p->stream>>>(t, reinterpret_cast<const PoaNodeNarrow*>(d), n_narrow);
-    }
-    if (n_wide > 0) {
-        char* dw = d + (size_t)n_narrow * sizeof(PoaNodeNarrow);
-        TSTA_CUDA_TRY(cudaMemcpyAsync(dw, wide, (size_t)n_wide * sizeof(PoaNodeWide), cudaMemcpyHostToDevice, p->stream));
-        poa_apply_wide_kernel<<<(n_wide + 255) / 256, 256, 0, p->stream>>>(t, reinterpret_cast<const PoaNodeWide*>(dw), n_wide);
-    }
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_recs.p, st.data(), bytes, cudaMemcpyHostToDevice, p->stream));
+    const int nrec = n1 + n2 + n_wide;
+    poa_apply_records_kernel<<<(nrec + 255) / 256, 256, 0, p->stream>>>(t, p->d_recs.as<int>(), n1, n2, n_wide);
     TSTA_CUDA_TRY(cudaGetLastError());
     // (the caller's records may be reused as soon as this returns)
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
@@ -364,8 +372,20 @@ int tsta_poa_fill_resident(tsta_poa* p, const tsta_params* prm, int L, int nrows
     if (int rc = poa_grow(p->d_keep, (size_t)nrows * 4)) return rc;
     if (int rc = poa_grow(p->d_pred, (size_t)nrows * 4 * kPoaNodePreds)) return rc;
     if (int rc = p->d_ctl.reserve(64)) return rc;
-    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_sort.p, sort, (size_t)nrows * 4, cudaMemcpyHostToDevice, p->stream));
-    p->h2d_bytes += (long long)nrows * 4;
+    // the permutation crosses PCIe as 3-byte ids
+    const int id_bytes = p->node_cap < (1 << 24) ? 3 : 4;
+    if (int rc = poa_grow(p->d_recs, (size_t)nrows * id_bytes + 4)) return rc;
+    p->h_stage.resize(((size_t)nrows * id_bytes + 3) / 4 + 1);
+    {
+        uint8_t* q = reinterpret_cast<uint8_t*>(p->h_stage.data());
+        for (int r = 0; r < nrows; r++, q += id_bytes) {
+            const unsigned id = (unsigned)sort[r];
+            q[0] = (uint8_t)id; q[1] = (uint8_t)(id >> 8); q[2] = (uint8_t)(id >> 16);
+            if (id_bytes == 4) q[3] = (uint8_t)(id >> 24);
+        }
+    }
+    TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_recs.p, p->h_stage.data(), (size_t)nrows * id_bytes, cudaMemcpyHostToDevice, p->stream));
+    p->h2d_bytes += (long long)nrows * id_bytes;
     const int* hneg1_dev = nullptr;
     if (!p->rows_kernel) {
         if (int rc = poa_grow(p->d_hneg1, (size_t)nrows * 4)) return rc;
@@ -378,7 +398,7 @@ int tsta_poa_fill_resident(tsta_poa* p, const tsta_params* prm, int L, int nrows
     const int nb = (nrows + 255) / 256;
     {
         NvtxRange range("tsta_poa build rows");
-        poa_rows_of_nodes_kernel<<<nb, 256, 0, p->stream>>>(t, p->d_sort.as<int>(), nrows, p->d_keep.as<int>());
+        poa_rows_of_nodes_kernel<<<nb, 256, 0, p->stream>>>(t, p->d_recs.as<uint8_t>(), id_bytes, p->d_sort.as<int>(), nrows, p->d_keep.as<int>());
         poa_build_rows_kernel<<<nb, 256, 0, p->stream>>>(t, p->d_sort.as<int>(), nrows, L, p->d_desc.as<uint4>(), p->d_pred.as<int>(), p->d_keep.as<int>());
         poa_build_keep_kernel<<<nb, 256, 0, p->stream>>>(nrows, p->d_desc.as<uint4>(), p->d_keep.as<int>(), p->d_ctl.as<int>() + 8);
     }

@@ -38,12 +38,12 @@ struct BatchCtx {
     cudaStream_t cp = nullptr, dh = nullptr;   // host -> device copies of the chunks ahead; device -> host of finished chunks
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEvent_t evc[kMaxChunks] = {};      // chunk c uploaded and its alphabet scanned
-    DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs;
+    DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs, p0, p1;
     int* h_present = nullptr;   // pinned, 8 words per chunk
     std::vector<cudaEvent_t> ev;   // timing events, two per kernel slice, grown on demand
     void release()
     {
-        DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs};
+        DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs, &p0, &p1};
         for (DevBuf* b : all) b->release();
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -90,7 +90,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
                           const char* seqs1, const int64_t* off1, const int32_t* len1,
                           int want_trace, int32_t* maxsorce, int32_t* corner,
                           uint8_t* ops, const int64_t* ops_off, int32_t* alen,
-                          float* kernel_ms, const bool pack2);
+                          float* kernel_ms, const bool pack2, const bool bits2 = false);
 
 extern "C" int tsta_psa_batch(const tsta_params* prm, int64_t npairs,
                               const char* seqs0, const int64_t* off0, const int32_t* len0,
@@ -112,12 +112,40 @@ extern "C" int tsta_psa_batch_packed(const tsta_params* prm, int64_t npairs,
     return psa_batch_impl(prm, npairs, seqs0, off0, len0, seqs1, off1, len1, 1, maxsorce, corner, ops2, ops_off, alen, kernel_ms, true);
 }
 
+extern "C" int tsta_psa_batch_2bit(const tsta_params* prm, int64_t npairs,
+                                   const uint8_t* bases0, const int64_t* off0, const int32_t* len0,
+                                   const uint8_t* bases1, const int64_t* off1, const int32_t* len1,
+                                   int want_trace, int32_t* maxsorce, int32_t* corner,
+                                   uint8_t* ops2, const int64_t* ops_off, int32_t* alen,
+                                   float* kernel_ms)
+{
+    return psa_batch_impl(prm, npairs, reinterpret_cast<const char*>(bases0), off0, len0, reinterpret_cast<const char*>(bases1), off1, len1,
+                          want_trace ? 1 : 0, maxsorce, corner, ops2, ops_off, alen, kernel_ms, want_trace != 0, true);
+}
+
+// 2-bit wire format -> the byte reads the kernels index their tables with: base i of the stream is bits 2(i%4)..
+// of byte i/4, codes 0..3 = A C G T.  One thread per four output bytes.
+__global__ void __launch_bounds__(256) unpack_2bit_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ out, long long lo, long long hi)
+{
+    const long long q0 = lo >> 2, q1 = (hi + 3) >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += stride) {
+        const unsigned b = packed[q];
+        const unsigned w = __byte_perm(0x54474341u, 0u, (b & 3u) | (((b >> 2) & 3u) << 4) | (((b >> 4) & 3u) << 8) | (((b >> 6) & 3u) << 12));   // "ACGT"
+        const long long i = q << 2;
+        if (i >= lo && i + 4 <= hi) *reinterpret_cast<uint32_t*>(out + i) = w;
+        else
+            for (int k = 0; k < 4; k++)
+                if (i + k >= lo && i + k < hi) out[i + k] = (uint8_t)(w >> (8 * k));
+    }
+}
+
 static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
                           const char* seqs0, const int64_t* off0, const int32_t* len0,
                           const char* seqs1, const int64_t* off1, const int32_t* len1,
                           int want_trace, int32_t* maxsorce, int32_t* corner,
                           uint8_t* ops, const int64_t* ops_off, int32_t* alen,
-                          float* kernel_ms, const bool pack2)
+                          float* kernel_ms, const bool pack2, const bool bits2)
 {
     if (kernel_ms) *kernel_ms = 0.f;
     if (int rc = check_params(prm)) return rc;
@@ -167,6 +195,11 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     int *d_len0, *d_len1, *d_ms, *d_corner, *d_ctl;
     if (int rc = g.alloc(&d_s0, (size_t)tot0, g_ctx.s0)) return rc;
     if (int rc = g.alloc(&d_s1, (size_t)tot1, g_ctx.s1)) return rc;
+    uint8_t *d_p0 = nullptr, *d_p1 = nullptr;       // 2-bit wire format: the packed bytes as they arrive
+    if (bits2) {
+        if (int rc = g.alloc(&d_p0, (size_t)(tot0 + 3) / 4 + 4, g_ctx.p0)) return rc;
+        if (int rc = g.alloc(&d_p1, (size_t)(tot1 + 3) / 4 + 4, g_ctx.p1)) return rc;
+    }
     if (int rc = g.alloc(&d_off0, (size_t)npairs, g_ctx.off0)) return rc;
     if (int rc = g.alloc(&d_off1, (size_t)npairs, g_ctx.off1)) return rc;
     if (int rc = g.alloc(&d_len0, (size_t)npairs, g_ctx.len0)) return rc;
@@ -198,8 +231,21 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
             lo1 = std::min<int64_t>(lo1, off1[k]); hi1 = std::max<int64_t>(hi1, off1[k] + len1[k]);
         }
         cudaStream_t cp = g_ctx.cp;
+        if (bits2) {
+            // a quarter of the bytes cross PCIe; the device expands them to the byte reads (0.1 ms per 500 MB)
+            if (hi0 > lo0) {
+                TSTA_CUDA_TRY(cudaMemcpyAsync(d_p0 + (lo0 >> 2), seqs0 + (lo0 >> 2), (size_t)(((hi0 + 3) >> 2) - (lo0 >> 2)), cudaMemcpyHostToDevice, cp));
+                unpack_2bit_kernel<<<sms * 8, 256, 0, cp>>>(d_p0, d_s0, lo0, hi0);
+            }
+            if (hi1 > lo1) {
+                TSTA_CUDA_TRY(cudaMemcpyAsync(d_p1 + (lo1 >> 2), seqs1 + (lo1 >> 2), (size_t)(((hi1 + 3) >> 2) - (lo1 >> 2)), cudaMemcpyHostToDevice, cp));
+                unpack_2bit_kernel<<<sms * 8, 256, 0, cp>>>(d_p1, d_s1, lo1, hi1);
+            }
+            TSTA_CUDA_TRY(cudaGetLastError());
+        } else {
         if (hi0 > lo0) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0 + lo0, seqs0 + lo0, (size_t)(hi0 - lo0), cudaMemcpyHostToDevice, cp));
         if (hi1 > lo1) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1 + lo1, seqs1 + lo1, (size_t)(hi1 - lo1), cudaMemcpyHostToDevice, cp));
+        }
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_off0 + a0, off0 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1 + a0, off1 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0 + a0, len0 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));

@@ -36,18 +36,30 @@ static void print_usage(void)
 
 #define MSA_ETOOMANY (-77)
 
-/* control() without the tile loop (c-t-simd.c:979-1049) */
+/* control() without the tile loop (c-t-simd.c:979-1049).  Backends that keep the graph on the device get the
+ * nodes that changed (poa_graph_delta) instead of a full export in row order; a graph with a node of more than
+ * eight predecessors -- or TSTA_MSA_FULL_EXPORT=1 -- stays on the full export for the rest of the job. */
+static poa_shadow g_shadow;
+static int g_resident = -1;          /* -1: not decided yet, 0: full export, 1: resident */
+
 static int align_read(poa_graph* g, const char* read, int num, const msa_params* p, const msa_backend* be)
 {
     const int len = (int)strlen(read);
+    if (g_resident < 0) g_resident = be->fill_resident != NULL && getenv("TSTA_MSA_FULL_EXPORT") == NULL;
     poa_csr csr;
+    memset(&csr, 0, sizeof csr);
     double t0 = now_s();
-    poa_graph_export(g, p->E, p->O, &csr);
+    int resident = g_resident;
+    if (resident && poa_graph_delta(g, &g_shadow) != 0) resident = g_resident = 0;
+    const int need_csr = !resident || memchr(read, 'N', (size_t)len) != NULL;   /* ('N' reads: the backend wants hneg1) */
+    if (need_csr) poa_graph_export(g, p->E, p->O, &csr);
     t_export += now_s() - t0;
-    int32_t* lastsorce = (int32_t*)malloc((size_t)(csr.nrows + 1) * sizeof(int32_t));
-    poa_step* path = (poa_step*)malloc((size_t)(csr.nrows + len + 1) * sizeof(poa_step));
+    const int nrows = g->len;
+    int32_t* lastsorce = (int32_t*)malloc((size_t)(nrows + 1) * sizeof(int32_t));
+    poa_step* path = (poa_step*)malloc((size_t)(nrows + len + 1) * sizeof(poa_step));
     t0 = now_s();
-    int rc = be->fill(be->ctx, &csr, read, len, p, lastsorce);
+    int rc = resident ? be->fill_resident(be->ctx, g, &g_shadow, need_csr ? csr.hneg1 : NULL, read, len, p, lastsorce)
+                      : be->fill(be->ctx, &csr, read, len, p, lastsorce);
     t_fill += now_s() - t0;
     if (rc == 0) {
         const int start = poa_graph_pick_start(g, lastsorce);
@@ -61,7 +73,7 @@ static int align_read(poa_graph* g, const char* read, int num, const msa_params*
     }
     free(path);
     free(lastsorce);
-    poa_csr_free(&csr);
+    if (need_csr) poa_csr_free(&csr);
     return rc;
 }
 
@@ -134,6 +146,7 @@ int msa_main(int argc, char* argv[], const msa_backend* be)
         fprintf(stderr, "timing: export %.3f fill %.3f walk %.3f fuse %.3f sort %.3f s (rows %d)\n",
                 t_export, t_fill, t_walk, t_fuse, t_sort, g.len);
     poa_graph_free(&g);
+    poa_shadow_free(&g_shadow);
     fasta_free(&f);
     return 0;
 }

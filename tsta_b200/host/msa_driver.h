@@ -23,6 +23,11 @@ typedef struct msa_backend {
     /* Walk the traceback from (start_row, len-1); path has room for nrows+len steps. */
     int (*walk)(void* ctx, int start_row, poa_step* path);
     const char* (*error)(void* ctx);
+    /* Optional (NULL: not offered): the same fill for a backend that keeps the graph resident -- it receives the
+     * graph itself (its sort[] order) and the records of the nodes that changed since its last call (`delta`);
+     * hneg1 is NULL unless the read contains 'N' (see include/tsta_cuda.h: tsta_poa_fill_resident). */
+    int (*fill_resident)(void* ctx, const poa_graph* g, const poa_shadow* delta, const int32_t* hneg1,
+                         const char* read, int len, const msa_params* p, int32_t* lastsorce);
 } msa_backend;
 
 int msa_main(int argc, char* argv[], const msa_backend* be);

@@ -210,6 +210,61 @@ void poa_csr_free(poa_csr* c)
     memset(c, 0, sizeof *c);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * delta export: node records that changed since the device last saw them
+ * ---------------------------------------------------------------------------------------- */
+int poa_graph_delta(const poa_graph* g, poa_shadow* sh)
+{
+    if (sh->cap < g->nnode) {
+        int cap = sh->cap ? sh->cap : 1024;
+        while (cap < g->nnode) cap *= 2;
+        sh->meta = (uint32_t*)realloc(sh->meta, (size_t)cap * sizeof(uint32_t));
+        sh->pre = (int32_t*)realloc(sh->pre, (size_t)cap * 8 * sizeof(int32_t));
+        memset(sh->meta + sh->cap, 0xff, (size_t)(cap - sh->cap) * sizeof(uint32_t));
+        sh->cap = cap;
+    }
+    sh->n2 = sh->n8 = 0;
+    sh->nedges = 0;
+    for (int r = 0; r < g->len; r++) {
+        const int id = g->sort[r];
+        const poa_node* n = &g->node[id];
+        sh->nedges += n->in > 0 ? n->in : 1;
+        if (n->in > 8) return -1;
+        const uint32_t meta = (uint32_t)n->base | ((uint32_t)n->in << 8);
+        int32_t* sp = sh->pre + (size_t)id * 8;
+        int same = sh->meta[id] == meta;
+        for (int j = 0; same && j < n->in; j++) same = sp[j] == n->pre[j];
+        if (same) continue;
+        sh->meta[id] = meta;
+        for (int j = 0; j < n->in; j++) sp[j] = n->pre[j];
+        if (n->in <= 2) {
+            if (sh->n2 == sh->cap2) {
+                sh->cap2 = sh->cap2 ? sh->cap2 * 2 : 4096;
+                sh->r2 = (poa_rec2*)realloc(sh->r2, (size_t)sh->cap2 * sizeof(poa_rec2));
+            }
+            poa_rec2* q = &sh->r2[sh->n2++];
+            q->id = id; q->base_in = meta;
+            q->pre[0] = n->in > 0 ? n->pre[0] : -1;
+            q->pre[1] = n->in > 1 ? n->pre[1] : -1;
+        } else {
+            if (sh->n8 == sh->cap8) {
+                sh->cap8 = sh->cap8 ? sh->cap8 * 2 : 1024;
+                sh->r8 = (poa_rec8*)realloc(sh->r8, (size_t)sh->cap8 * sizeof(poa_rec8));
+            }
+            poa_rec8* q = &sh->r8[sh->n8++];
+            q->id = id; q->base_in = meta;
+            for (int j = 0; j < 8; j++) q->pre[j] = j < n->in ? n->pre[j] : -1;
+        }
+    }
+    return 0;
+}
+
+void poa_shadow_free(poa_shadow* sh)
+{
+    free(sh->meta); free(sh->pre); free(sh->r2); free(sh->r8);
+    memset(sh, 0, sizeof *sh);
+}
+
 int poa_graph_pick_start(const poa_graph* g, const int32_t* lastsorce)
 {
     int num1 = g->len - 1, best = INT_MIN, seen = 0;

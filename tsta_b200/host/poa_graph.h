@@ -84,6 +84,23 @@ void poa_graph_free(poa_graph* g);
 void poa_graph_export(const poa_graph* g, int E, int O, poa_csr* out);
 void poa_csr_free(poa_csr* c);
 
+/* Delta export for a graph that stays resident on the device (include/tsta_cuda.h: tsta_poa_graph_update):
+ * the records (base, in-degree, predecessor NODE ids) of the live nodes that differ from what was sent
+ * before.  The shadow remembers what the device holds; no bookkeeping inside poa_graph_fuse is needed. */
+typedef struct { int32_t id; uint32_t base_in; int32_t pre[2]; } poa_rec2;
+typedef struct { int32_t id; uint32_t base_in; int32_t pre[8]; } poa_rec8;
+typedef struct {
+    int cap;              /* nodes the shadow covers */
+    uint32_t* meta;       /* [cap] base | in << 8 as last sent (0xffffffff: never sent) */
+    int32_t* pre;         /* [cap][8] */
+    poa_rec2* r2; int n2, cap2;   /* changed nodes with at most two predecessors */
+    poa_rec8* r8; int n8, cap8;   /* ... with three to eight */
+    long long nedges;     /* sum of in-degrees (heads count one) over the live rows */
+} poa_shadow;
+/* Returns 0, or -1 when a live node has more than eight predecessors (it cannot be resident). */
+int poa_graph_delta(const poa_graph* g, poa_shadow* sh);
+void poa_shadow_free(poa_shadow* sh);
+
 /* Start row of the traceback (c-t-simd.c:737-750): among the last `last_node_num` sinks in row
  * order, the one with the largest lastsorce, lowest row on ties. lastsorce is indexed by row. */
 int poa_graph_pick_start(const poa_graph* g, const int32_t* lastsorce);
