@@ -88,6 +88,10 @@ WORKLOADS = {
     "batch10k_linear": ("batch", (10_000, 10_000), False, LINEAR,
                         "batched PSA: 10,000 synthetic 10 kbp pairs per GPU, linear gaps (-O 0), score-only"),
     "batch250_trace": ("batch", (1_000_000, 250), True, AFFINE, "batched PSA with traceback: 1,000,000 pairs of 250 bp per GPU"),
+    "batch250_2bit": ("batch", (1_000_000, 250), False, AFFINE,
+                      "batched PSA: 1,000,000 synthetic 250 bp pairs per GPU, reads in the 2-bit wire format (tsta_psa_batch_2bit), score-only"),
+    "batch250_trace_2bit": ("batch", (1_000_000, 250), True, AFFINE,
+                            "batched PSA with traceback: 1,000,000 pairs of 250 bp per GPU, reads in the 2-bit wire format"),
     "batch10k_trace": ("batch", (2_000, 10_000), True, AFFINE, "batched PSA with traceback: 2,000 pairs of 10 kbp per GPU"),
     "batch10k_strong": ("batch_strong", (40_000, 10_000), False, AFFINE,
                         "batched PSA, FIXED job: 40,000 synthetic 10 kbp pairs sharded round-robin over all GPUs, results gathered on rank 0"),
@@ -100,7 +104,7 @@ WORKLOADS = {
 SUITE_NGPU = ["batch10k_strong", "batch250_strong", "pair100k_bands", "pair400k_bands"]
 # (the fixed jobs of the N-GPU suite also run on one GPU: the first point of their strong-scaling curves)
 SUITE_1GPU = ["pair100k_trace", "pair200k_trace", "batch250", "batch250_linear", "batch10k", "batch10k_linear",
-              "batch250_trace", "batch10k_trace", "msa16x50k"] + SUITE_NGPU
+              "batch250_trace", "batch10k_trace", "batch250_2bit", "batch250_trace_2bit", "msa16x50k"] + SUITE_NGPU
 
 
 def peaks():
@@ -661,7 +665,11 @@ def wl_batch(ctx, name, steps):
     npairs = a.shape[0]
     # inputs and outputs live in page-locked host memory (tsta_host_alloc), as a caller that
     # streams batches would keep them
-    pins = [api.pinned_copy(v) for v in batch_arrays(a, b)]
+    bits2 = name.endswith("_2bit")
+    arrs = list(batch_arrays(a, b))
+    if bits2:            # the wire format: four bases to a byte (packed once, outside the timed region, like a 2-bit read store)
+        arrs[0], arrs[3] = api.pack_2bit(arrs[0]), api.pack_2bit(arrs[3])
+    pins = [api.pinned_copy(v) for v in arrs]
     s0, o0, l0, s1, o1, l1 = [p.array for p in pins]
     outs = [api.PinnedArray(npairs, np.int32), api.PinnedArray(npairs, np.int32)]
     if trace:
@@ -675,7 +683,7 @@ def wl_batch(ctx, name, steps):
 
     def one_step():
         nonlocal gathered
-        r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, out=out, packed=trace, **prm)
+        r = api.psa_batch_arrays(s0, o0, l0, s1, o1, l1, trace=trace, out=out, packed=trace, bits2=bits2, **prm)
         if strong and world > 1:
             # the job ends when rank 0 holds every pair's result: ONE all_gather of (maxsorce, corner) per step
             mine = torch.from_numpy(np.stack([r.maxsorce, r.corner])).cuda()

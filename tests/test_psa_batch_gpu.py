@@ -109,3 +109,23 @@ def test_packed_moves_equal_byte_moves(gpu, chunks, monkeypatch):
         assert rp.output_bytes(k) == rb.output_bytes(k), k
         if k % 7 == 0:
             assert rp.output_bytes(k) == ob.psa(x, y).output_bytes(), k
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_2bit_wire_format_equals_byte_reads(gpu, chunks, monkeypatch):
+    """tsta_psa_batch_2bit (reads four bases to a byte over PCIe, expanded on the device; chunk boundaries fall inside
+    bytes) against the byte form and the oracle, score-only and traced, ragged lengths."""
+    monkeypatch.setenv("TSTA_BATCH_CHUNKS", str(chunks))
+    pairs = _mixed_pairs(500, 23, [1, 2, 3, 5, 30, 99, 127, 128, 129, 250, 255, 256, 257, 301, 700])
+    for trace in (False, True):
+        rb = gpu.psa_batch(pairs, trace=trace, packed=trace)
+        r2 = gpu.psa_batch(pairs, trace=trace, bits2=True)
+        assert (rb.maxsorce == r2.maxsorce).all() and (rb.corner == r2.corner).all()
+        for k, (x, y) in enumerate(pairs):
+            if trace:
+                assert r2.output_bytes(k) == rb.output_bytes(k), k
+            if k % 9 == 0:
+                o = ob.psa(x, y)
+                assert (r2.maxsorce[k], r2.corner[k]) == (o.maxsorce, o.corner), k
+                if trace:
+                    assert r2.output_bytes(k) == o.output_bytes(), k

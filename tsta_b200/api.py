@@ -340,9 +340,10 @@ class BatchResult:
         return b">1\n" + a + b"\n>2\n" + b
 
 
-def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False, packed=False) -> BatchResult:
+def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False, packed=False, bits2=False) -> BatchResult:
     """Many independent pairs through tsta_psa_batch.  `pairs` is a list of (x, y) byte strings
-    in any order; each pair is swapped like psa/psa.c:194-199."""
+    in any order; each pair is swapped like psa/psa.c:194-199.  bits2: ship the (ACGT) reads in the
+    2-bit wire format (tsta_psa_batch_2bit)."""
     ordered = [order_pair(x, y) for x, y in pairs]
     swapped = np.array([len(y) > len(x) for x, y in pairs], dtype=bool)
     npairs = len(ordered)
@@ -355,8 +356,10 @@ def psa_batch(pairs, M=2, X=-5, E=-2, O=-4, trace=False, packed=False) -> BatchR
         off1[1:] = np.cumsum(len1[:-1], dtype=np.int64)
     seqs0 = b"".join(a for a, _ in ordered) or b"\0"
     seqs1 = b"".join(b for _, b in ordered) or b"\0"
+    if bits2:
+        seqs0, seqs1 = pack_2bit(seqs0), pack_2bit(seqs1)
     return psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M, X, E, O, trace,
-                            pairs=ordered, swapped=swapped, packed=packed)
+                            pairs=ordered, swapped=swapped, packed=packed, bits2=bits2)
 
 
 def psa_batch_arrays(seqs0, off0, len0, seqs1, off1, len1, M=2, X=-5, E=-2, O=-4, trace=False,

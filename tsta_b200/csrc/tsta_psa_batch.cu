@@ -5,6 +5,7 @@
 // exactly what tsta_psa_align computes; pairs are independent, so persistent warps pull
 // whole pairs from a ticket and there is no inter-warp dependency.
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -155,22 +156,57 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     if (want_trace && (!ops || !ops_off || !alen)) return set_error(TSTA_EINVAL, "traceback requested without ops/ops_off/alen");
     if (int rc = ensure_device()) return rc;
 
+    // One pass over the pairs, in 64 blocks spread over a few host threads (a 1M-pair batch spends 15 ms in its
+    // kernels; three serial passes over 1M descriptors were 4 ms of the call): validation, the extents every chunk
+    // of the upload needs, totals.  Chunk boundaries are block boundaries (power-of-two chunk counts).
+    constexpr int kBlocks = 64;
+    struct BlockScan { int64_t lo0, hi0, lo1, hi1, max0, max1, ops_lo, ops_hi, bad; double cells; };
+    BlockScan bs[kBlocks];
+    auto scan_block = [&](int b) {
+        BlockScan r{INT64_MAX, 0, INT64_MAX, 0, 0, 0, INT64_MAX, 0, -1, 0.0};
+        const int64_t k0 = npairs * b / kBlocks, k1 = npairs * (b + 1) / kBlocks;
+        for (int64_t k = k0; k < k1; k++) {
+            const int64_t a = len0[k], c = len1[k], o0 = off0[k], o1 = off1[k];
+            bool bad = a < c || c < 0 || o0 < 0 || o1 < 0 || a + c > 4000000;
+            r.lo0 = std::min(r.lo0, o0); r.hi0 = std::max(r.hi0, o0 + a);
+            r.lo1 = std::min(r.lo1, o1); r.hi1 = std::max(r.hi1, o1 + c);
+            r.max0 = std::max(r.max0, a); r.max1 = std::max(r.max1, c);
+            r.cells += (double)a * (double)c;
+            if (want_trace) {
+                const int64_t oo = ops_off[k];
+                bad = bad || oo < 0 || (pack2 && (oo & 3));
+                r.ops_lo = std::min(r.ops_lo, oo); r.ops_hi = std::max(r.ops_hi, oo + a + c);
+            }
+            if (bad && r.bad < 0) r.bad = k;
+        }
+        bs[b] = r;
+    };
+    {
+        const int nthreads = npairs >= 200000 ? 4 : 1;
+        if (nthreads == 1) for (int b = 0; b < kBlocks; b++) scan_block(b);
+        else {
+            std::thread th[3];
+            for (int t = 1; t < nthreads; t++)
+                th[t - 1] = std::thread([&, t] { for (int b = t; b < kBlocks; b += nthreads) scan_block(b); });
+            for (int b = 0; b < kBlocks; b += nthreads) scan_block(b);
+            for (int t = 1; t < nthreads; t++) th[t - 1].join();
+        }
+    }
     int64_t tot0 = 0, tot1 = 0, max0 = 0, max1 = 0, ops_total = 0;
     double cells = 0.0;
-    for (int64_t k = 0; k < npairs; k++) {
-        if (len0[k] < len1[k] || len1[k] < 0 || off0[k] < 0 || off1[k] < 0)
-            return set_error(TSTA_EINVAL, "pair %lld: need len0 >= len1 >= 0 (the caller swaps, psa.c:194-199)", (long long)k);
-        if ((int64_t)len0[k] + len1[k] > 4000000) return set_error(TSTA_EINVAL, "pair %lld too long", (long long)k);
-        tot0 = std::max<int64_t>(tot0, off0[k] + len0[k]);
-        tot1 = std::max<int64_t>(tot1, off1[k] + len1[k]);
-        max0 = std::max<int64_t>(max0, len0[k]);
-        max1 = std::max<int64_t>(max1, len1[k]);
-        cells += (double)len0[k] * (double)len1[k];
-        if (want_trace) {
+    for (int b = 0; b < kBlocks; b++) {
+        if (bs[b].bad >= 0) {
+            const int64_t k = bs[b].bad;
+            if (len0[k] < len1[k] || len1[k] < 0 || off0[k] < 0 || off1[k] < 0)
+                return set_error(TSTA_EINVAL, "pair %lld: need len0 >= len1 >= 0 (the caller swaps, psa.c:194-199)", (long long)k);
+            if ((int64_t)len0[k] + len1[k] > 4000000) return set_error(TSTA_EINVAL, "pair %lld too long", (long long)k);
             if (ops_off[k] < 0) return set_error(TSTA_EINVAL, "pair %lld: negative ops_off", (long long)k);
-            if (pack2 && (ops_off[k] & 3)) return set_error(TSTA_EINVAL, "pair %lld: packed moves need ops_off to be a multiple of 4", (long long)k);
-            ops_total = std::max<int64_t>(ops_total, ops_off[k] + len0[k] + len1[k]);
+            return set_error(TSTA_EINVAL, "pair %lld: packed moves need ops_off to be a multiple of 4", (long long)k);
         }
+        tot0 = std::max(tot0, bs[b].hi0); tot1 = std::max(tot1, bs[b].hi1);
+        max0 = std::max(max0, bs[b].max0); max1 = std::max(max1, bs[b].max1);
+        ops_total = std::max(ops_total, bs[b].ops_hi);
+        cells += bs[b].cells;
     }
     const int S = want_trace ? 2 : 1;
 
@@ -219,29 +255,27 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     if (cells > 1000.0 * (double)(tot0 + tot1)) nch = 1;
     if (const char* e = getenv("TSTA_BATCH_CHUNKS")) nch = std::max(1, std::min(kMaxChunks, atoi(e)));
     nch = (int)std::min<int64_t>(nch, npairs);
+    while (nch & (nch - 1)) nch &= nch - 1;          // a power of two: chunk boundaries are block boundaries of the scan above
     int64_t kb[kMaxChunks + 1];
-    for (int c = 0; c <= nch; c++) kb[c] = npairs * c / nch;
+    int64_t ext[kMaxChunks][4] = {};                  // 2-bit wire format: base extents of each chunk's two streams
+    for (int c = 0; c <= nch; c++) kb[c] = npairs * (c * (kBlocks / nch)) / kBlocks;
     unsigned* d_present = reinterpret_cast<unsigned*>(d_ctl + 16);
     TSTA_CUDA_TRY(cudaMemsetAsync(d_present, 0, 8 * kMaxChunks * sizeof(unsigned), g_ctx.cp));
     for (int c = 0; c < nch; c++) {
         const int64_t a0 = kb[c], a1 = kb[c + 1];
         int64_t lo0 = INT64_MAX, hi0 = 0, lo1 = INT64_MAX, hi1 = 0;
-        for (int64_t k = a0; k < a1; k++) {
-            lo0 = std::min<int64_t>(lo0, off0[k]); hi0 = std::max<int64_t>(hi0, off0[k] + len0[k]);
-            lo1 = std::min<int64_t>(lo1, off1[k]); hi1 = std::max<int64_t>(hi1, off1[k] + len1[k]);
+        for (int b = c * (kBlocks / nch); b < (c + 1) * (kBlocks / nch); b++) {
+            lo0 = std::min(lo0, bs[b].lo0); hi0 = std::max(hi0, bs[b].hi0);
+            lo1 = std::min(lo1, bs[b].lo1); hi1 = std::max(hi1, bs[b].hi1);
         }
         cudaStream_t cp = g_ctx.cp;
         if (bits2) {
             // a quarter of the bytes cross PCIe; the device expands them to the byte reads (0.1 ms per 500 MB)
-            if (hi0 > lo0) {
-                TSTA_CUDA_TRY(cudaMemcpyAsync(d_p0 + (lo0 >> 2), seqs0 + (lo0 >> 2), (size_t)(((hi0 + 3) >> 2) - (lo0 >> 2)), cudaMemcpyHostToDevice, cp));
-                unpack_2bit_kernel<<<sms * 8, 256, 0, cp>>>(d_p0, d_s0, lo0, hi0);
-            }
-            if (hi1 > lo1) {
-                TSTA_CUDA_TRY(cudaMemcpyAsync(d_p1 + (lo1 >> 2), seqs1 + (lo1 >> 2), (size_t)(((hi1 + 3) >> 2) - (lo1 >> 2)), cudaMemcpyHostToDevice, cp));
-                unpack_2bit_kernel<<<sms * 8, 256, 0, cp>>>(d_p1, d_s1, lo1, hi1);
-            }
-            TSTA_CUDA_TRY(cudaGetLastError());
+            // (the expansion runs on the kernel stream, in front of the chunk's fill: behind a persistent fill kernel on
+            // another stream it would wait for SM slots)
+            if (hi0 > lo0) TSTA_CUDA_TRY(cudaMemcpyAsync(d_p0 + (lo0 >> 2), seqs0 + (lo0 >> 2), (size_t)(((hi0 + 3) >> 2) - (lo0 >> 2)), cudaMemcpyHostToDevice, cp));
+            if (hi1 > lo1) TSTA_CUDA_TRY(cudaMemcpyAsync(d_p1 + (lo1 >> 2), seqs1 + (lo1 >> 2), (size_t)(((hi1 + 3) >> 2) - (lo1 >> 2)), cudaMemcpyHostToDevice, cp));
+            ext[c][0] = lo0; ext[c][1] = hi0; ext[c][2] = lo1; ext[c][3] = hi1;
         } else {
         if (hi0 > lo0) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0 + lo0, seqs0 + lo0, (size_t)(hi0 - lo0), cudaMemcpyHostToDevice, cp));
         if (hi1 > lo1) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1 + lo1, seqs1 + lo1, (size_t)(hi1 - lo1), cudaMemcpyHostToDevice, cp));
@@ -250,9 +284,15 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1 + a0, off1 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0 + a0, len0 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));
         TSTA_CUDA_TRY(cudaMemcpyAsync(d_len1 + a0, len1 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));
-        if (hi0 > lo0) TSTA_CUDA_TRY(launch_byte_presence(d_s0 + lo0, hi0 - lo0, d_present + 8 * c, sms * 4, cp));
-        if (hi1 > lo1) TSTA_CUDA_TRY(launch_byte_presence(d_s1 + lo1, hi1 - lo1, d_present + 8 * c, sms * 4, cp));
-        TSTA_CUDA_TRY(cudaMemcpyAsync(g_ctx.h_present + 8 * c, d_present + 8 * c, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, cp));
+        if (bits2) {          // the alphabet is known: A C G T
+            unsigned* hp = reinterpret_cast<unsigned*>(g_ctx.h_present + 8 * c);
+            for (int w = 0; w < 8; w++) hp[w] = 0;
+            for (const char ch : {'A', 'C', 'G', 'T'}) hp[(unsigned char)ch >> 5] |= 1u << ((unsigned char)ch & 31);
+        } else {
+            if (hi0 > lo0) TSTA_CUDA_TRY(launch_byte_presence(d_s0 + lo0, hi0 - lo0, d_present + 8 * c, sms * 4, cp));
+            if (hi1 > lo1) TSTA_CUDA_TRY(launch_byte_presence(d_s1 + lo1, hi1 - lo1, d_present + 8 * c, sms * 4, cp));
+            TSTA_CUDA_TRY(cudaMemcpyAsync(g_ctx.h_present + 8 * c, d_present + 8 * c, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, cp));
+        }
         TSTA_CUDA_TRY(cudaEventRecord(g_ctx.evc[c], cp));
     }
 
@@ -314,8 +354,13 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     };
     for (int c = 0; c < nch; c++) {
         // ---- this chunk's alphabet decides its kernels -------------------------------------------
-        TSTA_CUDA_TRY(cudaEventSynchronize(g_ctx.evc[c]));
+        if (!bits2) TSTA_CUDA_TRY(cudaEventSynchronize(g_ctx.evc[c]));       // (its alphabet has to be read on the host)
         TSTA_CUDA_TRY(cudaStreamWaitEvent(g.st, g_ctx.evc[c], 0));
+        if (bits2) {
+            if (ext[c][1] > ext[c][0]) unpack_2bit_kernel<<<sms * 8, 256, 0, g.st>>>(d_p0, d_s0, ext[c][0], ext[c][1]);
+            if (ext[c][3] > ext[c][2]) unpack_2bit_kernel<<<sms * 8, 256, 0, g.st>>>(d_p1, d_s1, ext[c][2], ext[c][3]);
+            TSTA_CUDA_TRY(cudaGetLastError());
+        }
         const unsigned* present = reinterpret_cast<const unsigned*>(g_ctx.h_present + 8 * c);
         const int K = build_lut(present, a.sc.lut);
         const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
@@ -411,9 +456,9 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         // ---- results of a finished chunk travel back while the next one is computed --------------
         if (want_trace && nch > 1) {
             int64_t lo = INT64_MAX, hi = 0;
-            for (int64_t k = kb[c]; k < kend; k++) {
-                lo = std::min<int64_t>(lo, ops_off[k]);
-                hi = std::max<int64_t>(hi, ops_off[k] + len0[k] + len1[k]);
+            for (int b = c * (kBlocks / nch); b < (c + 1) * (kBlocks / nch); b++) {
+                lo = std::min(lo, bs[b].ops_lo);
+                hi = std::max(hi, bs[b].ops_hi);
             }
             if (last_done) TSTA_CUDA_TRY(cudaStreamWaitEvent(g_ctx.dh, last_done, 0));
             if (pack2) { lo >>= 2; hi = (hi + 3) >> 2; }      // (slots start at multiples of four moves: chunks do not share a byte)
