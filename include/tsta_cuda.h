@@ -223,7 +223,7 @@ int  tsta_poa_graph_update(tsta_poa* ctx, int nnodes, int n_narrow, const tsta_p
  * order (it crosses PCIe as 3 bytes per row; that, the changed records and the read are all that is copied).  Row descriptors, the
  * predecessor table in row indices and the spill slots are built on the device; H(r,-1) is computed
  * by the fill itself, so hneg1 may be NULL unless the read runs on the skewed kernel (it contains
- * 'N', or L is not a multiple of the strip width), in which case it is required. */
+ * 'N'), in which case it is required. */
 int  tsta_poa_fill_resident(tsta_poa* ctx, const tsta_params* p, int L, int nrows, const int32_t* sort,
                             const int32_t* hneg1, const char* read, int len, int32_t* lastsorce, float* kernel_ms);
 /* Bytes of graph tables and reads this context has copied to the device so far (TSTA_MSA_TIMING). */

@@ -149,7 +149,7 @@ def test_quirk_rows_n_columns_and_late_heads(gpu, seed):
     poa.close()
 
 
-@pytest.mark.parametrize("kernel,C", [("rows", 4), ("rows", 2), ("skew", 4), ("skew", 2)])
+@pytest.mark.parametrize("kernel,C", [("rows", 4), ("rows", 3), ("rows", 2), ("skew", 4), ("skew", 2)])
 def test_both_fill_kernels_late_heads_dense_graphs(gpu, monkeypatch, kernel, C):
     """The row-synchronous kernel (poa_rows.cuh: F by scan, register forwarding, serial pass for late heads in
     the band that owns column L) and the skewed kernel (poa_fill.cuh), each strip width, on reads WITHOUT 'N'
@@ -158,9 +158,10 @@ def test_both_fill_kernels_late_heads_dense_graphs(gpu, monkeypatch, kernel, C):
     monkeypatch.setenv("TSTA_POA_C", str(C))
     rnd = random.Random(4242 + C)
     poa = gpu.Poa()
-    for k in range(6):
+    for k in range(10):
         M, X, E, O = rnd.choice([(2, -5, -2, -4), (1, -1, -1, 0), (2, -5, -2, 0), (1, -3, -1, -5), (5, -4, 0, -3)])
-        nrows, ln, L = rnd.choice([90, 400, 1100]), rnd.choice([5, 131, 260, 900]), rnd.choice([64, 128, 640])
+        # (L anywhere inside a lane's strip: 70, 99, 130 are not multiples of any strip width)
+        nrows, ln, L = rnd.choice([90, 400, 1100]), rnd.choice([5, 131, 260, 900]), rnd.choice([64, 128, 640, 70, 99, 130])
         read = synth.random_read(ln, 900 + 13 * k + C)
         g = random_dag(nrows, rnd, E, O, far=rnd.choice([0.0, 0.2]), heads=rnd.choice([0.0, 0.06]),
                        maxin=rnd.choice([3, 6, 11]), backbone=read)

@@ -161,7 +161,7 @@ template <int C, bool QUIRKS>
 __device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], const uint8_t (&rc)[C], const bool (&isL)[C],
                                         const bool (&isLm1)[C], const int b, const int MS, const int XS, const int ES,
                                         const int ES64, const int ES128, const int OES, const int Fadj, int& Fk, int& Hleft,
-                                        int (&ko)[2 * C], uint32_t (&tw)[C / 2])
+                                        int (&ko)[2 * C], uint32_t (&tw)[(C + 1) / 2])
 {
     uint32_t lo8[C], hi8[C];
 #pragma unroll
@@ -197,6 +197,7 @@ __device__ __forceinline__ void poa_row(const int (&kd)[C], const int (&ke)[C], 
 #pragma unroll
     for (int c = 0; c + 1 < C; c += 2)
         tw[c / 2] = __byte_perm(__byte_perm(lo8[c], lo8[c + 1], 0x0040), __byte_perm(hi8[c], hi8[c + 1], 0x0040), 0x5140);
+    if constexpr (C & 1) tw[C / 2] = __byte_perm(lo8[C - 1], hi8[C - 1], 0x0040);
 }
 
 template <int C>

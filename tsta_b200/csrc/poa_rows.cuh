@@ -35,7 +35,15 @@ namespace tsta {
 constexpr int kPoaGroup = 8;                 // rows per boundary import group
 constexpr int kPoaRowsDescRing = 128;
 constexpr int kPoaPlane = 33 * 16;           // one 16-byte unit per lane (+ the band's left edge in unit 0)
-template <int C> constexpr int kPoaRowsSlotBytes = (C / 2) * kPoaPlane;
+// slot of one row: plane 0 = 16-byte units with columns 0, 1; plane 1 = columns 2, 3 (16-byte units) or column 2 alone
+// (8-byte units, strip width 3); slots stay 16-byte aligned
+template <int C> constexpr int kPoaRowsSlotBytes = C == 2 ? kPoaPlane : (C == 3 ? kPoaPlane + 33 * 8 + 8 : 2 * kPoaPlane);
+// byte offset, inside a slot, of the LAST column's H key of unit u (u = lane + 1: the lane's own, u = lane: the previous
+// lane's, u = 0: the band's left edge)
+template <int C> __device__ __forceinline__ uint32_t poa_rows_lasth(uint32_t u)
+{
+    return C == 2 ? u * 16 + 8 : (C == 3 ? kPoaPlane + u * 8 : kPoaPlane + u * 16 + 8);
+}
 
 // History: slot [row & 31] (+ the three constant slots) holds the keys of a row as C/2 planes of 16-byte units,
 // unit [lane + 1] of plane q = (H, Eout) keys of the lane's columns 2q and 2q+1.  All lanes read the same slot at
@@ -75,7 +83,20 @@ __device__ __forceinline__ void poa_rows_lds(uint32_t slot_addr, uint32_t lane16
         const int4 v23 = lds_s4(own + 16 + kPoaPlane);
         h[2] = v23.x; e[2] = v23.y; h[3] = v23.z; e[3] = v23.w;
     }
-    Hd0 = lds_s32(own + (C / 2 - 1) * kPoaPlane + 8);
+    if constexpr (C == 3) {
+        const uint2 v2 = lds_u2(slot_addr + kPoaPlane + (lane16 >> 1) + 8);
+        h[2] = (int)v2.x; e[2] = (int)v2.y;
+    }
+    Hd0 = lds_s32(slot_addr + poa_rows_lasth<C>(lane16 >> 4));
+}
+
+// the keys of one row into its slot: k[2c] = H key, k[2c+1] = E key of column c
+template <int C>
+__device__ __forceinline__ void poa_rows_sts(uint32_t slot_addr, uint32_t lane16, const int (&k)[2 * C])
+{
+    sts_s4(slot_addr + lane16 + 16, k[0], k[1], k[2], k[3]);
+    if constexpr (C == 4) sts_s4(slot_addr + kPoaPlane + lane16 + 16, k[4], k[5], k[6], k[7]);
+    if constexpr (C == 3) sts_u2(slot_addr + kPoaPlane + (lane16 >> 1) + 8, (uint32_t)k[4], (uint32_t)k[5]);
 }
 
 // One band (32*C columns, one warp) over all rows.  LAST: the band that holds column len-1 also writes lastsorce.
@@ -131,15 +152,16 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
     constexpr uint32_t kDescOff = (uint32_t)offsetof(PoaRowsSmem<C>, desc);
     constexpr uint32_t kBringOff = (uint32_t)offsetof(PoaRowsSmem<C>, bring);
     const uint32_t lane16 = (uint32_t)lane * 16u;
-    const uint32_t hist_lane = base + lane16;                   // + slot * kSlotB: unit [lane] of plane 0
     const int cin_dec = D1 * lane;                              // the band's left-edge F reaches this lane's first column
 
     // ---- constant history slots (as in poa_fill_kernel; c-t-simd.c:176-188 for the virtual rows) ----
     {
         const uint32_t none = base + kPoaSlotNone * kSlotB;
-        sts_s4(none + lane16 + 16, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
-        if constexpr (C == 4) sts_s4(none + kPoaPlane + lane16 + 16, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
-        if (lane == 0) sts_s4(none + (C / 2 - 1) * kPoaPlane, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin, kPoaKeyMin);
+        int kmin[2 * C];
+#pragma unroll
+        for (int q = 0; q < 2 * C; q++) kmin[q] = kPoaKeyMin;
+        poa_rows_sts<C>(none, lane16, kmin);
+        if (lane == 0) sts_u32(none + poa_rows_lasth<C>(0), (uint32_t)kPoaKeyMin);
 #pragma unroll
         for (int v = 0; v < 2; v++) {
             const bool late = v == 1;
@@ -153,11 +175,10 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                 k[2 * c + 1] = (Hp + OE) * 256 + 64;
             }
             const uint32_t slot = base + (kPoaSlotHead + v) * kSlotB;
-            sts_s4(slot + lane16 + 16, k[0], k[1], k[2], k[3]);
-            if constexpr (C == 4) sts_s4(slot + kPoaPlane + lane16 + 16, k[4], k[5], k[6], k[7]);
+            poa_rows_sts<C>(slot, lane16, k);
             if (lane == 0) {   // left edge: diagonal input of column j0
                 const int Hd0 = (late && j0 <= L - 1) ? j0 * E : (j0 == 0 ? 0 : O + j0 * E);
-                sts_s4(slot + (C / 2 - 1) * kPoaPlane, 0, 0, Hd0 * 256, 0);
+                sts_u32(slot + poa_rows_lasth<C>(0), (uint32_t)(Hd0 * 256));
             }
         }
     }
@@ -179,7 +200,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
     for (int q = 0; q < 2 * C; q++) ko[q] = kPoaKeyMin;
     int fwdH = kPoaKeyMin;               // H(r-1, j0-1): the previous lane's last H of the row just finished
     int edge_prev = kPoaKeyMin;          // EDGE0: H(r-1, -1) as a key
-    constexpr uint32_t kEdgeOff = (C / 2 - 1) * kPoaPlane + 8;   // the left-edge word of a history slot
+    const uint32_t kEdgeOff = poa_rows_lasth<C>(0);              // the left-edge word of a history slot
     const int OEk = OES - 64;            // (O+E)*256
     uint4 dsc_next = lds_u4(base + kDescOff);
     char* trow = reinterpret_cast<char*>(a.trace + j0);   // this lane's cells of row r
@@ -190,7 +211,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
     // vertical key.  F by scan (poa_rows.cuh header), then every column; history, trace, right edge.
     auto finish_row = [&](const int r, const int (&hk)[C], const int (&ke)[C], const int Hedge, const int Fin,
                           const unsigned flags, const unsigned spill_row) {
-        uint32_t tw[C / 2];
+        uint32_t tw[(C + 1) / 2];
         int Fout;                                               // Fg key entering the next lane's first column
         // this row's output addresses; the running pointers move on NOW, a row away from the stores that use them
         // (an increment right behind its store waits ~16 cycles for the store to release the address registers)
@@ -261,20 +282,25 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
 #pragma unroll
             for (int c = 0; c + 1 < C; c += 2)
                 tw[c / 2] = __byte_perm(__byte_perm(lo8[c], lo8[c + 1], 0x0040), __byte_perm(hi8[c], hi8[c + 1], 0x0040), 0x5140);
+            if constexpr (C & 1) tw[C / 2] = __byte_perm(lo8[C - 1], hi8[C - 1], 0x0040);
         }
         // ---- outputs: history slot, spill, trace, last column, right edge ----
-        const uint32_t own = hist_lane + ((uint32_t)r & (kPoaHist - 1)) * kSlotB + 16;
-        sts_s4(own, ko[0], ko[1], ko[2], ko[3]);
-        if constexpr (C == 4) sts_s4(own + kPoaPlane, ko[4], ko[5], ko[6], ko[7]);
-        sts_u32_if(own + (C / 2 - 1) * kPoaPlane - 8, (uint32_t)Hedge, lane == 0);     // lane 0: the band's left edge (unit 0)
+        const uint32_t slot = base + ((uint32_t)r & (kPoaHist - 1)) * kSlotB;
+        poa_rows_sts<C>(slot, lane16, ko);
+        sts_u32_if(slot + poa_rows_lasth<C>(0), (uint32_t)Hedge, lane == 0);     // lane 0: the band's left edge (unit 0)
         if (flags & kPoaKeep) {    // a successor further away than the history ring will read it back
             if constexpr (EDGE0) a.edge_spill[spill_row] = Hedge;         // (every lane, the same value)
             int2* g = a.HE + (long long)spill_row * a.stride + j0;
-            *reinterpret_cast<int4*>(g) = make_int4(ko[0], ko[1], ko[2], ko[3]);
-            if constexpr (C == 4) *reinterpret_cast<int4*>(g + 2) = make_int4(ko[4], ko[5], ko[6], ko[7]);
+#pragma unroll
+            for (int c = 0; c < C; c++) g[c] = make_int2(ko[2 * c], ko[2 * c + 1]);
         }
         if constexpr (C == 4) __stcs(reinterpret_cast<uint2*>(tcur), make_uint2(tw[0], tw[1]));
-        else __stcs(reinterpret_cast<uint32_t*>(tcur), tw[0]);
+        else if constexpr (C == 2) __stcs(reinterpret_cast<uint32_t*>(tcur), tw[0]);
+        else {   // strip width 3: six bytes per lane, 2-byte aligned
+            __stcs(reinterpret_cast<unsigned short*>(tcur), (unsigned short)tw[0]);
+            __stcs(reinterpret_cast<unsigned short*>(tcur) + 1, (unsigned short)(tw[0] >> 16));
+            __stcs(reinterpret_cast<unsigned short*>(tcur) + 2, (unsigned short)tw[1]);
+        }
         if constexpr (LAST) {
             if (owns_last) {
                 int hl = ko[0];
@@ -398,11 +424,10 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
                         } else {
                             if constexpr (EDGE0) emax = max(emax, __ldcg(a.edge_spill + __ldg(&a.desc[p].w)));
                             const int2* src = a.HE + (long long)__ldg(&a.desc[p].w) * a.stride + j0;
-                            const int4 v01 = __ldcg(reinterpret_cast<const int4*>(src));
-                            ph[0] = v01.x; pe[0] = v01.y; ph[1] = v01.z; pe[1] = v01.w;
-                            if constexpr (C == 4) {
-                                const int4 v23 = __ldcg(reinterpret_cast<const int4*>(src + 2));
-                                ph[2] = v23.x; pe[2] = v23.y; ph[3] = v23.z; pe[3] = v23.w;
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                const int2 v = __ldcg(src + c);
+                                ph[c] = v.x; pe[c] = v.y;
                             }
                             if (lane > 0) Hd0 = __ldcg(src - 1).x;
                             else if (band > 0) Hd0 = (int)(unsigned)ld_relaxed_u64(bnd_in + p);
@@ -429,7 +454,7 @@ __device__ __forceinline__ void poa_rows_sweep(const PoaFillArgs& a, PoaRowsSmem
 template <int C>
 __global__ void __launch_bounds__(32) poa_rows_kernel(const __grid_constant__ PoaFillArgs a)
 {
-    static_assert(C == 2 || C == 4, "strip widths of the POA fill");
+    static_assert(C >= 2 && C <= 4, "strip widths of the row-synchronous POA fill");
     extern __shared__ __align__(16) unsigned char poa_smem_raw[];
     PoaRowsSmem<C>& sm = *reinterpret_cast<PoaRowsSmem<C>*>(poa_smem_raw);
     const int lane = threadIdx.x;

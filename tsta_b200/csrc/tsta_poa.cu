@@ -90,15 +90,16 @@ static int poa_grow_keep(DevBuf& b, size_t bytes, size_t used, cudaStream_t st)
 // Strip width and kernel for this read (see tsta_poa_fill).
 static void poa_choose(tsta_poa* p, int L, int nrows, const char* read, int len)
 {
-    // Strip width.  The kernels are templates (2 or 4 columns per lane); 4 is the default: the per-row cost barely
-    // shrinks with the strip, so twice the bands only add start-up.
-    p->C = 4;
-    if (const char* e = getenv("TSTA_POA_C")) { const int c = atoi(e); if (c == 2 || c == 4) p->C = c; }
     // Kernel.  poa_rows_kernel (row-synchronous, F by a max-plus scan; poa_rows.cuh) is the default; the skewed
-    // poa_fill_kernel keeps the reads with 'N' columns (quirk Q3 is a second horizontal chain) and strip widths
-    // that do not divide L (the late-head re-base must fall on a lane's first column).  TSTA_POA_KERNEL=skew forces it.
-    p->rows_kernel = (L % p->C == 0) && memchr(read, 'N', (size_t)len) == nullptr;
+    // poa_fill_kernel keeps the reads with 'N' columns (quirk Q3 is a second horizontal chain).
+    // TSTA_POA_KERNEL=skew forces it.
+    p->rows_kernel = memchr(read, 'N', (size_t)len) == nullptr;
     if (const char* e = getenv("TSTA_POA_KERNEL")) { if (!strcmp(e, "skew")) p->rows_kernel = false; }
+    // Strip width (columns per lane; the kernels are templates).  Rows kernel: 3 -- a 50 kbp read is 521 bands, one
+    // per SM sub-partition (592), and the per-row time falls with the strip (4: 526 cycles, 3: ~470, 2: 405 alone
+    // but 498 once 782 bands share sub-partitions); skewed kernel: 4 (2 also compiled).  TSTA_POA_C overrides.
+    p->C = p->rows_kernel ? 3 : 4;
+    if (const char* e = getenv("TSTA_POA_C")) { const int c = atoi(e); if (c == 2 || c == 4 || (c == 3 && p->rows_kernel)) p->C = c; }
     const int band_cols = 32 * p->C;
     p->nbands = (len + band_cols - 1) / band_cols;
     p->stride = (long long)p->nbands * band_cols;
@@ -157,6 +158,7 @@ static int poa_launch(tsta_poa* p, const tsta_params* prm, int L, int nrows, siz
         (p->rows_kernel ? p->n_fill_rows : p->n_fill_skew)++;
         if (p->rows_kernel) {
             if (p->C == 2) poa_rows_kernel<2><<<p->nbands, 32, sizeof(PoaRowsSmem<2>), p->stream>>>(a);
+            else if (p->C == 3) poa_rows_kernel<3><<<p->nbands, 32, sizeof(PoaRowsSmem<3>), p->stream>>>(a);
             else poa_rows_kernel<4><<<p->nbands, 32, sizeof(PoaRowsSmem<4>), p->stream>>>(a);
         } else if (p->C == 2) poa_fill_kernel<2><<<p->nbands, 32, sizeof(PoaSmemC<2>), p->stream>>>(a);
         else poa_fill_kernel<4><<<p->nbands, 32, sizeof(PoaSmemC<4>), p->stream>>>(a);
@@ -192,6 +194,8 @@ int tsta_poa_create(tsta_poa** out)
         e = cudaFuncSetAttribute(poa_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaRowsSmem<4>));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(poa_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaRowsSmem<2>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(poa_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoaRowsSmem<3>));
     if (e != cudaSuccess) {
         poa_free(p);
         return set_error(TSTA_ECUDA, "POA context creation failed: %s", cudaGetErrorString(e));
@@ -365,7 +369,7 @@ int tsta_poa_fill_resident(tsta_poa* p, const tsta_params* prm, int L, int nrows
     const double t0 = poa_now();
     poa_choose(p, L, nrows, read, len);
     if (!p->rows_kernel && !hneg1)
-        return set_error(TSTA_EINVAL, "this read runs on the skewed kernel ('N' columns, or L not a multiple of the strip width): it needs hneg1");
+        return set_error(TSTA_EINVAL, "this read runs on the skewed kernel ('N' columns): it needs hneg1");
     p->fixed8 = true;
     if (int rc = poa_grow(p->d_desc, (size_t)nrows * sizeof(uint4))) return rc;
     if (int rc = poa_grow(p->d_sort, (size_t)nrows * 4)) return rc;

@@ -42,6 +42,7 @@ struct BatchCtx {
     DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs, p0, p1;
     int* h_present = nullptr;   // pinned, 8 words per chunk
     std::vector<cudaEvent_t> ev;   // timing events, two per kernel slice, grown on demand
+    std::vector<size_t> pair_bytes;   // traced batches: bytes of every pair's direction matrix
     void release()
     {
         DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs, &p0, &p1};
@@ -319,6 +320,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     // traceback: direction matrices are large (len1 * ceil(len0/band)*band/2 bytes per pair),
     // so pairs go through in slices that fit a fixed HBM budget
     std::vector<long long> dirs_off;
+    std::vector<size_t>& pair_bytes = g_ctx.pair_bytes;
     uint8_t* d_dirs = nullptr;
     long long* d_dirs_off = nullptr;
     uint8_t* d_ops = nullptr;
@@ -384,8 +386,22 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         const int64_t kend = kb[c + 1];
         size_t slice_target = dirs_budget;   // equal slices: a short last slice would leave most warps idle
         if (want_trace) {
+            // bytes of every pair's direction matrix: one division per pair, on four host threads for large chunks
+            pair_bytes.resize((size_t)npairs);
+            {
+                const int64_t a0 = kb[c], n = kend - kb[c];
+                const int nthreads = n >= 200000 ? 4 : 1;
+                auto part = [&](int t) {
+                    for (int64_t k = a0 + n * t / nthreads; k < a0 + n * (t + 1) / nthreads; k++)
+                        pair_bytes[(size_t)k] = (dirs_bytes(k) + 255) & ~(size_t)255;
+                };
+                std::thread th[3];
+                for (int t = 1; t < nthreads; t++) th[t - 1] = std::thread(part, t);
+                part(0);
+                for (int t = 1; t < nthreads; t++) th[t - 1].join();
+            }
             size_t total = 0;
-            for (int64_t k = kb[c]; k < kend; k++) total += (dirs_bytes(k) + 255) & ~(size_t)255;
+            for (int64_t k = kb[c]; k < kend; k++) total += pair_bytes[(size_t)k];
             const size_t nslices = std::max<size_t>(1, (total + dirs_budget - 1) / std::max<size_t>(dirs_budget, 1));
             slice_target = std::min(dirs_budget, (total + nslices - 1) / nslices + ((size_t)64 << 20));
         }
@@ -397,7 +413,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
             if (want_trace) {
                 k1 = k0;
                 while (k1 < kend) {
-                    const size_t b = (dirs_bytes(k1) + 255) & ~(size_t)255;
+                    const size_t b = pair_bytes[(size_t)k1];
                     if (k1 > k0 && slice_bytes + b > slice_target) break;
                     dirs_off[(size_t)k1] = (long long)slice_bytes;
                     slice_bytes += b;
