@@ -579,6 +579,7 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
     __shared__ int s_ptr[kPoaWinRows + 1];
     __shared__ int s_pred[kPoaWinEdges];
     __shared__ uint8_t s_base[kPoaWinRows], s_read[kPoaWinCols];
+    __shared__ uint8_t s_chain[kPoaWinRows][32];   // s_chain[w][k]: window row reached from window row w by k first-predecessor hops (255: outside)
     __shared__ int s_row, s_col, s_pend, s_n;
     if (threadIdx.x == 0) { s_row = a.start_row; s_col = a.len - 1; s_pend = 0; s_n = 0; }
     __syncthreads();
@@ -608,24 +609,51 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
         for (int u = threadIdx.x; u < ecount; u += kPoaWalkThreads) s_pred[u] = a.pred_row[ebase + u];
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
+        // First-predecessor chains of the window's rows, by doubling (5 rounds): a read that mostly matches the graph
+        // walks diagonally along them even where consecutive path nodes are not consecutive rows.
+        for (int w = threadIdx.x; w < kPoaWinRows; w += kPoaWalkThreads) {
+            const int row = r0 - w;
+            int hop = 255;
+            if (row >= rlo) {
+                const int e = s_ptr[row - rlo] - ebase;
+                const int p0 = e < kPoaWinEdges ? s_pred[e] : -1;
+                if (p0 >= rlo) hop = r0 - p0;
+            }
+            s_chain[w][0] = (uint8_t)w;
+            s_chain[w][1] = (uint8_t)hop;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int half = 1; half < 32; half *= 2) {                  // entries (half, 2 half] from entries (0, half]
+            for (int u = threadIdx.x; u < kPoaWinRows * half; u += kPoaWalkThreads) {
+                const int w = u / half, k = half + 1 + u % half;
+                if (k < 32) {
+                    const int mid = s_chain[w][half];
+                    s_chain[w][k] = mid == 255 ? (uint8_t)255 : s_chain[mid][k - half];
+                }
+            }
+            __syncthreads();
+        }
         if (threadIdx.x < 32) {
             // pend: how this cell was entered (1 = horizontal move, 2 = vertical move, 0 = otherwise);
             // the cell's own bits 14 / 15 then say whether the move is forced to continue.
-            // One warp walks: lane k ASSUMES that the k cells before it were diagonal moves into the row right above
-            // (the usual case along a read that mostly matches the graph) and decodes cell (r-k, c-k); the lanes up to
-            // the first cell that says otherwise are on the path, and the walk resumes from that cell's real successor.
-            // 10-30 steps per pass instead of one, for the same chain of two dependent shared-memory loads.
+            // One warp walks: lane k ASSUMES that the k cells before it were diagonal moves, each into its row's FIRST
+            // predecessor, and decodes the cell it would then stand on; the lanes up to the first cell that says
+            // otherwise are on the path, and the walk resumes from that cell's real successor.  10-30 steps per pass
+            // instead of one, for the same chain of dependent shared-memory loads.
             const int lane = threadIdx.x;
             int r = r0, c = c0, pend = s_pend, n = s_n;
             while (r >= rlo && c >= w0) {
-                const int rr = r - lane, cc = c - lane;
-                const bool in = rr >= rlo && cc >= w0;
+                const int wk = s_chain[r0 - r][lane];               // window row of this lane's cell (255: left the window)
+                const int rr = r0 - wk, cc = c - lane;
+                const bool in = wk != 255 && cc >= w0;
                 uint32_t type = 0;
-                int pj = 0, p = 0, kind = 0;
+                int pj = 0, p = 0, kind = 0, hop = 255;
                 if (in) {
-                    const uint32_t w = win[r0 - rr][cc - w0];
+                    const uint32_t w = win[wk][cc - w0];
                     const int e0 = s_ptr[rr - rlo] - ebase;
-                    const bool match = s_read[cc - w0] == s_base[r0 - rr];
+                    const bool match = s_read[cc - w0] == s_base[wk];
+                    hop = s_chain[wk][1];
                     const int pd = lane == 0 ? pend : 0;                  // lanes > 0 are entered by a diagonal move
                     const bool fF = pd == 1 && cc > 0 && (w & 0x8000u);
                     const bool fE = pd == 2 && rr > 0 && !(w & 0x4000u);
@@ -636,7 +664,8 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
                     p = s_pred[min(e, kPoaWinEdges - 1)];
                     if (type != 1u && e >= kPoaWinEdges) p = a.pred_row[ebase + e];   // (a window with > 2048 edges: never seen)
                 }
-                const bool cont = in && type == 3u && p == rr - 1;        // the next cell IS the one lane + 1 looks at
+                // the next cell IS the one lane + 1 looks at: a diagonal move into the row the chain continues with
+                const bool cont = in && type == 3u && hop != 255 && p == r0 - hop;
                 const unsigned okmask = __ballot_sync(kFullMask, cont);
                 const int d = okmask == 0xffffffffu ? 32 : __ffs((int)~okmask) - 1;   // first lane whose successor is elsewhere
                 if (lane <= d && in) {
@@ -644,17 +673,16 @@ __global__ void __launch_bounds__(kPoaWalkThreads) poa_walk_kernel(const PoaWalk
                     st.row = rr; st.col = cc; st.kind = (uint8_t)kind; st.pred = (uint8_t)(type == 1u ? 0 : pj); st.pad = 0;
                     a.path[n + lane] = st;
                 }
-                if (d == 32) {
-                    r -= 32; c -= 32; pend = 0; n += 32;
-                } else {
-                    const int src = d;
-                    const int d_in = __shfl_sync(kFullMask, (int)in, src);
-                    const int nr = __shfl_sync(kFullMask, type == 1u ? rr : p, src);
-                    const int nc = __shfl_sync(kFullMask, type == 2u ? cc : cc - 1, src);
-                    const int np = __shfl_sync(kFullMask, type == 1u ? 1 : (type == 2u ? 2 : 0), src);
-                    if (d_in) { r = nr; c = nc; pend = np; n += d + 1; }
-                    else { r -= d; c -= d; pend = d == 0 ? pend : 0; n += d; }   // left the window: reload around (r, c)
-                }
+                // where the walk goes on: lane d's own successor if lane d stands on a cell of the window, else (it left
+                // the window) the successor of lane d - 1, which is where lane d would stand
+                const int src = d == 32 ? 31 : d;
+                const int d_in = __shfl_sync(kFullMask, (int)in, src);
+                const int from = (d == 32 || d_in) ? src : d - 1;     // (d == 0 is always inside: the loop condition)
+                const int nr = __shfl_sync(kFullMask, type == 1u ? rr : p, from);
+                const int nc = __shfl_sync(kFullMask, type == 2u ? cc : cc - 1, from);
+                const int np = __shfl_sync(kFullMask, type == 1u ? 1 : (type == 2u ? 2 : 0), from);
+                r = nr; c = nc; pend = np;
+                n += (d == 32) ? 32 : (d_in ? d + 1 : d);
             }
             if (lane == 0) { s_row = r; s_col = c; s_pend = pend; s_n = n; }
         }
