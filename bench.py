@@ -819,23 +819,24 @@ def wl_msa(ctx, name, steps):
             "kernel": "poa_rows_kernel", "kernel_ms": fm, "fill_gcups": cells_rank / (fm * 1e-3) / 1e9 if fm else None, "traffic": None}
     # parity: OUR driver on the sample the reference arm is timed on (same generator, 10 kbp reads), -o md5 against
     # the reference's (the full 16 x 50 kbp comparison is tests/test_full_size_gpu.py)
+    last = dict(MSA_LAST)            # (the parity run below is another TSTA_msa job: it overwrites MSA_LAST)
     parity = None
     if ctx.rank == 0 and ctx.check_parity:
         parity = msa_parity(nreads, min(ln, 10_000), ctx.local_rank)
     return {"value": cells_total / (step_ms * 1e-3) / 1e9, "ms_per_step": step_ms, "steps": steps, "scaling": "weak",
             "e2e": {"value": cells_total / e2e_s / 1e9, "unit": "GCUPS",
-                    "h2d_bytes_per_step": export_bytes(MSA_LAST.get("export"), int(sum(len(r) for r in reads[1:]) + 30 * cells_rank / ln)),   # counted by the library (reads + changed node records + the permutation per read)
+                    "h2d_bytes_per_step": export_bytes(last.get("export"), int(sum(len(r) for r in reads[1:]) + 30 * cells_rank / ln)),   # counted by the library (reads + changed node records + the permutation per read)
                     "d2h_bytes_per_step": int(12 * cells_rank / ln),                                      # lastsorce + path steps per round
                     "ms_per_step": e2e_s * 1e3,
                     "is": "driver loop per read: graph export + H2D + fill + walk + D2H path + graph fusion + re-sort "
                           "(process start-up / CUDA context creation excluded; whole-process wall in wall_s)"},
-            "gpu_launches": steps * 2 * (nreads - 1), "roofline": roof, "clocks": clocks,
+            "gpu_launches": steps * 6 * (nreads - 1), "roofline": roof, "clocks": clocks,
             "config": {"reads": nreads, "read_length": ln, "node_cells_per_gpu": int(cells_rank)},
             "impl": {"parallelism": f"replicas only: one MSA job per GPU x {ctx.world}",
                      "value_is": "CUDA-event time of the POA fill + walk kernels (TSTA_msa driver, TSTA_MSA_TIMING=1)"},
             "result": result, "parity": parity, "dtype": "int32",
-            "extra": {"kernel_ms": step_ms, "fill_ms": MSA_LAST.get("fill_ms"), "walk_ms": MSA_LAST.get("walk_ms"),
-                      "wall_s": wall_s, "driver_loop_s_per_run": ls, "process_wall_s_per_run": ws, "export": MSA_LAST.get("export")}}
+            "extra": {"kernel_ms": step_ms, "fill_ms": last.get("fill_ms"), "walk_ms": last.get("walk_ms"),
+                      "wall_s": wall_s, "driver_loop_s_per_run": ls, "process_wall_s_per_run": ws, "export": last.get("export")}}
 
 
 def msa_parity(nreads, ln_s, device):

@@ -14,8 +14,8 @@ PY
 NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/r02f_launches_bench_pair100k.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-suite > $O/ncu1.log 2>&1
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/r02f_launches_msa16x50k.csv tsta_b200/_build/TSTA_msa -i /tmp/msa_in.fa -o /tmp/o.txt > $O/ncu2.log 2>&1
-$NCU --set full --import-source on -k regex:poa_rows -s 12 -c 1 -o $O/r02f_poa_rows_16x50k -f tsta_b200/_build/TSTA_msa -i /tmp/msa_in.fa -o /tmp/o.txt > $O/ncu3.log 2>&1
+$NCU --set full --import-source on -k regex:poa_rows_kernel -s 12 -c 1 -o $O/r02f_poa_rows_16x50k -f tsta_b200/_build/TSTA_msa -i /tmp/msa_in.fa -o /tmp/o.txt > $O/ncu3.log 2>&1
 $NCU --set full --import-source on -k regex:poa_walk -s 12 -c 1 -o $O/r02f_poa_walk_16x50k -f tsta_b200/_build/TSTA_msa -i /tmp/msa_in.fa -o /tmp/o.txt > $O/ncu4.log 2>&1
 $NCU --set full --import-source on -k regex:psa_pair16 -s 4 -c 1 -o $O/r02f_psa_pair16_100k -f python tools/quick_pair.py > $O/ncu5.log 2>&1
-tail -2 $O/ncu3.log $O/ncu5.log
+tail -n 2 $O/ncu3.log; tail -n 2 $O/ncu5.log
 tail -c 600 $O/r02f_bench.err
