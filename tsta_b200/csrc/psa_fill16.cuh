@@ -82,10 +82,12 @@
 // effective lag per band, profiles/r02_calibration.md).
 #pragma once
 #include "psa_fill.cuh"
+#include <type_traits>
 
 namespace tsta {
 
 constexpr int kRing16 = 128;          // row-table ring (rows)
+constexpr int kStreamRing = 32;       // streamed left boundary: rows of the shared-memory ring
 constexpr uint32_t kMin16x2 = 0x80008000u;
 constexpr int kDirSteps = 128;        // TRACE: ring of per-step direction words (steps)
 constexpr int kCkptChunks = kTileSteps / 32;          // checkpoint every 4 chunks of 32 steps
@@ -149,6 +151,45 @@ static __device__ __noinline__ bool psa_handoff_expired(int* abort_flag, unsigne
     return __any_sync(kFullMask, stop != 0);
 }
 
+// ---- streamed left boundary (score-only single pair; see TSTA_STREAM_IN below) ---------------------------------
+// rows [row0, row0 + 8) of a boundary column -> ring in shared memory (row0 a multiple of 8; the columns start on
+// 16-byte boundaries and are padded by kBndPadRows, rows >= m are copied but never used); one copy group per call
+__device__ __forceinline__ void psa_stream_issue(const unsigned long long* bnd_in, const int row0, const uint32_t sin_addr, const int lane)
+{
+    if (lane < 4) {
+        const int r = row0 + 2 * lane;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sin_addr + 8u * (uint32_t)(r & (kStreamRing - 1))), "l"(bnd_in + r) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// Cold path: the group [row0, row0 + 8) was copied before its producer had written all of it -- this band has caught
+// up with its left neighbour.  Wait until the producer is `hyst` rows past the group (or done), copy the window
+// (the group and the `ahead` groups behind it) again and check again.  Out of line: the unrolled chunk stays small.
+static __device__ __noinline__ void psa_stream_refill(const unsigned long long* bnd_in, const int row0, const int m, const unsigned epoch,
+                                                      const uint32_t sin_addr, const int lane, const int ahead, const int hyst,
+                                                      const bool watchdog, int* abort_flag, const unsigned long long timeout_ns)
+{
+    const unsigned long long* const pw = bnd_in + min(row0 + 7 + hyst, m - 1);
+    const int row = row0 + (lane & 7);
+    unsigned spins = 0;
+    unsigned long long t_wait = 0;
+    for (;;) {
+        while ((unsigned)(ld_relaxed_u64(pw) >> 32) != epoch) {
+            if (watchdog) {                                               // the producer is ANOTHER GPU: never hang on it
+                __nanosleep(20);
+                if ((++spins & 0xfffu) == 0 && psa_handoff_expired(abort_flag, timeout_ns, t_wait, lane)) return;
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");                  // (older copies must not land on top of the new ones)
+        __syncwarp();
+        for (int g = 0; g <= ahead; g++) psa_stream_issue(bnd_in, row0 + 8 * g, sin_addr, lane);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        const uint32_t tag = lds_u32(sin_addr + 8u * (uint32_t)(row & (kStreamRing - 1)) + 4u);
+        if (__all_sync(kFullMask, row >= m || tag == epoch)) return;
+    }
+}
+
 // Per-warp shared-memory workspace of the packed sweep.
 template <int C, bool RING>
 struct __align__(16) PsaWarpSmem16 {
@@ -161,6 +202,7 @@ struct __align__(16) PsaWarpSmem16 {
     uint2 rowring[kRing16 + kMaxChunkRows];
     uint32_t in[kMaxChunkRows];  // left boundary of the current chunk: lo16 = H, hi16 = Ft, relative to base
     uint2 in2[kMaxChunkRows];    // dual-pair mode: (H of pair A | pair B, F state of pair A | pair B)
+    uint2 sin[kStreamRing];      // streamed left boundary: tagged elements of rows r (slot r & 31), copied in by cp.async
 };
 
 // Dual-pair mode (short reads): the skew is 31 steps instead of 63, so with 16-row chunks a ring of
@@ -237,19 +279,20 @@ __device__ __forceinline__ void stg_cs_u2(uint32_t* p, uint32_t x, uint32_t y)
 //   dir_g     TM 2: this lane's direction word of step s = 0 in HBM ([band][step][lane])
 //   DUAL      the two halves are two independent PAIRS (short reads): no low -> high hand-off in lane 0,
 //             both halves work on row t-k, the boundary of both comes from sm.in2, m_hi = rows of pair B
-template <int C, int TM, int CK, bool DUAL = false>
+template <int C, int TM, int CK, bool DUAL = false, bool INREG = false>
 __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const int s, const int m, const int lane,
                                            const PsaConst16& k, const uint32_t selH, const uint32_t selF,
                                            const int src_lane, const uint32_t in_addr, const uint32_t ring_next,
                                            unsigned long long* bnd_row, const bool store_right,
                                            const uint32_t outHF, const unsigned epoch, const uint32_t dir_addr,
-                                           uint32_t* dir_g = nullptr, const int m_hi = 0)
+                                           uint32_t* dir_g = nullptr, const int m_hi = 0, const uint32_t in_reg = 0)
 {
     constexpr bool CHECK = CK == 1;
     const uint32_t rH = __shfl_sync(kFullMask, L.Hout, src_lane);
     const uint32_t rF = __shfl_sync(kFullMask, L.Fout, src_lane);
     uint32_t in, inF;                                             // broadcast: the band's left boundary
     if (DUAL) { const uint2 v = lds_u2(in_addr + s * 8); in = v.x; inF = v.y; }
+    else if (INREG) { in = in_reg; inF = in; }                   // streamed boundary: the caller holds the element
     else { in = lds_u32(in_addr + s * 4); inF = in; }
     const uint2 T = L.Tnext;
     L.Tnext = lds_u2(ring_next + s * 8);
@@ -487,7 +530,31 @@ __device__ __forceinline__ void psa_flush_dirs16_dual(const uint32_t* dirw, uint
 #ifndef TSTA_WATCHDOG
 #define TSTA_WATCHDOG 1
 #endif
+// Streamed left boundary (score-only single pair) -- an EXPERIMENT, off by default (profiles/r02_handoff.md).  Instead
+// of importing a whole chunk of boundary rows at the chunk start -- which makes a band wait until its left neighbour
+// has finished ALL rows of that chunk -- the rows are copied into a small shared-memory ring by cp.async in groups of
+// 8, TSTA_STREAM_AHEAD groups ahead of their use (cp.async.cg: through L2, and tracked by the copy-group counter; a
+// register ring of ordinary loads serialises on the ONE scoreboard ptxas gives them: 32 ms).  Every 8th step checks
+// the eight tags of the group that starts there (lanes 0..7, one vote); a stale group means this band has caught up
+// with its producer: it waits until the producer is TSTA_STREAM_HYST rows ahead and copies the window again (out of
+// line).  Measured on the 100 kbp pair: the start lag per band drops from 124 to 105 steps, but the check at every
+// group boundary (LDS -> ISETP -> VOTE -> BRA, ~100 cycles that nothing overlaps) makes a step 91.6 instead of 77.7
+// cycles: 7.26 ms against 6.19 ms.  The lag that is left is the skew (63 steps) plus the slow start-up chunks.
+#ifndef TSTA_STREAM_IN
+#define TSTA_STREAM_IN 0
+#endif
+#ifndef TSTA_STREAM_AHEAD
+#define TSTA_STREAM_AHEAD 1
+#endif
+#ifndef TSTA_STREAM_HYST
+#define TSTA_STREAM_HYST 12
+#endif
 constexpr int kImportGroup = TSTA_IMPORT_GROUP;
+constexpr int kStreamAhead = TSTA_STREAM_AHEAD;   // groups of 8 rows requested ahead of the group in use
+// boundary columns start on 16-byte boundaries (the streamed import copies two elements at a time)
+__host__ __device__ inline long long psa_bnd_stride(long long m) { return (m + 1) & ~1LL; }
+constexpr int kBndPadRows = 128;      // rows the streamed import may request past the last step (m + 63 + depth) of a boundary column
+static_assert(kStreamAhead >= 1 && kStreamAhead <= 2, "ring of 32 rows: the group in use, the groups ahead, and one being overwritten");
 // Per-band time stamps (tools/timeline.py): compiled in only for the experiment build (-DTSTA_TIMELINE=1).
 #ifndef TSTA_TIMELINE
 #define TSTA_TIMELINE 0
@@ -617,8 +684,15 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     uint32_t raw_next = (stager && t_begin + CH + lane < m) ? b.s1[t_begin + CH + lane] : 0xffffffffu;
     // left boundary: PIPE imports it in groups of G rows (lanes 0..G-1 hold the group that is consumed
     // next); sequential mode (batches) reads whole chunks of its own parked column
+    constexpr bool kStream = TSTA_STREAM_IN != 0 && PIPE && TM == 0;
+    const bool stream = kStream && import_left;
+    const uint32_t sin_addr = (uint32_t)__cvta_generic_to_shared(sm.sin);
+    if (stream) {
+#pragma unroll
+        for (int g = 0; g < kStreamAhead; g++) psa_stream_issue(b.bnd_in, t_begin + 8 * g, sin_addr, lane);
+    }
     unsigned long long bnd_next = 0;
-    if (import_left && (PIPE ? lane < G : stager) && t_begin + lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + t_begin + lane);
+    if (import_left && !stream && (PIPE ? lane < G : stager) && t_begin + lane < m) bnd_next = ld_relaxed_u64(b.bnd_in + t_begin + lane);
     __syncwarp();
     L.Tnext = lds_u2(ring_addr + 8u * ((t_begin - lane) & (kRing16 - 1)));      // table of this lane's row at the first step (row t_begin - lane)
 
@@ -719,7 +793,9 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             const int rownn = rown + CH;
             raw_next = (stager && rownn < m) ? b.s1[rownn] : 0u;
             const int row = stager ? t0 + lane : m;
-            if (import_left && PIPE) {
+            if (stream) {
+                // nothing to stage: the steps read the boundary from the streamed ring
+            } else if (import_left && PIPE) {
                 if (t0 < m) import_group(t0, 0, base);          // (also orders the ring stores above)
                 if (ch == 0) stamp(1);                          // the first rows of the left boundary have arrived
             } else if (import_left) {
@@ -740,51 +816,97 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
         unsigned long long* bnd_row = b.bnd_out + (t0 - 63);
         const uint32_t dir_addr = dirw_addr + (t0 & (kDirSteps - 1)) * (C == 8 ? 256 : 128);
         uint32_t* const dir_g = TM == 2 ? dir_lane + ((long long)t0 - b.dir_step0) * (C > 4 ? 64 : 32) : nullptr;
-        const bool groups = import_left && PIPE;
-
-        if (t0 + CH - 1 < m && (t0 >= 63 || fast_ramp)) {
-            // score-only: the whole chunk is unrolled (every address becomes an immediate);
-            // the traced step is several times as long, so it is unrolled just enough to overlap
-            // neighbouring steps without outgrowing the instruction cache
-            if (t0 >= 63) {
-                if constexpr (!TRACE && TSTA_SCORE_UNROLL >= CH) {
+        const bool groups = import_left && PIPE && !stream;
+        // streamed boundary: every 8th step requests the group kStreamAhead groups ahead, makes sure the group that
+        // starts here has landed and checks its eight tags (lanes 0..7, one vote); the steps read their element's
+        // value from the ring and re-centre it on this warp's base
+        const uint32_t rebase = pack16(-base, -base - shiftOE);
+        uint32_t sin_t0 = sin_addr + 8u * (uint32_t)(t0 & (kStreamRing - 1));   // (a chunk never wraps: CH divides the ring)
+        asm volatile("" : "+r"(sin_t0));                                          // keep it in a register (no S2UR rebuild per step)
+        auto stream_in = [&](const int s, const bool live) -> uint32_t {
+            if ((s & 7) == 0) {
+                psa_stream_issue(b.bnd_in, t0 + s + 8 * kStreamAhead, sin_addr, lane);
+                asm volatile("cp.async.wait_group %0;" ::"n"(kStreamAhead) : "memory");
+                __syncwarp();
+                const uint32_t tag = lds_u32(sin_t0 + 8u * (uint32_t)s + 8u * (uint32_t)(lane & 7) + 4u);
+                const bool ok = (!live && t0 + s + (lane & 7) >= m) || tag == epoch;
+                if (!__all_sync(kFullMask, ok))
+                    psa_stream_refill(b.bnd_in, t0 + s, m, epoch, sin_addr, lane, kStreamAhead, TSTA_STREAM_HYST,
+                                      TSTA_WATCHDOG && b.has_left && b.band == 0, b.abort_flag, b.timeout_ns);
+                if (kTimeline && s == 0 && ch == 0) stamp(1);               // the first rows of the left boundary have arrived
+            }
+            return vadd2(lds_u32(sin_t0 + 8u * (uint32_t)s), rebase);
+        };
+        // the steps of one chunk; ST: the left boundary comes from the streamed ring (stream_in) instead of sm.in
+        auto run_chunk = [&](auto st_tag) {
+            constexpr bool ST = decltype(st_tag)::value;
+            if (t0 + CH - 1 < m && (t0 >= 63 || fast_ramp)) {
+                // score-only: the whole chunk is unrolled (every address becomes an immediate);
+                // the traced step is several times as long, so it is unrolled just enough to overlap
+                // neighbouring steps without outgrowing the instruction cache
+                if (t0 >= 63) {
+                    if constexpr (!TRACE && TSTA_SCORE_UNROLL >= CH) {
 #pragma unroll
-                    for (int s = 0; s < CH; s++) {
-                        if (s > 0 && s % G == 0 && groups) import_group(t0 + s, s, base);
-                        psa_step16<C, TM, 0>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                             bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+                        for (int s = 0; s < CH; s++) {
+                            if (s > 0 && s % G == 0 && groups) import_group(t0 + s, s, base);
+                            uint32_t inr = 0;
+                            if constexpr (ST) inr = stream_in(s, true);
+                            psa_step16<C, TM, 0, false, ST>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                            bnd_row, store_right, outHF, epoch, dir_addr, dir_g, 0, inr);
+                        }
+                    } else {
+                        constexpr int U = G < 8 ? G : 8;
+#pragma unroll 1
+                        for (int s0 = 0; s0 < CH; s0 += U) {
+                            if (s0 > 0 && s0 % G == 0 && groups) import_group(t0 + s0, s0, base);
+#pragma unroll
+                            for (int q = 0; q < U; q++) {
+                                uint32_t inr = 0;
+                                if constexpr (ST) inr = stream_in(s0 + q, true);
+                                psa_step16<C, TM, 0, false, ST>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                                bnd_row, store_right, outHF, epoch, dir_addr, dir_g, 0, inr);
+                            }
+                        }
                     }
                 } else {
+                    // mask-free start-up chunks (t0 < 63): lanes whose first row is still to come sit on fixed-point rows
                     constexpr int U = G < 8 ? G : 8;
 #pragma unroll 1
                     for (int s0 = 0; s0 < CH; s0 += U) {
                         if (s0 > 0 && s0 % G == 0 && groups) import_group(t0 + s0, s0, base);
 #pragma unroll
-                        for (int q = 0; q < U; q++)
-                            psa_step16<C, TM, 0>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                                 bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+                        for (int q = 0; q < U; q++) {
+                            uint32_t inr = 0;
+                            if constexpr (ST) inr = stream_in(s0 + q, true);
+                            psa_step16<C, TM, 2, false, ST>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                            bnd_row, store_right, outHF, epoch, dir_addr, dir_g, 0, inr);
+                        }
+                    }
+                }
+            } else if constexpr (ST) {
+                // masked chunks, streamed: groups of 8 steps so that the ring slots stay compile-time
+#pragma unroll 1
+                for (int s0 = 0; s0 < CH; s0 += 8) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint32_t inr = stream_in(s0 + q, false);
+                        psa_step16<C, TM, 1, false, true>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                                          bnd_row, store_right, outHF, epoch, dir_addr, dir_g, 0, inr);
                     }
                 }
             } else {
-                // mask-free start-up chunks (t0 < 63): lanes whose first row is still to come sit on fixed-point rows
-                constexpr int U = G < 8 ? G : 8;
 #pragma unroll 1
-                for (int s0 = 0; s0 < CH; s0 += U) {
-                    if (s0 > 0 && s0 % G == 0 && groups) import_group(t0 + s0, s0, base);
-#pragma unroll
-                    for (int q = 0; q < U; q++)
-                        psa_step16<C, TM, 2>(L, t0 + s0 + q, s0 + q, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                             bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
+                for (int s = 0; s < CH; s++) {
+                    if (s > 0 && s % G == 0 && groups && t0 + s < m) import_group(t0 + s, s, base);
+                    psa_step16<C, TM, 1>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
+                                         bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
                 }
             }
-        } else {
-#pragma unroll 1
-            for (int s = 0; s < CH; s++) {
-                if (s > 0 && s % G == 0 && groups && t0 + s < m) import_group(t0 + s, s, base);
-                psa_step16<C, TM, 1>(L, t0 + s, s, m, lane, k, selH, selF, src_lane, in_addr, ring_next,
-                                     bnd_row, store_right, outHF, epoch, dir_addr, dir_g);
-            }
-        }
+        };
+        if constexpr (kStream) {
+            if (stream) run_chunk(std::true_type{});
+            else run_chunk(std::false_type{});
+        } else run_chunk(std::false_type{});
         __syncwarp();
         if constexpr (TM == 1) {
             // rows every virtual lane has finished: [t0 - 63, t0 + CH - 63)

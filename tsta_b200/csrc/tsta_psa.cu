@@ -312,7 +312,7 @@ static int launch_corridor_walk(tsta_psa_plan* p, int64_t i, int64_t j, int stat
     ra.sc = p->sc;
     ra.s0 = p->d_s0.as<uint8_t>(); ra.s1 = p->d_s1.as<uint8_t>();
     ra.n = (int)p->n; ra.m = (int)p->m; ra.nbands = p->nbands;
-    ra.bnd = p->d_bnd.as<unsigned long long>(); ra.bnd_stride = p->m;
+    ra.bnd = p->d_bnd.as<unsigned long long>(); ra.bnd_stride = psa_bnd_stride(p->m);
     ra.epoch = p->epoch;
     ra.ckpt = p->d_ckpt.as<uint32_t>(); ra.ckpt_band_words = psa_ckpt_band_words(p->m, p->C);
     ra.rows = p->d_tilerows.as<PsaTileRow>(); ra.nrows = K;
@@ -618,14 +618,15 @@ static int plan_upload(tsta_psa_plan* p, const tsta_params* prm, const char* s0,
         if (has_right && n % band_cols != 0)
             return set_error(TSTA_EINVAL, "a slice with a right neighbour must be a multiple of %d columns (got %lld)", band_cols, (long long)n);
         if (has_left && (size_t)m > p->inbox_rows) {
-            if (int rc = p->d_inbox.reserve((size_t)m * sizeof(unsigned long long))) return rc;
+            if (int rc = p->d_inbox.reserve(((size_t)m + kBndPadRows) * sizeof(unsigned long long))) return rc;
             TSTA_CUDA_TRY(cudaMemsetAsync(p->d_inbox.p, 0, p->d_inbox.cap, p->stream));
             p->inbox_rows = (size_t)m;
         }
     }
 
     {   // boundary columns: tagged elements, so fresh memory must start out all-zero (tag 0)
-        const size_t need = (size_t)p->nbands * (size_t)m * sizeof(unsigned long long);
+        // (+ kBndPadRows: the streamed import of psa_sweep_band16 requests a few rows past the end of a column)
+        const size_t need = ((size_t)p->nbands * (size_t)psa_bnd_stride(m) + kBndPadRows) * sizeof(unsigned long long);
         if (need > p->d_bnd.cap) {
             if (int rc = p->d_bnd.reserve(need + need / 4)) return rc;
             TSTA_CUDA_TRY(cudaMemsetAsync(p->d_bnd.p, 0, p->d_bnd.cap, p->stream));
@@ -752,7 +753,7 @@ int tsta_psa_plan_launch(tsta_psa_plan* p)
     fa.s1 = p->d_s1.as<uint8_t>();
     fa.n = (int)p->n; fa.m = (int)p->m; fa.nbands = p->nbands;
     fa.bnd = p->d_bnd.as<unsigned long long>();
-    fa.bnd_stride = p->m;
+    fa.bnd_stride = psa_bnd_stride(p->m);
     fa.epoch = p->epoch;
     fa.ticket = reinterpret_cast<unsigned*>(ctl);
     fa.dirs = p->d_dirs.as<uint8_t>();
