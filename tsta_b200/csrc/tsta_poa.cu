@@ -37,7 +37,7 @@ struct tsta_poa {
     long long stride = 0;
     bool filled = false;
     int launches = 0;
-    double t_desc = 0, t_alloc = 0, t_run = 0;   // host seconds per phase (TSTA_POA_TIMING=1 prints them)
+    double t_desc = 0, t_alloc = 0, t_run = 0, t_update = 0, t_update_first = 0, t_walk = 0;   // host seconds per phase (TSTA_POA_TIMING=1 prints them)
     long long n_fill_rows = 0, n_fill_skew = 0;   // fills by kernel
     long long n_rows = 0, n_wide = 0, n_far = 0, n_keep = 0, n_deg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -207,8 +207,8 @@ int tsta_poa_create(tsta_poa** out)
 void tsta_poa_destroy(tsta_poa* p)
 {
     if (p && getenv("TSTA_POA_TIMING"))
-        fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s; fills: %lld poa_rows_kernel, %lld poa_fill_kernel\n",
-                p->t_desc, p->t_alloc, p->t_run, p->n_fill_rows, p->n_fill_skew);
+        fprintf(stderr, "tsta_poa host phases: descriptors %.3f s, device buffers %.3f s, copies + kernel + sync %.3f s, graph updates %.3f s (the first one %.3f s; copy + kernel + sync %.3f s); fills: %lld poa_rows_kernel, %lld poa_fill_kernel\n",
+                p->t_desc, p->t_alloc, p->t_run, p->t_update, p->t_update_first, p->t_walk, p->n_fill_rows, p->n_fill_skew);
     if (p && getenv("TSTA_POA_TIMING"))
         fprintf(stderr, "tsta_poa rows %lld: in-degree>8 %lld, with a far predecessor %lld, spilled %lld; in-degree histogram 1:%lld 2:%lld 3:%lld 4:%lld 5:%lld 6:%lld 7+:%lld\n",
                 p->n_rows, p->n_wide, p->n_far, p->n_keep, p->n_deg[1], p->n_deg[2], p->n_deg[3], p->n_deg[4], p->n_deg[5], p->n_deg[6], p->n_deg[7]);
@@ -314,6 +314,7 @@ int tsta_poa_graph_update(tsta_poa* p, int nnodes, int n_narrow, const tsta_poa_
         if (wide[i].id < 0 || wide[i].id >= nnodes || ((wide[i].base_in >> 8) & 0xffu) > (unsigned)kPoaNodePreds)
             return set_error(TSTA_EINVAL, "wide node record %d: id out of range or more than eight predecessors", i);
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
+    const double t_in = poa_now();
     if (nnodes > p->node_cap) {
         const size_t used = (size_t)p->node_cap;
         if (int rc = poa_grow_keep(p->d_nmeta, (size_t)nnodes * 4, used * 4, p->stream)) return rc;
@@ -337,6 +338,7 @@ int tsta_poa_graph_update(tsta_poa* p, int nnodes, int n_narrow, const tsta_poa_
     }
     const size_t bytes = st.size() * sizeof(int);
     if (bytes == 0) return TSTA_OK;
+    const double t_staged = poa_now();
     if (int rc = poa_grow(p->d_recs, bytes)) return rc;
     PoaNodeTable t{p->d_nmeta.as<unsigned>(), p->d_npre.as<int>(), p->d_nsub.as<int>()};
     TSTA_CUDA_TRY(cudaMemcpyAsync(p->d_recs.p, st.data(), bytes, cudaMemcpyHostToDevice, p->stream));
@@ -346,6 +348,9 @@ int tsta_poa_graph_update(tsta_poa* p, int nnodes, int n_narrow, const tsta_poa_
     // (the caller's records may be reused as soon as this returns)
     TSTA_CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->h2d_bytes += (long long)bytes;
+    if (p->t_update == 0) p->t_update_first = poa_now() - t_in;
+    p->t_update += poa_now() - t_in;
+    p->t_walk += poa_now() - t_staged;      // (TSTA_POA_TIMING: copy + kernel + sync share of the updates)
     return TSTA_OK;
 }
 

@@ -6,6 +6,7 @@
 // whole pairs from a ticket and there is no inter-warp dependency.
 #include <algorithm>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -32,20 +33,23 @@ namespace {
 // Device buffers, stream and events of the calling thread, kept across calls: a caller that
 // streams batches pays for the allocations once (cudaMalloc/cudaFree of hundreds of MB cost
 // more than the kernels of a 1M x 250 bp batch).
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 16;
 struct BatchCtx {
     int device = -1;
     cudaStream_t st = nullptr;             // kernels
     cudaStream_t cp = nullptr, dh = nullptr;   // host -> device copies of the chunks ahead; device -> host of finished chunks
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEvent_t evc[kMaxChunks] = {};      // chunk c uploaded and its alphabet scanned
-    DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs, p0, p1;
+    DevBuf s0, s1, off0, off1, len0, len1, ms, corner, ctl, scratch, lastrow, ops, ops_off, alen, dirs_off, dirs, p0, p1, scan;
     int* h_present = nullptr;   // pinned, 8 words per chunk
+    void* h_scan = nullptr;     // pinned: the descriptor scan's per-block results
+    long long* h_dirs_off = nullptr;   // pinned, grown on demand: traced batches, offset of every pair's direction matrix in its slice
+    size_t h_dirs_off_cap = 0;
     std::vector<cudaEvent_t> ev;   // timing events, two per kernel slice, grown on demand
     std::vector<size_t> pair_bytes;   // traced batches: bytes of every pair's direction matrix
     void release()
     {
-        DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs, &p0, &p1};
+        DevBuf* all[] = {&s0, &s1, &off0, &off1, &len0, &len1, &ms, &corner, &ctl, &scratch, &lastrow, &ops, &ops_off, &alen, &dirs_off, &dirs, &p0, &p1, &scan};
         for (DevBuf* b : all) b->release();
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -56,7 +60,9 @@ struct BatchCtx {
         if (cp) cudaStreamDestroy(cp);
         if (dh) cudaStreamDestroy(dh);
         if (h_present) cudaFreeHost(h_present);
-        st = cp = dh = nullptr; e0 = e1 = nullptr; h_present = nullptr; device = -1;
+        if (h_scan) cudaFreeHost(h_scan);
+        if (h_dirs_off) cudaFreeHost(h_dirs_off);
+        st = cp = dh = nullptr; e0 = e1 = nullptr; h_present = nullptr; h_scan = nullptr; h_dirs_off = nullptr; h_dirs_off_cap = 0; device = -1;
     }
     ~BatchCtx() { /* process exit: the CUDA context may already be gone; leave the buffers to it */ }
 };
@@ -142,6 +148,62 @@ __global__ void __launch_bounds__(256) unpack_2bit_kernel(const uint8_t* __restr
     }
 }
 
+// Descriptor scan of a batch ON THE DEVICE: validation, the extents every chunk of the upload needs, totals.  The
+// descriptors have to be on the device anyway; reading 28 MB of them on the host cost 3.5-4.9 ms per 1M pairs even on
+// four threads (a third of the kernel time of a score-only 1M x 250 bp batch), here it is one pass at HBM speed.
+// One block of threads per scan block; chunk boundaries are scan-block boundaries (power-of-two chunk counts).
+constexpr int kScanBlocks = 64;
+struct BlockScan { int64_t lo0, hi0, lo1, hi1, max0, max1, ops_lo, ops_hi, bad; double cells; };
+__global__ void __launch_bounds__(256) batch_scan_kernel(const long long* __restrict__ off0, const int* __restrict__ len0,
+                                                         const long long* __restrict__ off1, const int* __restrict__ len1,
+                                                         const long long* __restrict__ ops_off, const int pack2,
+                                                         const long long npairs, BlockScan* __restrict__ out)
+{
+    const int b = blockIdx.x;
+    const long long k0 = npairs * b / kScanBlocks, k1 = npairs * (b + 1) / kScanBlocks;
+    long long lo0 = LLONG_MAX, hi0 = 0, lo1 = LLONG_MAX, hi1 = 0, mx0 = 0, mx1 = 0, olo = LLONG_MAX, ohi = 0, bad = LLONG_MAX;
+    double cells = 0.0;
+    for (long long k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        const long long a = len0[k], c = len1[k], o0 = off0[k], o1 = off1[k];
+        bool isbad = a < c || c < 0 || o0 < 0 || o1 < 0 || a + c > 4000000;
+        lo0 = min(lo0, o0); hi0 = max(hi0, o0 + a);
+        lo1 = min(lo1, o1); hi1 = max(hi1, o1 + c);
+        mx0 = max(mx0, a); mx1 = max(mx1, c);
+        cells += (double)a * (double)c;
+        if (ops_off) {
+            const long long oo = ops_off[k];
+            isbad = isbad || oo < 0 || (pack2 && (oo & 3));
+            olo = min(olo, oo); ohi = max(ohi, oo + a + c);
+        }
+        if (isbad) bad = min(bad, k);
+    }
+    __shared__ BlockScan part[8];
+    for (int d = 16; d > 0; d >>= 1) {
+        lo0 = min(lo0, __shfl_xor_sync(0xffffffffu, lo0, d)); hi0 = max(hi0, __shfl_xor_sync(0xffffffffu, hi0, d));
+        lo1 = min(lo1, __shfl_xor_sync(0xffffffffu, lo1, d)); hi1 = max(hi1, __shfl_xor_sync(0xffffffffu, hi1, d));
+        mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+        olo = min(olo, __shfl_xor_sync(0xffffffffu, olo, d)); ohi = max(ohi, __shfl_xor_sync(0xffffffffu, ohi, d));
+        bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, d));
+        cells += __shfl_xor_sync(0xffffffffu, cells, d);
+    }
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = BlockScan{(int64_t)lo0, (int64_t)hi0, (int64_t)lo1, (int64_t)hi1, (int64_t)mx0, (int64_t)mx1, (int64_t)olo, (int64_t)ohi, (int64_t)bad, cells};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockScan r = part[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+            const BlockScan q = part[w];
+            auto mn = [](int64_t x, int64_t y) { return x < y ? x : y; };
+            auto mx = [](int64_t x, int64_t y) { return x > y ? x : y; };
+            r.lo0 = mn(r.lo0, q.lo0); r.hi0 = mx(r.hi0, q.hi0); r.lo1 = mn(r.lo1, q.lo1); r.hi1 = mx(r.hi1, q.hi1);
+            r.max0 = mx(r.max0, q.max0); r.max1 = mx(r.max1, q.max1);
+            r.ops_lo = mn(r.ops_lo, q.ops_lo); r.ops_hi = mx(r.ops_hi, q.ops_hi); r.bad = mn(r.bad, q.bad);
+            r.cells += q.cells;
+        }
+        if (r.bad == LLONG_MAX) r.bad = -1;
+        out[b] = r;
+    }
+}
+
 static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
                           const char* seqs0, const int64_t* off0, const int32_t* len0,
                           const char* seqs1, const int64_t* off1, const int32_t* len1,
@@ -150,6 +212,13 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
                           float* kernel_ms, const bool pack2, const bool bits2)
 {
     if (kernel_ms) *kernel_ms = 0.f;
+    // TSTA_BATCH_TIMING=1: host-side phase times of this call on stderr (where the end-to-end time beyond the kernels goes)
+    const bool timing = getenv("TSTA_BATCH_TIMING") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (timing) fprintf(stderr, "[tsta_psa_batch] %8.3f ms  %s\n",
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), what);
+    };
     if (int rc = check_params(prm)) return rc;
     if (npairs < 0 || !maxsorce || !corner) return set_error(TSTA_EINVAL, "bad batch arguments");
     if (npairs == 0) return TSTA_OK;
@@ -157,42 +226,46 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     if (want_trace && (!ops || !ops_off || !alen)) return set_error(TSTA_EINVAL, "traceback requested without ops/ops_off/alen");
     if (int rc = ensure_device()) return rc;
 
-    // One pass over the pairs, in 64 blocks spread over a few host threads (a 1M-pair batch spends 15 ms in its
-    // kernels; three serial passes over 1M descriptors were 4 ms of the call): validation, the extents every chunk
-    // of the upload needs, totals.  Chunk boundaries are block boundaries (power-of-two chunk counts).
-    constexpr int kBlocks = 64;
-    struct BlockScan { int64_t lo0, hi0, lo1, hi1, max0, max1, ops_lo, ops_hi, bad; double cells; };
-    BlockScan bs[kBlocks];
-    auto scan_block = [&](int b) {
-        BlockScan r{INT64_MAX, 0, INT64_MAX, 0, 0, 0, INT64_MAX, 0, -1, 0.0};
-        const int64_t k0 = npairs * b / kBlocks, k1 = npairs * (b + 1) / kBlocks;
-        for (int64_t k = k0; k < k1; k++) {
-            const int64_t a = len0[k], c = len1[k], o0 = off0[k], o1 = off1[k];
-            bool bad = a < c || c < 0 || o0 < 0 || o1 < 0 || a + c > 4000000;
-            r.lo0 = std::min(r.lo0, o0); r.hi0 = std::max(r.hi0, o0 + a);
-            r.lo1 = std::min(r.lo1, o1); r.hi1 = std::max(r.hi1, o1 + c);
-            r.max0 = std::max(r.max0, a); r.max1 = std::max(r.max1, c);
-            r.cells += (double)a * (double)c;
-            if (want_trace) {
-                const int64_t oo = ops_off[k];
-                bad = bad || oo < 0 || (pack2 && (oo & 3));
-                r.ops_lo = std::min(r.ops_lo, oo); r.ops_hi = std::max(r.ops_hi, oo + a + c);
-            }
-            if (bad && r.bad < 0) r.bad = k;
-        }
-        bs[b] = r;
-    };
-    {
-        const int nthreads = npairs >= 200000 ? 4 : 1;
-        if (nthreads == 1) for (int b = 0; b < kBlocks; b++) scan_block(b);
-        else {
-            std::thread th[3];
-            for (int t = 1; t < nthreads; t++)
-                th[t - 1] = std::thread([&, t] { for (int b = t; b < kBlocks; b += nthreads) scan_block(b); });
-            for (int b = 0; b < kBlocks; b += nthreads) scan_block(b);
-            for (int t = 1; t < nthreads; t++) th[t - 1].join();
-        }
+    int dev = 0, sms = 0;
+    TSTA_CUDA_TRY(cudaGetDevice(&dev));
+    TSTA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (g_ctx.device != dev) {
+        if (g_ctx.device >= 0) { cudaSetDevice(g_ctx.device); g_ctx.release(); cudaSetDevice(dev); }
+        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.st, cudaStreamNonBlocking));
+        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.cp, cudaStreamNonBlocking));
+        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.dh, cudaStreamNonBlocking));
+        TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e0));
+        TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e1));
+        for (auto& e : g_ctx.evc) TSTA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        TSTA_CUDA_TRY(cudaMallocHost((void**)&g_ctx.h_present, kMaxChunks * 8 * sizeof(int)));
+        TSTA_CUDA_TRY(cudaMallocHost(&g_ctx.h_scan, kScanBlocks * sizeof(BlockScan)));
+        g_ctx.device = dev;
     }
+    Guard g(g_ctx);
+
+    // ---- the descriptors go to the device in one piece and are scanned there (batch_scan_kernel) -----------------
+    constexpr int kBlocks = kScanBlocks;
+    long long *d_off0, *d_off1, *d_ops_off = nullptr;
+    int *d_len0, *d_len1;
+    BlockScan* d_scan;
+    if (int rc = g.alloc(&d_off0, (size_t)npairs, g_ctx.off0)) return rc;
+    if (int rc = g.alloc(&d_off1, (size_t)npairs, g_ctx.off1)) return rc;
+    if (int rc = g.alloc(&d_len0, (size_t)npairs, g_ctx.len0)) return rc;
+    if (int rc = g.alloc(&d_len1, (size_t)npairs, g_ctx.len1)) return rc;
+    if (want_trace) { if (int rc = g.alloc(&d_ops_off, (size_t)npairs, g_ctx.ops_off)) return rc; }
+    if (int rc = g.alloc(&d_scan, (size_t)kScanBlocks, g_ctx.scan)) return rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_off0, off0, (size_t)npairs * 8, cudaMemcpyHostToDevice, g_ctx.cp));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0, len0, (size_t)npairs * 4, cudaMemcpyHostToDevice, g_ctx.cp));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1, off1, (size_t)npairs * 8, cudaMemcpyHostToDevice, g_ctx.cp));
+    TSTA_CUDA_TRY(cudaMemcpyAsync(d_len1, len1, (size_t)npairs * 4, cudaMemcpyHostToDevice, g_ctx.cp));
+    if (want_trace) TSTA_CUDA_TRY(cudaMemcpyAsync(d_ops_off, ops_off, (size_t)npairs * 8, cudaMemcpyHostToDevice, g_ctx.cp));
+    batch_scan_kernel<<<kScanBlocks, 256, 0, g_ctx.cp>>>(d_off0, d_len0, d_off1, d_len1, d_ops_off, pack2 ? 1 : 0, npairs, d_scan);
+    TSTA_CUDA_TRY(cudaGetLastError());
+    TSTA_CUDA_TRY(cudaMemcpyAsync(g_ctx.h_scan, d_scan, kScanBlocks * sizeof(BlockScan), cudaMemcpyDeviceToHost, g_ctx.cp));
+    TSTA_CUDA_TRY(cudaStreamSynchronize(g_ctx.cp));
+    const BlockScan* const bs = static_cast<const BlockScan*>(g_ctx.h_scan);
+    mark("descriptor scan done");
     int64_t tot0 = 0, tot1 = 0, max0 = 0, max1 = 0, ops_total = 0;
     double cells = 0.0;
     for (int b = 0; b < kBlocks; b++) {
@@ -211,25 +284,8 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     }
     const int S = want_trace ? 2 : 1;
 
-    int dev = 0, sms = 0;
-    TSTA_CUDA_TRY(cudaGetDevice(&dev));
-    TSTA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (g_ctx.device != dev) {
-        if (g_ctx.device >= 0) { cudaSetDevice(g_ctx.device); g_ctx.release(); cudaSetDevice(dev); }
-        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.st, cudaStreamNonBlocking));
-        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.cp, cudaStreamNonBlocking));
-        TSTA_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.dh, cudaStreamNonBlocking));
-        TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e0));
-        TSTA_CUDA_TRY(cudaEventCreate(&g_ctx.e1));
-        for (auto& e : g_ctx.evc) TSTA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        TSTA_CUDA_TRY(cudaMallocHost((void**)&g_ctx.h_present, kMaxChunks * 8 * sizeof(int)));
-        g_ctx.device = dev;
-    }
-    Guard g(g_ctx);
-
     uint8_t *d_s0, *d_s1;
-    long long *d_off0, *d_off1;
-    int *d_len0, *d_len1, *d_ms, *d_corner, *d_ctl;
+    int *d_ms, *d_corner, *d_ctl;
     if (int rc = g.alloc(&d_s0, (size_t)tot0, g_ctx.s0)) return rc;
     if (int rc = g.alloc(&d_s1, (size_t)tot1, g_ctx.s1)) return rc;
     uint8_t *d_p0 = nullptr, *d_p1 = nullptr;       // 2-bit wire format: the packed bytes as they arrive
@@ -237,21 +293,16 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         if (int rc = g.alloc(&d_p0, (size_t)(tot0 + 3) / 4 + 4, g_ctx.p0)) return rc;
         if (int rc = g.alloc(&d_p1, (size_t)(tot1 + 3) / 4 + 4, g_ctx.p1)) return rc;
     }
-    if (int rc = g.alloc(&d_off0, (size_t)npairs, g_ctx.off0)) return rc;
-    if (int rc = g.alloc(&d_off1, (size_t)npairs, g_ctx.off1)) return rc;
-    if (int rc = g.alloc(&d_len0, (size_t)npairs, g_ctx.len0)) return rc;
-    if (int rc = g.alloc(&d_len1, (size_t)npairs, g_ctx.len1)) return rc;
     if (int rc = g.alloc(&d_ms, (size_t)npairs, g_ctx.ms)) return rc;
     if (int rc = g.alloc(&d_corner, (size_t)npairs, g_ctx.corner)) return rc;
     if (int rc = g.alloc(&d_ctl, 16 + 8 * kMaxChunks, g_ctx.ctl)) return rc;
-    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
 
     // ---- chunks: the reads of chunk c+1 travel to the device while chunk c is computed -----------
     // (a 1M x 250 bp batch is 0.5 GB of reads against 15 ms of kernel time).  Every chunk gets its
     // own alphabet scan, so its kernels can start as soon as its bytes have arrived.
     // Worth it only when the copy is not negligible against the kernels (short reads: ~125 cells per
     // byte; 10 kbp reads: 5000) and every chunk still has many pairs per resident warp.
-    int nch = (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(1, (tot0 + tot1) / ((int64_t)48 << 20)));
+    int nch = (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(1, (tot0 + tot1) / ((int64_t)32 << 20)));
     nch = (int)std::min<int64_t>(nch, std::max<int64_t>(1, npairs / ((int64_t)sms * 24 * 16)));
     if (cells > 1000.0 * (double)(tot0 + tot1)) nch = 1;
     if (const char* e = getenv("TSTA_BATCH_CHUNKS")) nch = std::max(1, std::min(kMaxChunks, atoi(e)));
@@ -263,7 +314,6 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
     unsigned* d_present = reinterpret_cast<unsigned*>(d_ctl + 16);
     TSTA_CUDA_TRY(cudaMemsetAsync(d_present, 0, 8 * kMaxChunks * sizeof(unsigned), g_ctx.cp));
     for (int c = 0; c < nch; c++) {
-        const int64_t a0 = kb[c], a1 = kb[c + 1];
         int64_t lo0 = INT64_MAX, hi0 = 0, lo1 = INT64_MAX, hi1 = 0;
         for (int b = c * (kBlocks / nch); b < (c + 1) * (kBlocks / nch); b++) {
             lo0 = std::min(lo0, bs[b].lo0); hi0 = std::max(hi0, bs[b].hi0);
@@ -281,10 +331,6 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         if (hi0 > lo0) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s0 + lo0, seqs0 + lo0, (size_t)(hi0 - lo0), cudaMemcpyHostToDevice, cp));
         if (hi1 > lo1) TSTA_CUDA_TRY(cudaMemcpyAsync(d_s1 + lo1, seqs1 + lo1, (size_t)(hi1 - lo1), cudaMemcpyHostToDevice, cp));
         }
-        TSTA_CUDA_TRY(cudaMemcpyAsync(d_off0 + a0, off0 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
-        TSTA_CUDA_TRY(cudaMemcpyAsync(d_off1 + a0, off1 + a0, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, cp));
-        TSTA_CUDA_TRY(cudaMemcpyAsync(d_len0 + a0, len0 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));
-        TSTA_CUDA_TRY(cudaMemcpyAsync(d_len1 + a0, len1 + a0, (size_t)(a1 - a0) * 4, cudaMemcpyHostToDevice, cp));
         if (bits2) {          // the alphabet is known: A C G T
             unsigned* hp = reinterpret_cast<unsigned*>(g_ctx.h_present + 8 * c);
             for (int w = 0; w < 8; w++) hp[w] = 0;
@@ -297,6 +343,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaEventRecord(g_ctx.evc[c], cp));
     }
 
+    mark("uploads queued");
     PsaBatchArgs a{};
     a.sc.M = prm->M; a.sc.X = prm->X; a.sc.E = prm->E; a.sc.O = prm->O;
     // strip widths depend on the longest read of the whole batch; the largest band any variant uses
@@ -319,27 +366,38 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
 
     // traceback: direction matrices are large (len1 * ceil(len0/band)*band/2 bytes per pair),
     // so pairs go through in slices that fit a fixed HBM budget
-    std::vector<long long> dirs_off;
+    long long* dirs_off = nullptr;            // pinned and kept across calls (a fresh 8 MB vector per call was 2 ms of page faults)
     std::vector<size_t>& pair_bytes = g_ctx.pair_bytes;
     uint8_t* d_dirs = nullptr;
     long long* d_dirs_off = nullptr;
     uint8_t* d_ops = nullptr;
-    long long* d_ops_off = nullptr;
     int* d_alen = nullptr;
     size_t dirs_budget = 0;
+    bool budget_known = false;
     if (want_trace) {
-        size_t free_b = 0, total_b = 0;
         if (int rc = g.alloc(&d_ops, (size_t)(pack2 ? (ops_total + 3) / 4 + 4 : ops_total), g_ctx.ops)) return rc;
-        if (int rc = g.alloc(&d_ops_off, (size_t)npairs, g_ctx.ops_off)) return rc;
         if (int rc = g.alloc(&d_alen, (size_t)npairs, g_ctx.alen)) return rc;
         if (int rc = g.alloc(&d_dirs_off, (size_t)npairs, g_ctx.dirs_off)) return rc;
-        TSTA_CUDA_TRY(cudaMemcpyAsync(d_ops_off, ops_off, (size_t)npairs * 8, cudaMemcpyHostToDevice, g.st));
-        dirs_off.resize((size_t)npairs);
-        TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        // slices of direction matrices: as large as HBM allows -- a slice with fewer pairs than
-        // resident warps (3552) leaves sub-partitions idle
-        dirs_budget = (size_t)((double)(free_b + g_ctx.dirs.cap) * 0.8);
+        if ((size_t)npairs > g_ctx.h_dirs_off_cap) {
+            if (g_ctx.h_dirs_off) cudaFreeHost(g_ctx.h_dirs_off);
+            g_ctx.h_dirs_off = nullptr; g_ctx.h_dirs_off_cap = 0;
+            TSTA_CUDA_TRY(cudaMallocHost((void**)&g_ctx.h_dirs_off, (size_t)npairs * sizeof(long long)));
+            g_ctx.h_dirs_off_cap = (size_t)npairs;
+        }
+        dirs_off = g_ctx.h_dirs_off;
+        // slices of direction matrices: as large as HBM allows -- a slice with fewer pairs than resident warps (3552)
+        // leaves sub-partitions idle.  What is already allocated is a budget that needs no driver call; free memory
+        // is only asked for (cudaMemGetInfo, ~1 ms) when a chunk does not fit it.
+        dirs_budget = g_ctx.dirs.cap;
     }
+    auto full_budget = [&]() -> int {
+        if (budget_known) return TSTA_OK;
+        size_t free_b = 0, total_b = 0;
+        TSTA_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        dirs_budget = (size_t)((double)(free_b + g_ctx.dirs.cap) * 0.8);
+        budget_known = true;
+        return TSTA_OK;
+    };
 
     // No host synchronisation inside the loop: the host prepares chunk c+1 (slice layout, alphabet)
     // while the kernels of chunk c run; kernel time is summed from event pairs at the end.
@@ -354,6 +412,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         *out = g_ctx.ev[nev++];
         return cudaSuccess;
     };
+    mark("buffers ready");
     for (int c = 0; c < nch; c++) {
         // ---- this chunk's alphabet decides its kernels -------------------------------------------
         if (!bits2) TSTA_CUDA_TRY(cudaEventSynchronize(g_ctx.evc[c]));       // (its alphabet has to be read on the host)
@@ -363,6 +422,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
             if (ext[c][3] > ext[c][2]) unpack_2bit_kernel<<<sms * 8, 256, 0, g.st>>>(d_p1, d_s1, ext[c][2], ext[c][3]);
             TSTA_CUDA_TRY(cudaGetLastError());
         }
+        mark("chunk: reads on the device");
         const unsigned* present = reinterpret_cast<const unsigned*>(g_ctx.h_present + 8 * c);
         const int K = build_lut(present, a.sc.lut);
         const bool prmt = (K <= kPadCode) && abs(S * prm->M) <= 127 && abs(S * prm->X) <= 127;
@@ -402,6 +462,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
             }
             size_t total = 0;
             for (int64_t k = kb[c]; k < kend; k++) total += pair_bytes[(size_t)k];
+            if (total > dirs_budget) { if (int rc = full_budget()) return rc; }
             const size_t nslices = std::max<size_t>(1, (total + dirs_budget - 1) / std::max<size_t>(dirs_budget, 1));
             slice_target = std::min(dirs_budget, (total + nslices - 1) / nslices + ((size_t)64 << 20));
         }
@@ -422,7 +483,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
                 if (slice_bytes > g_ctx.dirs.cap) TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));   // (the old buffer may still be read)
                 if (int rc = g_ctx.dirs.reserve(std::max<size_t>(slice_bytes, 256))) return rc;
                 d_dirs = g_ctx.dirs.as<uint8_t>();
-                TSTA_CUDA_TRY(cudaMemcpyAsync(d_dirs_off + k0, dirs_off.data() + k0, (size_t)(k1 - k0) * 8,
+                TSTA_CUDA_TRY(cudaMemcpyAsync(d_dirs_off + k0, dirs_off + k0, (size_t)(k1 - k0) * 8,
                                               cudaMemcpyHostToDevice, g.st));
             }
             a.off0 = d_off0 + k0; a.off1 = d_off1 + k0; a.len0 = d_len0 + k0; a.len1 = d_len1 + k0;
@@ -469,6 +530,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
             last_done = eb;
             k0 = k1;
         }
+        mark("chunk: kernels queued");
         // ---- results of a finished chunk travel back while the next one is computed --------------
         if (want_trace && nch > 1) {
             int64_t lo = INT64_MAX, hi = 0;
@@ -487,8 +549,11 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
         TSTA_CUDA_TRY(cudaMemcpyAsync(alen, d_alen, (size_t)npairs * 4, cudaMemcpyDeviceToHost, g.st));
         if (nch == 1) TSTA_CUDA_TRY(cudaMemcpyAsync(ops, d_ops, (size_t)(pack2 ? (ops_total + 3) / 4 : ops_total), cudaMemcpyDeviceToHost, g.st));
     }
+    mark("all queued");
     TSTA_CUDA_TRY(cudaStreamSynchronize(g.st));
+    mark("kernel stream drained");
     TSTA_CUDA_TRY(cudaStreamSynchronize(g_ctx.dh));
+    mark("result copies drained");
     float total_ms = 0.f;
     for (size_t i = 0; i + 1 < nev; i += 2) {
         float ms = 0.f;
