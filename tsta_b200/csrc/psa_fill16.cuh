@@ -255,6 +255,13 @@ struct PsaConst16 {
     uint32_t E1;      // traced: 4E+1
 };
 constexpr uint32_t kM1 = 0x00010001u, kM2 = 0x00020002u, kM3 = 0x00030003u;
+// Traced BATCHES: 3 = the codes of TM 2 (14.5 ALU-pipe instructions per packed column; wf / we are read at the cell a
+// walk enters) through the step ring of TM 1; 1 = the round-1 form (17.5; cF / cE are read at the cell a walk leaves).
+#ifndef TSTA_BATCH_TM
+#define TSTA_BATCH_TM 3
+#endif
+constexpr int kBatchTM = TSTA_BATCH_TM;
+static_assert(kBatchTM == 1 || kBatchTM == 3, "trace mode of the batched kernels");
 constexpr uint32_t kFakeTab = 0x80808080u;   // substitution table of the rows above row 0: -128 for every symbol
 
 // TM (trace mode): 0 score-only, 1 traced through the shared-memory step ring (batches), 2 traced with
@@ -371,7 +378,7 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
         // the cF flag of the next lane's first column rides in bit 0 of the H hand-off
         L.Hout = f1;                                              // merged below
     } else {
-        // ---- TM 2: everything a cell's code needs is known in the cell itself -----------------
+        // ---- TM 2 / TM 3: everything a cell's code needs is known in the cell itself ------------
         uint32_t hs3[C], Ec1[C];
 #pragma unroll
         for (int c = 0; c < C; c++) {
@@ -399,7 +406,11 @@ __device__ __forceinline__ void psa_step16(PsaLane16<C>& L, const int t, const i
             L.Et[c] = CHECK ? bsel(mask, En, L.Et[c]) : En;
         }
         // (halves on rows outside [0, m) store garbage nobody reads)
-        if (C > 4) stg_cs_u2(dir_g + s * 64, prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x5410u), prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x7632u));
+        if constexpr (TM == 3) {
+            // batches: the same codes through the step ring (flushed row-major like TM 1)
+            if (C == 8) sts_u2(dir_addr + s * 256, prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x5410u), prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x7632u));
+            else sts_u32(dir_addr + s * 128, acc[0]);
+        } else if (C > 4) stg_cs_u2(dir_g + s * 64, prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x5410u), prmtu(acc[0], acc[(C + 3) / 4 - 1], 0x7632u));
         else stg_cs_u32(dir_g + s * 32, acc[0]);
     }
     uint32_t msn = L.ms;
@@ -562,13 +573,14 @@ static_assert(kStreamAhead >= 1 && kStreamAhead <= 2, "ring of 32 rows: the grou
 constexpr bool kTimeline = TSTA_TIMELINE != 0;
 template <int C, int TM, bool PIPE, int CH>
 __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScoring& sc, const uint32_t* tab4,
-                                                PsaWarpSmem16<C, TM == 1>& sm, const int lane)
+                                                PsaWarpSmem16<C, TM == 1 || TM == 3>& sm, const int lane)
 {
     constexpr bool TRACE = TM != 0;
     constexpr int S = TRACE ? 4 : 1;
     constexpr int G = kImportGroup < CH ? kImportGroup : CH;
     static_assert(CH == 16 || CH == 32, "chunk rows");
-    static_assert(TM != 1 || C == 2 || C == 4 || C == 8, "ring-traced strips pack to 8 / 16 / 32 bits per virtual lane");
+    static_assert((TM != 1 && TM != 3) || C == 2 || C == 4 || C == 8, "ring-traced strips pack to 8 / 16 / 32 bits per virtual lane");
+    static_assert(TM != 3 || !PIPE, "TM 3 is the batch form (codes of TM 2, step ring of TM 1)");
     static_assert(TM != 2 || C <= 8, "skewed direction words hold at most 8 columns per virtual lane");
     static_assert(TM != 2 || PIPE, "the skewed layout belongs to the single-pair kernel");
     const int m = b.m;
@@ -576,7 +588,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     PsaConst16 k;
     // traced: the candidates' tags are folded into the constants: Eg+1 extends by 4E-1, Fg+2 by Kf-2
     k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.E1 = dup16(Es + 1);
-    k.Kf2 = dup16(TM == 2 ? Es - 2 : max(Es, OEs) - 2);
+    k.Kf2 = dup16(TM >= 2 ? Es - 2 : max(Es, OEs) - 2);
     const int shiftOE = TRACE ? 0 : OEs;                         // score-only: gap states are carried minus (O+E)
     const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, S);
     const int jlo = (b.band * 64 + lane) * C, jhi = jlo + 32 * C;
@@ -908,7 +920,7 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             else run_chunk(std::false_type{});
         } else run_chunk(std::false_type{});
         __syncwarp();
-        if constexpr (TM == 1) {
+        if constexpr (TM == 1 || TM == 3) {
             // rows every virtual lane has finished: [t0 - 63, t0 + CH - 63)
             psa_flush_dirs16<C>(sm.dirw, b, min(m, max(0, t0 - 63)), min(m, max(0, t0 + CH - 63)), lane);
             __syncwarp();
@@ -947,7 +959,7 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
     static_assert(!TRACE || C == 4 || C == 8, "traced dual strips");
     const int Es = S * sc.E, OEs = S * (sc.O + sc.E) + (TRACE ? 2 : 0);
     PsaConst16 k;
-    k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.Kf2 = dup16(max(Es, OEs) - 2); k.E1 = dup16(Es + 1);
+    k.E2 = dup16(TRACE ? Es - 1 : Es); k.OE2 = dup16(OEs); k.Kf2 = dup16(kBatchTM >= 2 ? Es - 2 : max(Es, OEs) - 2); k.E1 = dup16(Es + 1);
     const int shiftOE = TRACE ? 0 : OEs;                         // score-only: gap states are carried minus (O+E)
     const int padlow = psa16_pad_low(sc.M, sc.X, sc.E, sc.O, S);
     const int j0 = lane * C;
@@ -1030,18 +1042,18 @@ __device__ __forceinline__ void psa_sweep_dual16(const uint8_t* s0A, const int n
             if constexpr (!TRACE) {
 #pragma unroll
                 for (int s = 0; s < CH; s++)
-                    psa_step16<C, TRACE ? 1 : 0, 0, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                    psa_step16<C, TRACE ? kBatchTM : 0, 0, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
                                                       nullptr, false, 0u, 0u, dir_addr, nullptr, mB);
             } else {
 #pragma unroll 2
                 for (int s = 0; s < CH; s++)
-                    psa_step16<C, TRACE ? 1 : 0, 0, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                    psa_step16<C, TRACE ? kBatchTM : 0, 0, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
                                                       nullptr, false, 0u, 0u, dir_addr, nullptr, mB);
             }
         } else {
 #pragma unroll 1
             for (int s = 0; s < CH; s++)
-                psa_step16<C, TRACE ? 1 : 0, 1, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
+                psa_step16<C, TRACE ? kBatchTM : 0, 1, true>(L, t0 + s, s, mA, lane, k, selHF, selHF, src_lane, in_addr, ring_next,
                                                  nullptr, false, 0u, 0u, dir_addr, nullptr, mB);
         }
         __syncwarp();
@@ -1216,7 +1228,7 @@ __global__ void __launch_bounds__(32 * WARPS) psa_batch16_kernel(const __grid_co
             for (int band = 0; band < nbands; band++) {
                 b.band = band;
                 b.lastrow = (band == nbands - 1) ? lastrow : nullptr;
-                ms = max(ms, psa_sweep_band16<C, TRACE ? 1 : 0, false, 32>(b, a.sc, tab4, sm[w], lane));
+                ms = max(ms, psa_sweep_band16<C, TRACE ? kBatchTM : 0, false, 32>(b, a.sc, tab4, sm[w], lane));
             }
         }
         ms = warp_max(ms);

@@ -526,6 +526,20 @@ static __global__ void __launch_bounds__(128) psa_batch_trace_kernel(const PsaBa
         } else ops[-nops] = (uint8_t)mv;
         nops++;
     };
+    if (a.enc == 2) {
+        // codes of psa_step16's TM 2 / TM 3: bit 2 (wf) / bit 3 (we) are read at the cell a walk ENTERS by a left / up move
+        int entered = 1;                                  // how the walk came into the current cell: 1 free, 0 by a left move, 2 by an up move
+        while (i >= 0 && j >= 0) {
+            const uint8_t byte = __ldcs(d + (long long)i * stride + (j >> 1));
+            const int c = (j & 1) ? (byte >> 4) : (byte & 15);
+            const int mv = (entered == 0 && (c & 4)) ? 0 : ((entered == 2 && (c & 8)) ? 2 : psa_back_move(c, 1));
+            put(mv);
+            if (mv == 1) { i--; j--; }
+            else if (mv == 0) j--;
+            else i--;
+            entered = mv;
+        }
+    } else
     while (i >= 0 && j >= 0) {
         const uint8_t byte = __ldcs(d + (long long)i * stride + (j >> 1));
         const int c = (j & 1) ? (byte >> 4) : (byte & 15);

@@ -505,7 +505,7 @@ static int psa_batch_impl(const tsta_params* prm, int64_t npairs,
                 } else if (C == 4) launch_batch<4, true, kBatchWarps>(prmt, blocks, g.st, a);
                 else launch_batch<8, true, kBatchWarps>(prmt, blocks, g.st, a);
                 PsaBatchTraceArgs t{};
-                t.enc = packed ? 1 : 0;
+                t.enc = packed ? (kBatchTM == 3 ? 2 : 1) : 0;      // how psa_batch_trace_kernel reads the codes
                 t.dirs = d_dirs; t.dirs_off = d_dirs_off + k0;
                 t.len0 = d_len0 + k0; t.len1 = d_len1 + k0; t.npairs = k1 - k0;
                 t.cols_per_band = band_cols;
