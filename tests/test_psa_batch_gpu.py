@@ -129,3 +129,41 @@ def test_2bit_wire_format_equals_byte_reads(gpu, chunks, monkeypatch):
                 assert (r2.maxsorce[k], r2.corner[k]) == (o.maxsorce, o.corner), k
                 if trace:
                     assert r2.output_bytes(k) == o.output_bytes(), k
+
+
+def test_bad_descriptors_are_rejected_with_the_first_bad_pair(gpu):
+    """The descriptor scan runs on the device (batch_scan_kernel): a batch with a bad pair fails with TSTA_EINVAL naming
+    the FIRST bad pair, nothing is computed; the call after it works (psa/psa.c:194-199: the caller orders the pair)."""
+    n, ln = 5000, 40
+    rng = np.random.default_rng(5)
+    s0 = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n * ln)
+    s1 = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n * ln)
+    off = np.arange(n, dtype=np.int64) * ln
+    l0 = np.full(n, ln, dtype=np.int32)
+    l1 = np.full(n, ln, dtype=np.int32)
+
+    def run(o0=off, a=l0, o1=off, c=l1, trace=False, packed=False, out=None):
+        return gpu.psa_batch_arrays(s0, o0, a, s1, o1, c, trace=trace, packed=packed, out=out)
+
+    good = run()
+    short0 = l0.copy(); short0[[4321, 777]] = ln - 1              # len0 < len1 at two pairs: the lower index is reported
+    with pytest.raises(gpu.TstaError, match="pair 777:"):
+        run(a=short0)
+    neg = off.copy(); neg[3000] = -8
+    with pytest.raises(gpu.TstaError, match="pair 3000:"):
+        run(o1=neg)
+    neg_len = l1.copy(); neg_len[12] = -1
+    with pytest.raises(gpu.TstaError, match="pair 12:"):
+        run(c=neg_len)
+    # packed moves: every slot has to start at a multiple of four moves
+    cap = 2 * ln
+    ops_off = np.arange(n, dtype=np.int64) * cap
+    bad_off = ops_off.copy(); bad_off[99] += 2
+    out = (np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n * cap // 4 + 4, np.uint8), bad_off, np.zeros(n, np.int32))
+    with pytest.raises(gpu.TstaError, match="pair 99:"):
+        run(trace=True, packed=True, out=out)
+    again = run()
+    assert np.array_equal(again.maxsorce, good.maxsorce) and np.array_equal(again.corner, good.corner)
+    k = 1234
+    o = ob.psa(s0[k * ln:(k + 1) * ln].tobytes(), s1[k * ln:(k + 1) * ln].tobytes())
+    assert (good.maxsorce[k], good.corner[k]) == (o.maxsorce, o.corner)
