@@ -72,7 +72,9 @@ int  tsta_psa_align(const tsta_params* p, const char* s0, int64_t n, const char*
                     int want_trace, tsta_psa_result* out);
 /* tsta_psa_align keeps one plan per (calling thread, trace mode) so that repeated calls reuse the
  * device buffers (a traced 100 kbp pair keeps ~7 GB of directions).  They are freed when the
- * thread exits, or right away by this call (calling thread's plans only). */
+ * thread exits, or right away by this call (calling thread's plans only).  The call also returns the
+ * buffers, streams and pinned staging memory the calling thread's tsta_psa_batch* calls keep between
+ * calls (those are otherwise left to process exit). */
 void tsta_psa_release_cache(void);
 void tsta_psa_result_free(tsta_psa_result* r);
 

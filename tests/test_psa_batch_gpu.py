@@ -167,3 +167,14 @@ def test_bad_descriptors_are_rejected_with_the_first_bad_pair(gpu):
     k = 1234
     o = ob.psa(s0[k * ln:(k + 1) * ln].tobytes(), s1[k * ln:(k + 1) * ln].tobytes())
     assert (good.maxsorce[k], good.corner[k]) == (o.maxsorce, o.corner)
+
+
+def test_release_cache_returns_the_batch_context(gpu):
+    """tsta_psa_release_cache() also frees what tsta_psa_batch keeps between calls; the next call rebuilds it."""
+    pairs = _mixed_pairs(60, 9, [30, 100, 250])
+    r0 = gpu.psa_batch(pairs, trace=True)
+    gpu.load().tsta_psa_release_cache()
+    gpu.load().tsta_psa_release_cache()          # (idempotent)
+    r1 = gpu.psa_batch(pairs, trace=True)
+    assert np.array_equal(r0.maxsorce, r1.maxsorce) and np.array_equal(r0.corner, r1.corner)
+    assert all(r0.output_bytes(k) == r1.output_bytes(k) for k in range(len(pairs)))

@@ -422,6 +422,8 @@ static int fetch_moves(tsta_psa_plan* p, uint8_t* out, int64_t nops)
     return TSTA_OK;
 }
 
+namespace tsta { void batch_release_ctx(); }   // tsta_psa_batch.cu: the calling thread's batch context
+
 extern "C" {
 
 const char* tsta_last_error(void) { return g_last_error.c_str(); }
@@ -1020,6 +1022,6 @@ int tsta_psa_align(const tsta_params* prm, const char* s0, int64_t n, const char
     return tsta_psa_plan_fetch(plan, out);
 }
 
-void tsta_psa_release_cache(void) { g_align_cache.release(); }
+void tsta_psa_release_cache(void) { g_align_cache.release(); tsta::batch_release_ctx(); }
 
 }  // extern "C"

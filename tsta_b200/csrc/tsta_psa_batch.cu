@@ -68,6 +68,23 @@ struct BatchCtx {
 };
 thread_local BatchCtx g_ctx;
 
+}  // namespace
+
+namespace tsta {
+// tsta_psa_release_cache(): the calling thread's batch buffers, streams and pinned staging go back to the driver
+void batch_release_ctx()
+{
+    if (g_ctx.device < 0) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(g_ctx.device);
+    g_ctx.release();
+    cudaSetDevice(cur);
+    std::vector<size_t>().swap(g_ctx.pair_bytes);
+}
+}  // namespace tsta
+
+namespace {
 struct Guard {   // shim over the persistent context: same call sites as a scoped allocator
     BatchCtx& c;
     cudaStream_t& st;
