@@ -316,10 +316,16 @@ int tsta_poa_graph_update(tsta_poa* p, int nnodes, int n_narrow, const tsta_poa_
     TSTA_CUDA_TRY(cudaSetDevice(p->device));
     const double t_in = poa_now();
     if (nnodes > p->node_cap) {
+        // Node ids are never reused and every read adds one provisional node per base, so the id space of a job
+        // grows by a read length per read (16 x 50 kbp: 50 k -> 850 k ids).  The tables are 40 bytes per id: reserve
+        // four times what is asked for, at least a million ids -- a job then reallocates them once or twice instead
+        // of at every 1.6 x step (cudaMalloc / cudaFree next to a multi-GB trace buffer cost up to 100 ms each on a
+        // shared GPU: the outliers of the driver loop).
         const size_t used = (size_t)p->node_cap;
-        if (int rc = poa_grow_keep(p->d_nmeta, (size_t)nnodes * 4, used * 4, p->stream)) return rc;
-        if (int rc = poa_grow_keep(p->d_npre, (size_t)nnodes * 4 * kPoaNodePreds, used * 4 * kPoaNodePreds, p->stream)) return rc;
-        if (int rc = poa_grow_keep(p->d_nsub, (size_t)nnodes * 4, 0, p->stream)) return rc;
+        const size_t want = std::max<size_t>((size_t)nnodes * 4, (size_t)1 << 20);
+        if (int rc = poa_grow_keep(p->d_nmeta, want * 4, used * 4, p->stream)) return rc;
+        if (int rc = poa_grow_keep(p->d_npre, want * 4 * kPoaNodePreds, used * 4 * kPoaNodePreds, p->stream)) return rc;
+        if (int rc = poa_grow_keep(p->d_nsub, want * 4, 0, p->stream)) return rc;
         p->node_cap = (int)std::min<size_t>(p->d_nmeta.cap / 4, std::min(p->d_npre.cap / (4 * kPoaNodePreds), p->d_nsub.cap / 4));
     }
     // transport form (poa_build.cuh): 12-byte records for in-degree <= 1, 16 bytes for 2, 40 bytes up to 8
