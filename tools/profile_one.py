@@ -10,10 +10,10 @@ trace = len(sys.argv) > 2 and sys.argv[2] == "trace"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 import os
 m = int(os.environ.get("M_ROWS", n))
-x, y = synth.read_pair(n, m, 1)
+x, y = synth.read_pair(n, m, int(os.environ.get("SEED", 1)))
 p = api.PsaPlan(trace)
 p.upload(x, y)
 for _ in range(reps):
     f, t = p.run()
 print("m=%d " % m, end="")
-print("n=%d trace=%s fill %.3f ms trace %.3f ms %.1f GCUPS" % (n, trace, f, t, n * m / f / 1e6), p.info())
+print("n=%d trace=%s fill %.3f ms trace %.3f ms %.1f GCUPS" % (n, trace, f, t, n * m / f / 1e6), p.info(), p.trace_stats() if trace else "")

@@ -240,8 +240,16 @@ static thread_local AlignCache g_align_cache;
 static long long build_corridor(const tsta_psa_plan* p, int64_t i, int64_t j, PsaTileRow* rows, int* k_low, int* width)
 {
     const int K = (int)psa_tile_rows(p->m);
-    // (every corridor after the first doubles the margin: the path has shown that it wanders further than expected)
-    const int64_t band_cols = 64 * p->C, W = p->corridor_w << std::min(p->rounds, 6);
+    // Margin of corridor number `rounds`: the second corridor keeps the margin of the first (it is centred on the
+    // point the walk got to, which is what the first one lacked), every later one doubles it (a path that has left
+    // two corridors wanders further than expected).  Measured on 200 / 300 kbp pairs that need two corridors: 4.4-7.1
+    // ms of traceback against 5.4-8.9 ms when the second corridor already doubles (profiles/r02_corridor_sweep.md).
+    // (TSTA_PSA_CORRIDOR_GROWTH=<percent>: experiments, a plain geometric growth from the second corridor on.)
+    static const int growth_pct = getenv("TSTA_PSA_CORRIDOR_GROWTH") ? std::max(100, atoi(getenv("TSTA_PSA_CORRIDOR_GROWTH"))) : 0;
+    int64_t W = p->corridor_w;
+    if (growth_pct) { for (int r = 0; r < std::min(p->rounds, 12) && W < (int64_t)1 << 30; r++) W = W * growth_pct / 100; }
+    else if (p->rounds >= 2) W <<= std::min(p->rounds - 1, 6);
+    const int64_t band_cols = 64 * p->C;
     long long slots = 0;
     bool full = false;
     *k_low = K;
