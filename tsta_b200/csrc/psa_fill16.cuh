@@ -709,28 +709,60 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
     L.Tnext = lds_u2(ring_addr + 8u * ((t_begin - lane) & (kRing16 - 1)));      // table of this lane's row at the first step (row t_begin - lane)
 
     // PIPE: make rows [row0, row0 + G) of the left boundary available in sm.in[slot0 ..] and prefetch the next group
-    auto import_group = [&](const int row0, const int slot0, const int cur_base) {
-        const int row = row0 + lane;
-        const bool mine = lane < G && row < m;
-        const long long dbg_c0 = (kTimeline && b.timeline) ? clock64() : 0;
+    // (epoch, m and the column pointer pinned in registers: as kernel parameters they are re-read from the constant
+    // bank -- LDCU, waited for -- at every import, in the middle of the chunk boundary's serial chain)
+#ifndef TSTA_IMPORT_PIN
+#define TSTA_IMPORT_PIN 1
+#endif
+    unsigned epoch_pin = epoch;
+    int m_pin = m;
+    const unsigned long long* bin_pin = b.bnd_in;
+    uint32_t in_lane = in_addr + 4u * (uint32_t)lane;
+    if (TSTA_IMPORT_PIN && PIPE) {
+        // (through shared memory: an empty asm leaves no PTX, and ptxas folds a mov -- or a shuffle of a uniform value --
+        // back into the constant-bank operand; sm.in is not in use yet)
+        const unsigned long long pb = (unsigned long long)bin_pin;
+        __syncwarp();
+        if (lane == 0) {
+            sts_u32(in_addr, epoch_pin); sts_u32(in_addr + 4, (uint32_t)m_pin);
+            sts_u32(in_addr + 8, (uint32_t)pb); sts_u32(in_addr + 12, (uint32_t)(pb >> 32));
+        }
+        __syncwarp();
+        epoch_pin = lds_u32(in_addr);
+        m_pin = (int)lds_u32(in_addr + 4);
+        bin_pin = reinterpret_cast<const unsigned long long*>(((unsigned long long)lds_u32(in_addr + 12) << 32) | lds_u32(in_addr + 8));
+        __syncwarp();
+        sts_u32(in_lane, in_lane);                     // (each lane its own slot: no S2UR + ULEA rebuild of the shared window per import)
+        __syncwarp();
+        in_lane = lds_u32(in_lane);
+        __syncwarp();
+    }
+    // the wait for rows that are not there yet (start-up, or a producer that was held up): off the straight path
+    auto import_poll = [&](const int row, const bool mine) {
         if (TSTA_WATCHDOG && b.has_left && b.band == 0) {
             // the producer is ANOTHER GPU (column slices): never hang on a neighbour that does not come
             unsigned spins = 0;
             unsigned long long t_wait = 0;
-            while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
+            while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch_pin)) {
                 __nanosleep(20);
-                if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
+                if (mine && (unsigned)(bnd_next >> 32) != epoch_pin) bnd_next = ld_relaxed_u64(bin_pin + row);
                 if ((++spins & 0xfffu) == 0 && psa_handoff_expired(b.abort_flag, b.timeout_ns, t_wait, lane)) break;
             }
         } else {
             // the producer is a band of this launch that took its ticket earlier: it runs, or has run, whatever this
             // warp does -- the wait always ends.  No watchdog here: any code inside this loop delays every band
             // behind this one (measured on the 100 kbp pair: 6.6 ms with a check every 4096 polls, 6.2 ms without)
-            while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch)) {
+            do {
                 __nanosleep(20);
-                if (mine && (unsigned)(bnd_next >> 32) != epoch) bnd_next = ld_relaxed_u64(b.bnd_in + row);
-            }
+                if (mine && (unsigned)(bnd_next >> 32) != epoch_pin) bnd_next = ld_relaxed_u64(bin_pin + row);
+            } while (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch_pin));
         }
+    };
+    auto import_group = [&](const int row0, const int slot0, const int cur_base) {
+        const int row = row0 + lane;
+        const bool mine = lane < G && row < m_pin;
+        const long long dbg_c0 = (kTimeline && b.timeline) ? clock64() : 0;
+        if (!__all_sync(kFullMask, !mine || (unsigned)(bnd_next >> 32) == epoch_pin)) import_poll(row, mine);
 #if TSTA_DEBUG_ASSERTS
         if (mine && !(b.abort_flag && *reinterpret_cast<volatile int*>(b.abort_flag))) assert((unsigned)(bnd_next >> 32) == epoch);
 #endif
@@ -742,9 +774,9 @@ __device__ __forceinline__ int psa_sweep_band16(const PsaBand& b, const PsaScori
             const uint32_t rel = vadd2(raw, dup16(-(cur_base >> 2)));
             const uint32_t opened = (((raw >> 16) - raw - (uint32_t)(sc.O + sc.E)) & 0xffffu) == 0u ? 0x00020000u : 0u;
             if (mine) sts_u32(in_addr + 4u * (slot0 + lane), ((rel & 0x3fff3fffu) << 2) + opened);
-        } else if (mine) sts_u32(in_addr + 4u * (slot0 + lane), vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE)));
+        } else if (mine) sts_u32(in_lane + 4u * slot0, vadd2((uint32_t)bnd_next, pack16(-cur_base, -cur_base - shiftOE)));
         __syncwarp();
-        if (lane < G && row + G < m) bnd_next = ld_relaxed_u64(b.bnd_in + row + G);
+        if (lane < G && row + G < m_pin) bnd_next = ld_relaxed_u64(bin_pin + row + G);
         if (kTimeline && b.timeline && lane == 0) {   // diagnostics: polls that found stale rows, cycles spent importing, imports
             b.timeline[b.band * 16 + 8] += 0;   // (stale polls are no longer counted)
             b.timeline[b.band * 16 + 9] += (unsigned long long)(clock64() - dbg_c0);
