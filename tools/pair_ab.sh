@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of the streamed left boundary on the 100 kbp pair (tools/quick_pair.py): variants = names of _build/libtsta_cuda_<v>.so
+# A/B of library builds on the 100 kbp pair (tools/quick_pair.py): arguments = names of _build/libtsta_cuda_<v>.so made with
+# tsta_b200.build.build_variant (e.g. nostream, nopin); "" = the default build.  Log: gpurun_out/stream_ab.log
 mkdir -p gpurun_out
 {
 for v in "" "$@" ""; do
