@@ -136,6 +136,16 @@ void poa_graph_init(poa_graph* g, const char* a, int nseq)
     g->nseq = nseq;
     const int len = (int)strlen(a);
     order_reserve(g, len > 0 ? len : 1);
+    {
+        /* Node ids are never reused and every read adds one provisional node per base: a job ends with about
+         * (reads + 1) x read length node records.  Reserve them now (untouched pages cost nothing) instead of
+         * doubling -- and copying up to ~50 MB -- four or five times while reads are fused. */
+        const size_t want = (size_t)(nseq > 0 ? nseq + 1 : 2) * (size_t)(len > 0 ? len : 1) + 1024;
+        if (want < ((size_t)1 << 27)) {
+            poa_node* arr = (poa_node*)malloc(want * sizeof(poa_node));
+            if (arr) { g->node = arr; g->cap = (int)want; }
+        }
+    }
     for (int i = 0; i < len; i++) {
         const int id = node_new(g, (unsigned char)a[i]);
         poa_node* n = &g->node[id];
